@@ -1,0 +1,179 @@
+"""Generate ``tests/golden/*.npz`` by running the REFERENCE's own code (build container only).
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).   Usage:  ``python -m oracle.gen_golden``
+
+What is the reference's own code in these vectors: ``MPPIDelay`` (noise injected by replacing
+``noise_dist.sample``, the one sampling call per ``command()``, ``mppi_delay.py:319``),
+``NeuralLaplaceModel`` with its GRU encoder and representation MLP, the ``dynamics`` closure shape
+of ``mppi_with_model.py:103-122``, and ``oracle.py``'s analytic delayed dynamics.  What is NOT: the
+inverse Laplace transform (``oracle.ilt`` restatement, parity unpinned) and the reward formulas
+(``oracle.costs`` restatement; the env modules need ``gym``).
+
+Weight families:
+* ``raw``        - the reference modules' own random init under ``torch.manual_seed(0)``.
+  Its rollouts explode (|delta state| ~ 1e2 per step, costs ~ 1e8): even the fp32 CPU oracle
+  differs from fp64 by O(1) after 30 steps, so raw weights are used for single model steps and
+  3-step rollouts only.
+* ``calibrated`` - the same weights with ``PHI_BIAS_SHIFT`` added to the phi half of the last MLP
+  layer's bias, which puts |F(s)| ~ 1e-2 and |delta state| ~ 0.1 per step (a trained model's
+  operating range) so that whole-horizon plans are a meaningful parity target.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import costs, mppi, ref_harness
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+PHI_BIAS_SHIFT = -4.0
+S_TERMS = 17
+DT = 0.05
+ENVS = ("oderl-pendulum", "oderl-cartpole", "oderl-acrobot")
+START_STATE = {
+    "oderl-pendulum": [-1.0, 1.2246467991473532e-16, 1.0],
+    "oderl-cartpole": [0.0, 0.0, -1.0, 1.2246467991473532e-16, 0.0],
+    "oderl-acrobot": [1.0, 0.0, 1.0, 0.0, 0.0, 0.0],
+}
+
+
+def calibrate_(sd, nx, S=S_TERMS, shift=PHI_BIAS_SHIFT):
+    sd["laplace_rep_func.linear_tanh_stack.4.bias"][nx * S:] += shift
+    return sd
+
+
+def injected_noise(K, T, nu, seed=1, sigma=1.0):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(K, T, nu, generator=g, dtype=torch.float64)
+    return z @ torch.linalg.cholesky(mppi.noise_sigma_for(nu, sigma)).T
+
+
+def _np(d):
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def reference_plan(model, env, K, T, U_init, state, action_buffer, noise, n_calls=1, dynamics=None):
+    """Run the reference ``MPPIDelay.command`` ``n_calls`` times (buffer rolled with the returned
+    action, delay 1) and return the planner's tensors after the last call."""
+    MPPIDelay, _, _ = ref_harness.load()
+    nx, nu = costs.ENV_DIMS[env]
+    act_high = np.float32(costs.ENV_ACT_HIGH[env])  # gym Box bounds are float32 (mppi_with_model.py:57-58)
+    ts_pred = torch.tensor(DT, dtype=torch.float64).view(1, 1).repeat(K, 1)
+
+    if dynamics is None:
+        def dynamics(state, window):
+            return state + model(state, window, ts_pred)
+
+    planner = MPPIDelay(dynamics, costs.running_cost(env), nx, mppi.noise_sigma_for(nu), num_samples=K,
+                        horizon=T, device="cpu", lambda_=1.0, u_min=torch.tensor(-act_high),
+                        u_max=torch.tensor(act_high), u_scale=act_high, U_init=U_init.clone())
+    out = None
+    buf = action_buffer.clone()
+    for call in range(n_calls):
+        nz = noise[call] if noise.dim() == 4 else noise
+        planner.noise_dist.sample = lambda shape, nz=nz: nz.clone()
+        action = planner.command(np.asarray(state, dtype=np.float64), buf)
+        out = {"noise": planner.noise, "perturbed_action": planner.perturbed_action,
+               "cost_total": planner.cost_total, "cost_total_non_zero": planner.cost_total_non_zero,
+               "omega": planner.omega, "states": planner.states, "actions": planner.actions,
+               "U": planner.U, "action": action}
+        buf, _ = mppi.get_action(buf, action, 1)
+    return out
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_grad_enabled(False)
+    torch.set_num_threads(4)
+    _, _, ref_oracle = ref_harness.load()
+    for env in ENVS:
+        nx, nu = costs.ENV_DIMS[env]
+        short = env.split("-")[1]
+        model = ref_harness.build_reference_model(env, seed=0, s_recon_terms=S_TERMS, dt=DT)
+        sd_raw = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"weights_{short}.npz"), **_np(sd_raw))
+
+        # --- single model steps, raw weights, reference NeuralLaplaceModel.forward -------------
+        g = torch.Generator().manual_seed(10)
+        K = 80
+        obs = torch.randn(K, nx, generator=g, dtype=torch.float64) * torch.tensor(costs.ENV_STATE_STD[env])
+        act = (torch.rand(K, 4, nu, generator=g, dtype=torch.float64) * 2 - 1) * costs.ENV_ACT_HIGH[env]
+        ts_fixed = torch.full((K, 1), DT, dtype=torch.float64)
+        ts_irreg = 0.01 + 0.39 * torch.rand(K, 1, generator=g, dtype=torch.float64)
+        enc = model.action_encoder((act - model.action_mean) / model.action_std)
+        fwd = {"obs": obs, "act": act, "ts_fixed": ts_fixed, "ts_irreg": ts_irreg,
+               "p_action": enc, "out_fixed": model(obs, act, ts_fixed), "out_irreg": model(obs, act, ts_irreg)}
+        # representation MLP alone (reference LaplaceRepresentationFunc.forward)
+        rep_in = torch.randn(K, 2 * S_TERMS + nx + 2, generator=g, dtype=torch.float64)
+        theta, phi = model.laplace_rep_func(rep_in)
+        fwd.update({"rep_in": rep_in, "rep_theta": theta, "rep_phi": phi})
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"model_fwd_{short}.npz"), **_np(fwd))
+
+        # --- raw weights, 3-step plan -----------------------------------------------------------
+        K, T = 64, 3
+        noise = injected_noise(K, T, nu, seed=3)
+        U0 = torch.zeros(T, nu, dtype=torch.float64)
+        buf = torch.zeros(4, nu, dtype=torch.float64)
+        out = reference_plan(model, env, K, T, U0, START_STATE[env], buf, noise)
+        out.update({"in_noise": noise, "in_U": U0, "in_state": np.array(START_STATE[env]), "in_buffer": buf})
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"plan_raw_{short}.npz"), **_np(out))
+
+        # --- calibrated weights -----------------------------------------------------------------
+        sd_cal = calibrate_({k: v.clone() for k, v in sd_raw.items()}, nx)
+        model.load_state_dict(sd_cal)
+
+        # ragged K, non-zero U / buffer / generic state, two consecutive control steps
+        K, T = 100, 7
+        g = torch.Generator().manual_seed(20)
+        noise = torch.stack([injected_noise(K, T, nu, seed=4), injected_noise(K, T, nu, seed=5)])
+        U0 = torch.randn(T, nu, generator=g, dtype=torch.float64) * 0.3
+        buf = (torch.rand(4, nu, generator=g, dtype=torch.float64) * 2 - 1) * costs.ENV_ACT_HIGH[env]
+        st = np.array(START_STATE[env]) + 0.05 * torch.randn(nx, generator=g, dtype=torch.float64).numpy()
+        for n_calls in (1, 2):
+            out = reference_plan(model, env, K, T, U0, st, buf, noise, n_calls=n_calls)
+            out.update({"in_noise": noise, "in_U": U0, "in_state": st, "in_buffer": buf,
+                        "phi_bias_shift": PHI_BIAS_SHIFT})
+            np.savez_compressed(os.path.join(GOLDEN_DIR, f"plan_cal_{short}_calls{n_calls}.npz"), **_np(out))
+
+        # per-sample start states (K, nx) (mppi_delay.py:243-244)
+        stK = torch.tensor(st).view(1, -1) + 0.05 * torch.randn(K, nx, generator=g, dtype=torch.float64)
+        out = reference_plan(model, env, K, T, U0, stK.numpy(), buf, noise[0])
+        out.update({"in_noise": noise[0], "in_U": U0, "in_state": stK, "in_buffer": buf,
+                    "phi_bias_shift": PHI_BIAS_SHIFT})
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"plan_cal_{short}_stateK.npz"), **_np(out))
+
+        # --- reference oracle.py dynamics in the same planner slot ----------------
+        fn = {"oderl-pendulum": ref_oracle.pendulum_dynamics_dt_delay,
+              "oderl-cartpole": ref_oracle.cartpole_dynamics_dt_delay,
+              "oderl-acrobot": ref_oracle.acrobot_dynamics_dt_delay}[env]
+        for delay in (0, 1, 3):
+            K, T = 100, 12
+            ts_pred = torch.full((K, 1), DT, dtype=torch.float64)
+            dyn = (lambda s, w, fn=fn, delay=delay, ts_pred=ts_pred: fn(s, w, ts=ts_pred, delay=delay, friction=False))
+            noise = injected_noise(K, T, nu, seed=6 + delay)
+            out = reference_plan(None, env, K, T, U0.new_zeros(T, nu), START_STATE[env], buf, noise, dynamics=dyn)
+            out.update({"in_noise": noise, "in_U": U0.new_zeros(T, nu), "in_state": np.array(START_STATE[env]),
+                        "in_buffer": buf, "delay": delay})
+            np.savez_compressed(os.path.join(GOLDEN_DIR, f"plan_oracledyn_{short}_d{delay}.npz"), **_np(out))
+
+    # --- BASELINE config 1: pendulum K=1000 H=20 (calibrated weights), trimmed outputs ----------
+    env = "oderl-pendulum"
+    nx, nu = costs.ENV_DIMS[env]
+    model = ref_harness.build_reference_model(env, seed=0, s_recon_terms=S_TERMS, dt=DT)
+    model.load_state_dict(calibrate_({k: v.clone() for k, v in model.state_dict().items()}, nx))
+    K, T = 1000, 20
+    out = reference_plan(model, env, K, T, torch.zeros(T, nu, dtype=torch.float64), START_STATE[env],
+                         torch.zeros(4, nu, dtype=torch.float64), injected_noise(K, T, nu, seed=1))
+    keep = {"cost_total": out["cost_total"], "omega": out["omega"], "U": out["U"], "action": out["action"],
+            "states_first16": out["states"][:16], "states_last": out["states"][:, -1],
+            "noise_seed": 1, "phi_bias_shift": PHI_BIAS_SHIFT}
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "plan_cfg1_pendulum_K1000_H20.npz"), **_np(keep))
+    print("golden vectors written to", GOLDEN_DIR)
+    for f in sorted(os.listdir(GOLDEN_DIR)):
+        print(f"  {f}  {os.path.getsize(os.path.join(GOLDEN_DIR, f)) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""The CPU oracle against golden vectors produced by the reference's own code
+(oracle/gen_golden.py) and, when /root/reference is present, against the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import costs, mppi, nl_model, ref_harness
+
+from _util import DT, ENVS, S_TERMS, load, relerr, short, weights
+
+torch.set_grad_enabled(False)
+TIGHT = 1e-11  # fp64 oracle vs fp64 reference: same ops, possibly different summation order
+
+
+@pytest.mark.parametrize("env", ENVS)
+def test_model_forward_matches_reference(env):
+    g = load("model_fwd_" + short(env))
+    sd = weights(env)
+    obs, act = torch.from_numpy(g["obs"]), torch.from_numpy(g["act"])
+    for key in ("fixed", "irreg"):
+        out, p_action = nl_model.nl_forward(sd, obs, act, torch.from_numpy(g["ts_" + key]), return_parts=True)
+        assert relerr(g["out_" + key], out) < TIGHT
+        assert relerr(g["p_action"], p_action) < TIGHT
+
+
+@pytest.mark.parametrize("env", ENVS)
+def test_rep_mlp_matches_reference(env):
+    g = load("model_fwd_" + short(env))
+    nx = costs.ENV_DIMS[env][0]
+    theta, phi = nl_model.laplace_rep(weights(env), torch.from_numpy(g["rep_in"]), nx, S_TERMS)
+    assert relerr(g["rep_theta"], theta) < TIGHT
+    assert relerr(g["rep_phi"], phi) < TIGHT
+
+
+def _run_oracle_plan(env, g, sd, n_calls=1):
+    nx, nu = costs.ENV_DIMS[env]
+    ah = costs.ENV_ACT_HIGH[env]
+    U = torch.from_numpy(g["in_U"]).clone()
+    buf = torch.from_numpy(g["in_buffer"]).clone()
+    noise = torch.from_numpy(g["in_noise"])
+    out = None
+    for c in range(n_calls):
+        nz = noise[c] if noise.dim() == 4 else noise
+        out = mppi.command(U, torch.from_numpy(np.asarray(g["in_state"])), buf, nz, mppi.make_nl_dynamics(sd, DT),
+                           costs.running_cost(env), noise_sigma=mppi.noise_sigma_for(nu), u_scale=ah,
+                           u_min=-ah, u_max=ah)
+        U = out["U"]
+        buf, _ = mppi.get_action(buf, out["action"], 1)
+    return out
+
+
+PLAN_KEYS = ("noise", "perturbed_action", "cost_total", "cost_total_non_zero", "omega", "states", "actions", "U",
+             "action")
+
+
+@pytest.mark.parametrize("env", ENVS)
+@pytest.mark.parametrize("case", ["raw", "cal_calls1", "cal_calls2", "cal_stateK"])
+def test_plan_matches_reference(env, case):
+    name = f"plan_raw_{short(env)}" if case == "raw" else f"plan_{case.replace('cal_', 'cal_' + short(env) + '_')}"
+    g = load(name)
+    sd = weights(env, calibrated=case != "raw")
+    out = _run_oracle_plan(env, g, sd, n_calls=2 if case.endswith("calls2") else 1)
+    for k in PLAN_KEYS:
+        assert relerr(g[k], out[k]) < (1e-9 if k in ("omega", "cost_total_non_zero", "U", "action") else TIGHT), k
+    if not case.endswith("calls2"):  # stage 1 is pure elementwise: bit exact given a bit-identical U
+        assert np.array_equal(g["perturbed_action"], out["perturbed_action"].numpy())
+        assert np.array_equal(g["noise"], out["noise"].numpy())
+
+
+def test_cfg1_pendulum_K1000_H20():
+    from oracle.gen_golden import START_STATE, injected_noise
+
+    env = "oderl-pendulum"
+    g = load("plan_cfg1_pendulum_K1000_H20")
+    K, T, nu = 1000, 20, 1
+    gg = {"in_U": np.zeros((T, nu)), "in_buffer": np.zeros((4, nu)), "in_state": np.array(START_STATE[env]),
+          "in_noise": injected_noise(K, T, nu, seed=int(g["noise_seed"])).numpy()}
+    out = _run_oracle_plan(env, gg, weights(env, calibrated=True))
+    assert relerr(g["cost_total"], out["cost_total"]) < TIGHT
+    assert relerr(g["states_first16"], out["states"][:16]) < TIGHT
+    assert relerr(g["omega"], out["omega"]) < 1e-9
+    assert relerr(g["action"], out["action"]) < 1e-9
+
+
+def test_shard_combine_equals_unsharded():
+    g = torch.Generator().manual_seed(0)
+    K, T, nu = 96, 5, 2
+    cost = torch.rand(K, generator=g, dtype=torch.float64) * 30
+    noise = torch.randn(K, T, nu, generator=g, dtype=torch.float64)
+    U = torch.randn(T, nu, generator=g, dtype=torch.float64)
+    U_ref, _, _ = mppi.softmax_update(U, cost, noise, 0.7)
+    for G in (1, 2, 3, 8):
+        idx = torch.tensor_split(torch.arange(K), G)
+        U_sh, _, _ = mppi.combine_shards(U, [mppi.shard_triple(cost[i], noise[i], 0.7) for i in idx], 0.7)
+        assert relerr(U_ref, U_sh) < 1e-13
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present")
+@pytest.mark.parametrize("env", ENVS)
+def test_live_reference_plan(env):
+    """Fresh inputs (not the committed ones) through the live reference planner + model."""
+    from oracle.gen_golden import START_STATE, calibrate_, injected_noise, reference_plan
+
+    nx, nu = costs.ENV_DIMS[env]
+    model = ref_harness.build_reference_model(env, seed=3)
+    sd = calibrate_({k: v.clone() for k, v in model.state_dict().items()}, nx)
+    model.load_state_dict(sd)
+    K, T = 37, 5
+    noise = injected_noise(K, T, nu, seed=99)
+    U0 = torch.full((T, nu), 0.1, dtype=torch.float64)
+    buf = torch.full((4, nu), -0.4, dtype=torch.float64)
+    ref = reference_plan(model, env, K, T, U0, START_STATE[env], buf, noise)
+    g = {"in_U": U0.numpy(), "in_buffer": buf.numpy(), "in_state": np.array(START_STATE[env]), "in_noise": noise.numpy()}
+    out = _run_oracle_plan(env, g, sd)
+    for k in PLAN_KEYS:
+        assert relerr(ref[k], out[k]) < 1e-9, k
