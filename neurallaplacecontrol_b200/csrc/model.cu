@@ -1,0 +1,241 @@
+// Model handle: packs a reference NeuralLaplaceModel state_dict (w_nl.py:66-145) into the device
+// layouts the kernels read, and folds the constants of a fixed prediction time in fp64.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_pack.cuh"
+
+namespace nlc {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int check_device_arch(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device visible: this library has no CPU path");
+    return NLC_ERR_ARCH;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (%d visible)", device, n);
+    return NLC_ERR_ARCH;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaGetDeviceProperties(%d) failed", device);
+    return NLC_ERR_ARCH;
+  }
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    return NLC_ERR_ARCH;
+  }
+  return NLC_OK;
+}
+
+}  // namespace nlc
+
+using namespace nlc;
+
+extern "C" const char* nlc_last_error(void) { return g_err; }
+extern "C" int nlc_version(void) { return NLC_VERSION; }
+extern "C" int nlc_device_check(int device) { return check_device_arch(device); }
+extern "C" uint64_t nlc_launch_count(void) { return g_launches.load(); }
+
+namespace {
+
+struct Arena {  // host-side staging of one contiguous device allocation
+  std::vector<float> data;
+  size_t add(size_t n) {
+    size_t off = (data.size() + 63) / 64 * 64;  // 256-byte aligned sections
+    data.resize(off + n, 0.0f);
+    return off;
+  }
+};
+
+const double kAlpha = 1.0e-3, kTol = 1.0e-2, kScale = 2.0, kEps = 1.0e-6;  // torchlaplace Fourier defaults
+
+}  // namespace
+
+// Fold everything that depends on the (normalised) prediction time.  oracle/ilt.py:fourier_s_points,
+// complex_to_sphere, fourier_line_integrate are the CPU statement of the same arithmetic.
+static int fold_prediction_time(nlc_model_s* m, double ts_pred) {
+  const int S = m->S, Hm = m->Hm, L = m->nx + 2, in0 = 2 * S + L;
+  double t = ts_pred;
+  if (m->normalize && m->normalize_time) t = ts_pred / (m->dt * 8.0);  // w_nl.py:123
+  NLC_REQUIRE(t > 0.0, NLC_ERR_ARG, "prediction time must be positive (got %g)", ts_pred);
+  const double T = kScale * (t + kEps);
+  const double gamma = kAlpha - log(kTol) / T;
+  std::vector<double> th(S), ph(S);
+  std::vector<float> phase(S), weight(S), b1(Hm);
+  const double scale = exp(gamma * t) / T;
+  for (int k = 0; k < S; ++k) {
+    double re = gamma, im = M_PI * k / T;
+    double r2 = re * re + im * im;
+    th[k] = atan2(im, re);
+    ph[k] = asin((r2 - 1.0) / (r2 + 1.0));
+    double a = fmod(k * M_PI * t / T, 2.0 * M_PI);
+    if (a > M_PI) a -= 2.0 * M_PI;
+    phase[k] = (float)a;
+    weight[k] = (float)(scale * (k == 0 ? 0.5 : 1.0));
+  }
+  for (int n = 0; n < Hm; ++n) {
+    double acc = m->h.b0[n];
+    const double* row = m->h.w0 + (size_t)n * in0;
+    for (int k = 0; k < S; ++k) acc += row[k] * th[k];
+    for (int k = 0; k < S; ++k) acc += row[S + k] * ph[k];
+    b1[n] = (float)acc;
+  }
+  NLC_CUDA_OK(cudaSetDevice(m->device));
+  NLC_CUDA_OK(cudaMemcpy(m->d.b1_fold, b1.data(), sizeof(float) * Hm, cudaMemcpyHostToDevice));
+  NLC_CUDA_OK(cudaMemcpy(m->d.ilt_phase, phase.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
+  NLC_CUDA_OK(cudaMemcpy(m->d.ilt_weight, weight.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
+  m->ts_pred = ts_pred;
+  m->t_norm = t;
+  return NLC_OK;
+}
+
+extern "C" int nlc_model_set_prediction_time(nlc_model_t m, double ts_pred) {
+  NLC_REQUIRE(m != nullptr, NLC_ERR_ARG, "null model");
+  return fold_prediction_time(m, ts_pred);
+}
+
+extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int device) {
+  NLC_REQUIRE(out && d, NLC_ERR_ARG, "null argument");
+  *out = nullptr;
+  int rc = check_device_arch(device);
+  if (rc != NLC_OK) return rc;
+  const int nx = d->state_dim, nu = d->action_dim, Hm = d->hidden_units, S = d->s_terms;
+  const int gin = nu + (d->encode_obs_time ? 1 : 0);
+  NLC_REQUIRE(nx >= 1 && nx <= kMaxNx, NLC_ERR_SHAPE, "state_dim %d outside [1,%d]", nx, kMaxNx);
+  NLC_REQUIRE(nu >= 1 && gin <= kMaxNu, NLC_ERR_SHAPE, "GRU input width %d outside [1,%d]", gin, kMaxNu);
+  NLC_REQUIRE(Hm == 128, NLC_ERR_SHAPE, "hidden_units must be 128 (config.py:37); got %d", Hm);
+  NLC_REQUIRE(S >= 2 && S <= kMaxS, NLC_ERR_SHAPE, "s_terms %d outside [2,%d]", S, kMaxS);
+  NLC_REQUIRE(d->action_std_len == 1 || d->action_std_len == nu, NLC_ERR_SHAPE, "action_std_len must be 1 or nu");
+  const void* ptrs[] = {d->state_mean, d->state_std, d->action_mean, d->action_std, d->gru_w_ih_l0, d->gru_w_hh_l0,
+                        d->gru_b_ih_l0, d->gru_b_hh_l0, d->gru_w_ih_l1, d->gru_w_hh_l1, d->gru_b_ih_l1, d->gru_b_hh_l1,
+                        d->enc_out_w, d->enc_out_b, d->mlp_w0, d->mlp_b0, d->mlp_w2, d->mlp_b2, d->mlp_w4, d->mlp_b4};
+  for (const void* p : ptrs) NLC_REQUIRE(p != nullptr, NLC_ERR_ARG, "null weight pointer in nlc_model_desc");
+
+  const int Hg = Hm / 2, G3 = 3 * Hg, L = nx + 2, in0 = 2 * S + L, N3 = 2 * nx * S, N3p = (N3 + 3) / 4 * 4;
+  nlc_model_s* m = new nlc_model_s();
+  memset(&m->d, 0, sizeof(m->d));
+  m->device = device; m->nx = nx; m->nu = nu; m->gin = gin; m->Hm = Hm; m->Hg = Hg; m->S = S; m->N3 = N3; m->N3p = N3p;
+  m->normalize = d->normalize; m->normalize_time = d->normalize_time; m->encode_obs_time = d->encode_obs_time;
+  m->dt = d->dt; m->arena = nullptr;
+
+  Arena A;
+  auto put = [&](size_t off, size_t i, double v) { A.data[off + i] = (float)v; };
+  size_t o_w_ih0 = A.add((size_t)G3 * gin), o_b_ih0 = A.add(G3), o_b_hh0 = A.add(G3);
+  size_t o_hh0 = A.add((size_t)Hg * G3), o_ih1 = A.add((size_t)Hg * G3), o_hh1 = A.add((size_t)Hg * G3);
+  size_t o_b_ih1 = A.add(G3), o_b_hh1 = A.add(G3), o_wout = A.add(2 * Hg), o_bout = A.add(2);
+  size_t o_w1full = A.add((size_t)in0 * Hm), o_b1raw = A.add(Hm), o_w1x = A.add((size_t)L * Hm), o_b1f = A.add(Hm);
+  size_t o_w2 = A.add((size_t)Hm * Hm), o_b2 = A.add(Hm), o_w3 = A.add((size_t)Hm * N3p), o_b3 = A.add(N3p);
+  size_t o_phase = A.add(S), o_weight = A.add(S);
+  size_t o_smean = A.add(nx), o_sinv = A.add(nx), o_amean = A.add(gin), o_ainv = A.add(gin);
+  // tensor-core operand image of the three recurrent GRU matrices: fp16 hi/lo, UMMA canonical layout
+  const size_t tc_halves = (size_t)3 * 2 * G3 * Hg;
+  size_t o_tc = A.add(tc_halves / 2);
+
+  for (int i = 0; i < G3 * gin; ++i) put(o_w_ih0, i, d->gru_w_ih_l0[i]);
+  for (int i = 0; i < G3; ++i) {
+    put(o_b_ih0, i, d->gru_b_ih_l0[i]); put(o_b_hh0, i, d->gru_b_hh_l0[i]);
+    put(o_b_ih1, i, d->gru_b_ih_l1[i]); put(o_b_hh1, i, d->gru_b_hh_l1[i]);
+  }
+  for (int g = 0; g < G3; ++g)
+    for (int k = 0; k < Hg; ++k) {
+      put(o_hh0, (size_t)k * G3 + g, d->gru_w_hh_l0[(size_t)g * Hg + k]);
+      put(o_ih1, (size_t)k * G3 + g, d->gru_w_ih_l1[(size_t)g * Hg + k]);
+      put(o_hh1, (size_t)k * G3 + g, d->gru_w_hh_l1[(size_t)g * Hg + k]);
+    }
+  for (int i = 0; i < 2 * Hg; ++i) put(o_wout, i, d->enc_out_w[i]);
+  for (int i = 0; i < 2; ++i) put(o_bout, i, d->enc_out_b[i]);
+  for (int n = 0; n < Hm; ++n) {
+    for (int i = 0; i < in0; ++i) put(o_w1full, (size_t)i * Hm + n, d->mlp_w0[(size_t)n * in0 + i]);
+    for (int i = 0; i < L; ++i) put(o_w1x, (size_t)i * Hm + n, d->mlp_w0[(size_t)n * in0 + 2 * S + i]);
+    put(o_b1raw, n, d->mlp_b0[n]);
+    put(o_b2, n, d->mlp_b2[n]);
+    for (int k = 0; k < Hm; ++k) put(o_w2, (size_t)k * Hm + n, d->mlp_w2[(size_t)n * Hm + k]);
+  }
+  // third layer: pair the theta and phi columns of every (channel, term)
+  for (int c = 0; c < nx; ++c)
+    for (int k = 0; k < S; ++k)
+      for (int part = 0; part < 2; ++part) {
+        const int src = (part * nx + c) * S + k;  // w_nl.py:56-62: theta rows [0,nx), phi rows [nx,2nx)
+        const int dst = 2 * (c * S + k) + part;
+        for (int h = 0; h < Hm; ++h) put(o_w3, (size_t)h * N3p + dst, d->mlp_w4[(size_t)src * Hm + h]);
+        put(o_b3, dst, d->mlp_b4[src]);
+      }
+  for (int i = 0; i < nx; ++i) {
+    put(o_smean, i, d->normalize ? d->state_mean[i] : 0.0);
+    put(o_sinv, i, d->normalize ? 1.0 / d->state_std[i] : 1.0);
+  }
+  for (int i = 0; i < gin; ++i) {
+    // w_nl.py:121 (normalised) / :129 (actions / 3.0).  With encode_obs_time the extra channel is
+    // normalised like an action, as the reference's broadcast does.
+    double mean = 0.0, stdv = 3.0;
+    if (d->normalize) {
+      mean = d->action_mean[i < nu ? i : nu - 1];
+      stdv = d->action_std[d->action_std_len == 1 ? 0 : (i < nu ? i : nu - 1)];
+    }
+    put(o_amean, i, mean);
+    put(o_ainv, i, 1.0 / stdv);
+  }
+  {
+    uint16_t* tc = reinterpret_cast<uint16_t*>(A.data.data() + o_tc);
+    const double* mats[3] = {d->gru_w_hh_l0, d->gru_w_ih_l1, d->gru_w_hh_l1};
+    for (int w = 0; w < 3; ++w)
+      nlc::tc_pack_weight_split(mats[w], G3, Hg, tc + (size_t)w * 2 * G3 * Hg, tc + (size_t)w * 2 * G3 * Hg + (size_t)G3 * Hg);
+  }
+
+  m->h.w0 = new double[(size_t)Hm * in0];
+  m->h.b0 = new double[Hm];
+  memcpy(m->h.w0, d->mlp_w0, sizeof(double) * Hm * in0);
+  memcpy(m->h.b0, d->mlp_b0, sizeof(double) * Hm);
+
+  auto fail = [&](int code) {
+    if (m->arena) cudaFree(m->arena);
+    delete[] m->h.w0; delete[] m->h.b0; delete m;
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return fail(NLC_ERR_CUDA); }
+  m->arena_bytes = A.data.size() * sizeof(float);
+  if (cudaMalloc(&m->arena, m->arena_bytes) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", m->arena_bytes); cudaGetLastError(); m->arena = nullptr; return fail(NLC_ERR_NOMEM); }
+  if (cudaMemcpy(m->arena, A.data.data(), m->arena_bytes, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("weight upload failed"); return fail(NLC_ERR_CUDA); }
+  float* base = static_cast<float*>(m->arena);
+  m->d.w_ih0 = base + o_w_ih0; m->d.b_ih0 = base + o_b_ih0; m->d.b_hh0 = base + o_b_hh0;
+  m->d.w_hh0_t = base + o_hh0; m->d.w_ih1_t = base + o_ih1; m->d.w_hh1_t = base + o_hh1;
+  m->d.b_ih1 = base + o_b_ih1; m->d.b_hh1 = base + o_b_hh1; m->d.w_out = base + o_wout; m->d.b_out = base + o_bout;
+  m->d.enc_tc_w = base + o_tc;
+  m->d.w1_full_t = base + o_w1full; m->d.b1_raw = base + o_b1raw; m->d.w1x_t = base + o_w1x; m->d.b1_fold = base + o_b1f;
+  m->d.w2_t = base + o_w2; m->d.b2 = base + o_b2; m->d.w3_t = base + o_w3; m->d.b3 = base + o_b3;
+  m->d.ilt_phase = base + o_phase; m->d.ilt_weight = base + o_weight;
+  m->d.state_mean = base + o_smean; m->d.state_inv_std = base + o_sinv; m->d.act_mean = base + o_amean; m->d.act_inv_std = base + o_ainv;
+  rc = fold_prediction_time(m, d->dt);
+  if (rc != NLC_OK) return fail(rc);
+  *out = m;
+  return NLC_OK;
+}
+
+extern "C" int nlc_model_destroy(nlc_model_t m) {
+  if (!m) return NLC_OK;
+  cudaSetDevice(m->device);
+  if (m->arena) cudaFree(m->arena);
+  delete[] m->h.w0;
+  delete[] m->h.b0;
+  delete m;
+  return NLC_OK;
+}

@@ -1,0 +1,185 @@
+// Planner handle: the device-resident state of one MPPIDelay object (planners/mppi_delay.py:64-230) and
+// the control step as a fixed sequence of kernel launches on one stream:
+//   perturb -> encode_history -> rollout_cost -> softmax (init, min, sum) -> [exchange triples] -> combine
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct nlc_planner_s {
+  int device;
+  nlc_model_t model;
+  nlc_planner_desc d;
+  uint64_t calls;
+  // device buffers (one arena)
+  void* arena;
+  size_t arena_bytes;
+  float *U, *U_rolled, *noise, *perturbed, *hist, *actions, *pert_cost, *p, *cost_total, *weights, *states;
+  float *triple, *all_triples, *action, *stats, *state_in, *abuf_in;
+  void* softmax_ws;
+  // pinned host staging for the host-buffer entry point
+  float* h_in;   // [K*nx max? no: nx + B*nu]
+  float* h_out;  // [nu]
+};
+
+using namespace nlc;
+
+extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const nlc_planner_desc* d, int device) {
+  NLC_REQUIRE(out && d, NLC_ERR_ARG, "nlc_planner_create: null argument");
+  *out = nullptr;
+  int rc = check_device_arch(device);
+  if (rc != NLC_OK) return rc;
+  const nlc_mppi_params& mp = d->mppi;
+  NLC_REQUIRE(mp.K >= 1 && mp.T >= 1 && mp.B >= 1 && mp.B <= 8, NLC_ERR_SHAPE, "planner: K, T >= 1 and 1 <= B <= 8 required");
+  NLC_REQUIRE(mp.nu >= 1 && mp.nu <= 4 && d->nx >= 1 && d->nx <= kMaxNx, NLC_ERR_SHAPE, "planner: nu/nx out of range");
+  NLC_REQUIRE(mp.T * mp.nu <= 256, NLC_ERR_SHAPE, "planner: T*nu exceeds 256");
+  NLC_REQUIRE(d->n_shards >= 1 && d->shard_index >= 0 && d->shard_index < d->n_shards, NLC_ERR_ARG, "planner: bad shard spec");
+  NLC_REQUIRE(mp.lambda_ > 0.0f, NLC_ERR_ARG, "planner: lambda must be positive");
+  if (d->rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
+    NLC_REQUIRE(model != nullptr, NLC_ERR_ARG, "planner: Neural Laplace dynamics need a model handle");
+    NLC_REQUIRE(model->device == device, NLC_ERR_ARG, "planner: model lives on device %d, planner on %d", model->device, device);
+    NLC_REQUIRE(model->nx == d->nx && model->gin == mp.nu, NLC_ERR_SHAPE, "planner: model dims do not match");
+  }
+  nlc_planner_s* p = new nlc_planner_s();
+  p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;
+  const size_t K = mp.K, T = mp.T, nu = mp.nu, B = mp.B, nx = d->nx, L = B - 1 + T, TN = T * nu;
+  std::vector<size_t> sizes = {
+      TN, TN, K * TN, K * TN, K * L * nu, K * TN, K, K * T * 2, K, K, (d->keep_states ? K * T * nx : 0),
+      2 + TN, (size_t)d->n_shards * (2 + TN), 4, 4, K * nx, B * nu, (size_t)(nlc_softmax_workspace_bytes((int)K, (int)TN) / 4 + 1)};
+  std::vector<size_t> offs;
+  size_t total = 0;
+  for (size_t s : sizes) { offs.push_back(total); total += (s + 63) / 64 * 64; }
+  p->arena_bytes = total * sizeof(float);
+  auto fail = [&](int code) {
+    if (p->arena) cudaFree(p->arena);
+    if (p->h_in) cudaFreeHost(p->h_in);
+    if (p->h_out) cudaFreeHost(p->h_out);
+    delete p;
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(NLC_ERR_CUDA); }
+  if (cudaMalloc(&p->arena, p->arena_bytes) != cudaSuccess) { cudaGetLastError(); p->arena = nullptr; set_error("planner: cudaMalloc(%zu) failed", p->arena_bytes); return fail(NLC_ERR_NOMEM); }
+  if (cudaMemset(p->arena, 0, p->arena_bytes) != cudaSuccess) { set_error("planner: memset failed"); return fail(NLC_ERR_CUDA); }
+  float* base = static_cast<float*>(p->arena);
+  float** slots[] = {&p->U, &p->U_rolled, &p->noise, &p->perturbed, &p->hist, &p->actions, &p->pert_cost, &p->p,
+                     &p->cost_total, &p->weights, &p->states, &p->triple, &p->all_triples, &p->action, &p->stats,
+                     &p->state_in, &p->abuf_in};
+  for (size_t i = 0; i < sizeof(slots) / sizeof(slots[0]); ++i) *slots[i] = base + offs[i];
+  if (!d->keep_states) p->states = nullptr;
+  p->softmax_ws = base + offs[17];
+  if (cudaMallocHost(&p->h_in, sizeof(float) * (nx + B * nu)) != cudaSuccess || cudaMallocHost(&p->h_out, sizeof(float) * 4) != cudaSuccess) {
+    cudaGetLastError(); set_error("planner: pinned allocation failed"); return fail(NLC_ERR_NOMEM);
+  }
+  *out = p;
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_destroy(nlc_planner_t p) {
+  if (!p) return NLC_OK;
+  cudaSetDevice(p->device);
+  if (p->arena) cudaFree(p->arena);
+  if (p->h_in) cudaFreeHost(p->h_in);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  delete p;
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_set_U(nlc_planner_t p, const double* U_host) {
+  NLC_REQUIRE(p && U_host, NLC_ERR_ARG, "nlc_planner_set_U: null argument");
+  const int n = p->d.mppi.T * p->d.mppi.nu;
+  std::vector<float> tmp(n);
+  for (int i = 0; i < n; ++i) tmp[i] = (float)U_host[i];
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  NLC_CUDA_OK(cudaMemcpy(p->U, tmp.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_get_U(nlc_planner_t p, double* U_host) {
+  NLC_REQUIRE(p && U_host, NLC_ERR_ARG, "nlc_planner_get_U: null argument");
+  const int n = p->d.mppi.T * p->d.mppi.nu;
+  std::vector<float> tmp(n);
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  NLC_CUDA_OK(cudaMemcpy(tmp.data(), p->U, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) U_host[i] = tmp[i];
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_buffer(nlc_planner_t p, int which, void** dev_ptr, int64_t* n_floats) {
+  NLC_REQUIRE(p && dev_ptr && n_floats, NLC_ERR_ARG, "nlc_planner_buffer: null argument");
+  const nlc_mppi_params& mp = p->d.mppi;
+  const int64_t K = mp.K, T = mp.T, nu = mp.nu, B = mp.B, nx = p->d.nx, TN = T * nu;
+  float* ptr = nullptr; int64_t n = 0;
+  switch (which) {
+    case NLC_BUF_U: ptr = p->U; n = TN; break;
+    case NLC_BUF_NOISE: ptr = p->noise; n = K * TN; break;
+    case NLC_BUF_PERTURBED: ptr = p->perturbed; n = K * TN; break;
+    case NLC_BUF_COST_TOTAL: ptr = p->cost_total; n = K; break;
+    case NLC_BUF_WEIGHTS: ptr = p->weights; n = K; break;
+    case NLC_BUF_STATES: ptr = p->states; n = p->states ? K * T * nx : 0; break;
+    case NLC_BUF_ACTIONS: ptr = p->actions; n = K * TN; break;
+    case NLC_BUF_TRIPLE: ptr = p->triple; n = 2 + TN; break;
+    case NLC_BUF_ALL_TRIPLES: ptr = p->all_triples; n = (int64_t)p->d.n_shards * (2 + TN); break;
+    case NLC_BUF_ACTION: ptr = p->action; n = nu; break;
+    case NLC_BUF_STATS: ptr = p->stats; n = 2; break;
+    case NLC_BUF_HIST: ptr = p->hist; n = K * (B - 1 + T) * nu; break;
+    case NLC_BUF_P: ptr = p->p; n = K * T * 2; break;
+    case NLC_BUF_STATE: ptr = p->state_in; n = K * nx; break;
+    case NLC_BUF_ACTION_BUFFER: ptr = p->abuf_in; n = B * nu; break;
+    default: set_error("nlc_planner_buffer: unknown buffer id %d", which); return NLC_ERR_ARG;
+  }
+  *dev_ptr = ptr; *n_floats = n;
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int state_per_sample,
+                                   const float* action_buffer_dev, const float* noise_in_dev, void* stream) {
+  NLC_REQUIRE(p && state_dev && action_buffer_dev, NLC_ERR_ARG, "nlc_planner_rollout: null argument");
+  const nlc_mppi_params& mp = p->d.mppi;
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  int rc = nlc_perturb(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, p->calls, action_buffer_dev, p->perturbed,
+                       p->noise, p->hist, p->actions, p->pert_cost, stream);
+  if (rc != NLC_OK) return rc;
+  p->calls++;
+  if (p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
+    rc = nlc_encode_history(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, stream);
+    if (rc != NLC_OK) return rc;
+  }
+  rc = nlc_rollout_cost(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,
+                        mp.nu, p->cost_total, p->states, p->d.math_mode, stream);
+  if (rc != NLC_OK) return rc;
+  return nlc_softmax_partial(p->cost_total, p->noise, mp.K, mp.T, mp.nu, mp.lambda_, p->triple, p->weights, p->softmax_ws, stream);
+}
+
+extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {
+  NLC_REQUIRE(p, NLC_ERR_ARG, "nlc_planner_finish: null planner");
+  const nlc_mppi_params& mp = p->d.mppi;
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // U <- rolled U (the update is applied to the rolled sequence, mppi_delay.py:199-216)
+  NLC_CUDA_OK(cudaMemcpyAsync(p->U, p->U_rolled, sizeof(float) * mp.T * mp.nu, cudaMemcpyDeviceToDevice, s));
+  const float* triples = p->d.n_shards == 1 ? p->triple : p->all_triples;
+  return nlc_softmax_combine(triples, p->d.n_shards, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats, stream);
+}
+
+extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_host, const double* action_buffer_host,
+                                        const float* noise_in_dev, double* action_host, void* stream) {
+  NLC_REQUIRE(p && state_host && action_buffer_host && action_host, NLC_ERR_ARG, "nlc_planner_command_host: null argument");
+  NLC_REQUIRE(p->d.n_shards == 1, NLC_ERR_UNSUPPORTED, "nlc_planner_command_host is the single-shard entry point");
+  const nlc_mppi_params& mp = p->d.mppi;
+  const int nx = p->d.nx, nb = mp.B * mp.nu;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  for (int i = 0; i < nx; ++i) p->h_in[i] = (float)state_host[i];
+  for (int i = 0; i < nb; ++i) p->h_in[nx + i] = (float)action_buffer_host[i];
+  NLC_CUDA_OK(cudaMemcpyAsync(p->state_in, p->h_in, sizeof(float) * nx, cudaMemcpyHostToDevice, s));
+  NLC_CUDA_OK(cudaMemcpyAsync(p->abuf_in, p->h_in + nx, sizeof(float) * nb, cudaMemcpyHostToDevice, s));
+  int rc = nlc_planner_rollout(p, p->state_in, 0, p->abuf_in, noise_in_dev, stream);
+  if (rc != NLC_OK) return rc;
+  rc = nlc_planner_finish(p, stream);
+  if (rc != NLC_OK) return rc;
+  NLC_CUDA_OK(cudaMemcpyAsync(p->h_out, p->action, sizeof(float) * mp.nu, cudaMemcpyDeviceToHost, s));
+  NLC_CUDA_OK(cudaStreamSynchronize(s));
+  for (int i = 0; i < mp.nu; ++i) action_host[i] = p->h_out[i];
+  return NLC_OK;
+}

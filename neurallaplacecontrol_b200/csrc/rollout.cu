@@ -1,0 +1,289 @@
+// Stages 2+3 of MPPIDelay.command for the Neural Laplace dynamics: the sequential rollout
+//   state <- state + ILT(rep_mlp([s-points | (state-mean)/std | p_action]))      (w_nl.py:117-145)
+//   cost  += running_cost(state, u_t)                                            (mppi_delay.py:271-296)
+// in ONE launch for the whole horizon.  The encoder outputs p_action[k][t] were produced up front by
+// nlc_encode_history (they do not depend on the state).
+//
+// fp32 CUDA-core (FFMA) form - the 1e-4 parity anchor.  One CTA owns R <= 64 samples for all T steps;
+// W2^T, the pair-permuted W3^T and all folded constants stay in shared memory, activations are
+// row-major [sample][128] so that the A operand is a warp-wide broadcast and W reads are 512 B rows.
+// Per step: L1 (fold of the 2S constant s-columns into the bias leaves an (nx+2)->128 layer), L2
+// 128->128, L3 128->2*nx*S with the sphere->complex map and the Fourier weights applied in the epilogue
+// (term = w_k * tan(phi/2+pi/4) * cos(theta + k*pi*t/T)), a deterministic fixed-order sum over k, the
+// residual state update and the env cost.
+#include "common.cuh"
+#include "env_cost.cuh"
+
+namespace nlc {
+
+constexpr int kH = 128;
+constexpr int kRT = 8;  // rows per register tile
+
+struct RollArgs {
+  ModelDev m;
+  int nx, S, N3p, nu;
+  nlc_rollout_opts o;
+  const float* state0; int state_per_sample;
+  const float* p;     // [K][T][2]
+  const float* hist;  // [K][L][nu]
+  const float* pert_cost;
+  int K, T, B, L, R;
+  float* cost_total;
+  float* states;
+  float* delta_out;  // forward-only mode (nlc_model_forward): write the model output, skip the cost
+  int termRows;  // rows of the a1/term buffer
+};
+
+__device__ __forceinline__ void tile_gemm_128(const float* __restrict__ act, const float* __restrict__ WT, int ldw,
+                                              int row0, int col0, float acc[kRT][4]) {
+#pragma unroll 2
+  for (int k4 = 0; k4 < kH / 4; ++k4) {
+    float4 a[kRT];
+#pragma unroll
+    for (int i = 0; i < kRT; ++i) a[i] = *reinterpret_cast<const float4*>(act + (row0 + i) * kH + 4 * k4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 w = *reinterpret_cast<const float4*>(WT + (4 * k4 + kk) * ldw + col0);
+#pragma unroll
+      for (int i = 0; i < kRT; ++i) {
+        const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
+        acc[i][0] = fmaf(av, w.x, acc[i][0]);
+        acc[i][1] = fmaf(av, w.y, acc[i][1]);
+        acc[i][2] = fmaf(av, w.z, acc[i][2]);
+        acc[i][3] = fmaf(av, w.w, acc[i][3]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int nx = a.nx, S = a.S, N3p = a.N3p, R = a.R, Lp = nx + 2, nP = nx * S;
+  float* w2 = smem;                       // [128][128]
+  float* w3 = w2 + kH * kH;               // [128][N3p]
+  float* a1 = w3 + kH * N3p;              // [R][128]; reused as term[R][nP] after L2 (nP may exceed 128)
+  float* a2 = a1 + R * (a.termRows);      // [R][128]
+  float* w1x = a2 + R * kH;               // [Lp][128]
+  float* b1 = w1x + Lp * kH;              // [128]
+  float* b2 = b1 + kH;                    // [128]
+  float* b3 = b2 + kH;                    // [N3p]
+  float* phase = b3 + N3p;                // [S]
+  float* weight = phase + S;              // [S]
+  float* in = weight + S;                 // [R][Lp]   normalised [obs | p_action]
+  float* st = in + R * Lp;                // [R][nx]   state, env units
+  float* smean = st + R * nx;             // [nx]
+  float* sinv = smean + nx;               // [nx]
+  const int ldt = a.termRows;             // row stride of a1 / term
+
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * R;
+
+  for (int i = tid; i < kH * kH / 4; i += 256) reinterpret_cast<float4*>(w2)[i] = __ldg(reinterpret_cast<const float4*>(a.m.w2_t) + i);
+  for (int i = tid; i < kH * N3p / 4; i += 256) reinterpret_cast<float4*>(w3)[i] = __ldg(reinterpret_cast<const float4*>(a.m.w3_t) + i);
+  for (int i = tid; i < Lp * kH; i += 256) w1x[i] = a.m.w1x_t[i];
+  for (int i = tid; i < kH; i += 256) { b1[i] = a.m.b1_fold[i]; b2[i] = a.m.b2[i]; }
+  for (int i = tid; i < N3p; i += 256) b3[i] = a.m.b3[i];
+  for (int i = tid; i < S; i += 256) { phase[i] = a.m.ilt_phase[i]; weight[i] = a.m.ilt_weight[i]; }
+  if (tid < nx) { smean[tid] = a.m.state_mean[tid]; sinv[tid] = a.m.state_inv_std[tid]; }
+  __syncthreads();
+  for (int i = tid; i < R * nx; i += 256) {
+    const int r = i / nx, c = i - r * nx;
+    const int k = min(k0 + r, a.K - 1);
+    const float v = a.state_per_sample ? a.state0[(size_t)k * nx + c] : a.state0[c];
+    st[i] = v;
+    in[r * Lp + c] = (v - smean[c]) * sinv[c];
+  }
+  for (int i = tid; i < R * 2; i += 256) {
+    const int r = i >> 1, o = i & 1;
+    const int k = min(k0 + r, a.K - 1);
+    in[r * Lp + nx + o] = a.p[((size_t)k * a.T) * 2 + o];
+  }
+  __syncthreads();
+
+  float cost_acc = 0.0f;
+  const int RG = R / kRT;
+  for (int t = 0; t < a.T; ++t) {
+    // ---- cost of the previous step's state (mppi_delay.py:288-290), by the row-owner threads ----
+    if (t > 0 && tid < R && a.cost_total) {
+      const int k = min(k0 + tid, a.K - 1);
+      cost_acc += env_running_cost(a.o, st + tid * nx, a.hist + ((size_t)k * a.L + (t - 1) + a.B - 1) * a.nu, a.nu);
+    }
+    // ---- L1: a1 = tanh(b1' + W1x . in) ----
+    for (int i = tid; i < R * kH; i += 256) {
+      const int r = i >> 7, n = i & (kH - 1);
+      float acc = b1[n];
+      for (int j = 0; j < Lp; ++j) acc = fmaf(w1x[j * kH + n], in[r * Lp + j], acc);
+      a1[r * ldt + n] = tanh_acc(acc);
+    }
+    __syncthreads();
+    // ---- L2: a2 = tanh(b2 + a1 . W2^T) ----
+    for (int it = tid; it < RG * (kH / 4); it += 256) {
+      const int rg = it >> 5, cg = it & 31;
+      float acc[kRT][4];
+#pragma unroll
+      for (int i = 0; i < kRT; ++i) { acc[i][0] = b2[4 * cg]; acc[i][1] = b2[4 * cg + 1]; acc[i][2] = b2[4 * cg + 2]; acc[i][3] = b2[4 * cg + 3]; }
+      // a1 rows have stride ldt
+      {
+        const float* act = a1;
+#pragma unroll 2
+        for (int k4 = 0; k4 < kH / 4; ++k4) {
+          float4 av4[kRT];
+#pragma unroll
+          for (int i = 0; i < kRT; ++i) av4[i] = *reinterpret_cast<const float4*>(act + (rg * kRT + i) * ldt + 4 * k4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float4 w = *reinterpret_cast<const float4*>(w2 + (4 * k4 + kk) * kH + 4 * cg);
+#pragma unroll
+            for (int i = 0; i < kRT; ++i) {
+              const float av = kk == 0 ? av4[i].x : (kk == 1 ? av4[i].y : (kk == 2 ? av4[i].z : av4[i].w));
+              acc[i][0] = fmaf(av, w.x, acc[i][0]);
+              acc[i][1] = fmaf(av, w.y, acc[i][1]);
+              acc[i][2] = fmaf(av, w.z, acc[i][2]);
+              acc[i][3] = fmaf(av, w.w, acc[i][3]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kRT; ++i)
+        *reinterpret_cast<float4*>(a2 + (rg * kRT + i) * kH + 4 * cg) =
+            make_float4(tanh_acc(acc[i][0]), tanh_acc(acc[i][1]), tanh_acc(acc[i][2]), tanh_acc(acc[i][3]));
+    }
+    __syncthreads();
+    // ---- L3 + sphere->complex + Fourier weights: term[r][c*S+k] ----
+    const int CG = N3p / 4;
+    for (int it = tid; it < RG * CG; it += 256) {
+      const int rg = it / CG, cg = it - rg * CG;
+      float acc[kRT][4];
+#pragma unroll
+      for (int i = 0; i < kRT; ++i) { acc[i][0] = b3[4 * cg]; acc[i][1] = b3[4 * cg + 1]; acc[i][2] = b3[4 * cg + 2]; acc[i][3] = b3[4 * cg + 3]; }
+      tile_gemm_128(a2, w3, N3p, rg * kRT, 4 * cg, acc);
+      const int pair0 = 2 * cg;  // pairs pair0, pair0+1 ; pair = c*S + k
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pair = pair0 + h;
+        if (pair < nP) {
+          const int kk = pair % S;
+          const float ph = phase[kk], wt = weight[kk];
+#pragma unroll
+          for (int i = 0; i < kRT; ++i) {
+            const float theta = 3.14159265358979f * tanh_acc(acc[i][2 * h]);  // w_nl.py:59
+            const float rad = sphere_radius(acc[i][2 * h + 1]);               // w_nl.py:60-62 + sphere_to_complex
+            a1[(rg * kRT + i) * ldt + pair] = wt * rad * cos_reduced(theta + ph);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- fixed-order sum over k, residual update (mppi_with_model.py:121), next step's inputs ----
+    for (int i = tid; i < R * nx; i += 256) {
+      const int r = i / nx, c = i - r * nx;
+      const float* tp = a1 + r * ldt + c * S;
+      float d = 0.0f;
+      for (int kk = 0; kk < S; ++kk) d += tp[kk];
+      const float v = st[i] + d;
+      st[i] = v;
+      in[r * Lp + c] = (v - smean[c]) * sinv[c];
+      if (a.states && k0 + r < a.K) a.states[((size_t)(k0 + r) * a.T + t) * nx + c] = v;
+      if (a.delta_out && k0 + r < a.K) a.delta_out[(size_t)(k0 + r) * nx + c] = d;
+    }
+    if (t + 1 < a.T)
+      for (int i = tid; i < R * 2; i += 256) {
+        const int r = i >> 1, o = i & 1;
+        const int k = min(k0 + r, a.K - 1);
+        in[r * Lp + nx + o] = a.p[((size_t)k * a.T + t + 1) * 2 + o];
+      }
+    __syncthreads();
+  }
+  if (a.cost_total && tid < R && k0 + tid < a.K) {
+    const int k = k0 + tid;
+    cost_acc += env_running_cost(a.o, st + tid * nx, a.hist + ((size_t)k * a.L + (a.T - 1) + a.B - 1) * a.nu, a.nu);
+    a.cost_total[k] = cost_acc + (a.pert_cost ? a.pert_cost[k] : 0.0f);
+  }
+}
+
+static size_t rollout_smem_floats(int nx, int S, int N3p, int R, int termRows) {
+  const int Lp = nx + 2;
+  return (size_t)kH * kH + (size_t)kH * N3p + (size_t)R * termRows + (size_t)R * kH + (size_t)Lp * kH + 2 * kH + N3p +
+         2 * S + (size_t)R * Lp + (size_t)R * nx + 2 * nx + 8;
+}
+
+int launch_rollout_fp32(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
+                        const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost,
+                        float* states, float* delta_out, cudaStream_t stream) {
+  RollArgs a;
+  a.delta_out = delta_out;
+  a.m = m->d; a.nx = m->nx; a.S = m->S; a.N3p = m->N3p; a.nu = nu; a.o = *o;
+  a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
+  a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.cost_total = cost; a.states = states;
+  const int nP = m->nx * m->S;
+  a.termRows = ((nP > kH ? nP : kH) + 3) / 4 * 4;
+  const size_t max_bytes = 227 * 1024;
+  int R = 64;
+  while (R > 8 && rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows) * sizeof(float) > max_bytes) R -= 8;
+  NLC_REQUIRE(rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows) * sizeof(float) <= max_bytes, NLC_ERR_SHAPE,
+              "rollout: model (nx=%d, S=%d) does not fit shared memory", m->nx, m->S);
+  // spread small K over the SMs: the horizon is sequential, so latency is set by the rows one CTA owns
+  int want = (K + 147) / 148;
+  want = (want + 7) / 8 * 8;
+  if (want < R) R = want;
+  a.R = R;
+  const size_t smem = rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows) * sizeof(float);
+  NLC_CUDA_OK(cudaFuncSetAttribute(rollout_nl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes));
+  const int grid = (K + R - 1) / R;
+  rollout_nl_kernel<<<grid, 256, smem, stream>>>(a);
+  NLC_LAUNCH_OK("rollout_nl_kernel");
+  return NLC_OK;
+}
+
+int launch_rollout_analytic(const nlc_rollout_opts* o, int nx, const float* state, int sps, const float* hist,
+                            const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
+                            cudaStream_t stream);
+
+}  // namespace nlc
+
+using namespace nlc;
+
+extern "C" int nlc_rollout_cost(nlc_model_t m, const nlc_rollout_opts* o, const float* state_dev, int state_per_sample,
+                                const float* p_dev, const float* hist_dev, const float* pert_cost_dev, int K, int T,
+                                int B, int nu, float* cost_total_dev, float* states_dev, int math_mode, void* stream) {
+  NLC_REQUIRE(o && state_dev && hist_dev && cost_total_dev, NLC_ERR_ARG, "nlc_rollout_cost: null pointer");
+  NLC_REQUIRE(K >= 1 && T >= 1 && B >= 1, NLC_ERR_ARG, "nlc_rollout_cost: K, T, B must be positive");
+  NLC_REQUIRE(o->env >= NLC_ENV_PENDULUM && o->env <= NLC_ENV_ACROBOT, NLC_ERR_ARG, "unknown env id %d", o->env);
+  const int env_nx[3] = {3, 5, 6}, env_nu[3] = {1, 1, 2};
+  NLC_REQUIRE(nu == env_nu[o->env], NLC_ERR_SHAPE, "env %d takes nu=%d actions, got %d", o->env, env_nu[o->env], nu);
+  if (o->env != NLC_ENV_CARTPOLE)
+    NLC_REQUIRE(!o->state_constraint && o->goal_x == 0.0f, NLC_ERR_UNSUPPORTED,
+                "state_constraint / change_goal exist only on the cartpole reward (ctcartpole.py:289-297)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (o->dynamics == NLC_DYN_ANALYTIC_DELAY) {
+    NLC_REQUIRE(o->delay >= 0 && o->delay < B, NLC_ERR_ARG, "delay %d outside the %d-entry window", o->delay, B);
+    return launch_rollout_analytic(o, env_nx[o->env], state_dev, state_per_sample, hist_dev, pert_cost_dev, K, T, B, nu,
+                                   cost_total_dev, states_dev, s);
+  }
+  NLC_REQUIRE(o->dynamics == NLC_DYN_NEURAL_LAPLACE, NLC_ERR_ARG, "unknown dynamics kind %d", o->dynamics);
+  NLC_REQUIRE(m && p_dev, NLC_ERR_ARG, "nlc_rollout_cost: Neural Laplace dynamics need a model and p_dev");
+  NLC_REQUIRE(m->nx == env_nx[o->env] && m->nu == nu, NLC_ERR_SHAPE, "model dims (%d,%d) do not match env %d", m->nx, m->nu, o->env);
+  NLC_REQUIRE(math_mode == NLC_MATH_FP32 || math_mode == NLC_MATH_TC_SPLIT3 || math_mode == NLC_MATH_TC_FP16, NLC_ERR_ARG,
+              "unknown math_mode %d", math_mode);
+  // The rollout's MLP runs on the FFMA path in every mode for now; math_mode selects the encoder's
+  // arithmetic (the tcgen05 rollout is tracked in DESIGN.md).
+  return launch_rollout_fp32(m, o, state_dev, state_per_sample, p_dev, hist_dev, pert_cost_dev, K, T, B, nu,
+                             cost_total_dev, states_dev, nullptr, s);
+}
+
+// NeuralLaplaceModel.forward (w_nl.py:117-145) at the folded prediction time: encoder over the one
+// window per sample, then one representation-MLP + ILT evaluation.
+extern "C" int nlc_model_forward(nlc_model_t m, const float* obs_dev, const float* act_dev, int K, int B, float* out_dev,
+                                 float* p_action_dev, int math_mode, void* stream) {
+  NLC_REQUIRE(m && obs_dev && act_dev && out_dev, NLC_ERR_ARG, "nlc_model_forward: null pointer");
+  NLC_REQUIRE(p_action_dev != nullptr, NLC_ERR_ARG, "nlc_model_forward: p_action_dev scratch [K][2] is required");
+  NLC_REQUIRE(K >= 1, NLC_ERR_ARG, "nlc_model_forward: K must be positive");
+  int rc = nlc_encode_history(m, act_dev, K, 1, B, p_action_dev, math_mode, stream);
+  if (rc != NLC_OK) return rc;
+  nlc_rollout_opts o;
+  o.env = m->nx == 3 ? NLC_ENV_PENDULUM : (m->nx == 5 ? NLC_ENV_CARTPOLE : NLC_ENV_ACROBOT);
+  o.state_constraint = 0; o.goal_x = 0.0f; o.dynamics = NLC_DYN_NEURAL_LAPLACE; o.delay = 0; o.dt = (float)m->dt;
+  return launch_rollout_fp32(m, &o, obs_dev, 1, p_action_dev, act_dev, nullptr, K, 1, B, m->gin, nullptr, nullptr, out_dev,
+                             static_cast<cudaStream_t>(stream));
+}

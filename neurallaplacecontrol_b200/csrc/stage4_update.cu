@@ -1,0 +1,176 @@
+// Stage 4 of MPPIDelay.command (planners/mppi_delay.py:210-224): the exponential-weight update as a
+// two-pass max-then-sum reduction (here: min of the cost, then the sums), split into the shard-local
+// part and a combine over G shards so that K can be sharded over GPUs with ONE small exchange of the
+// (beta, eta, W[T][nu]) triple per control step.
+//
+//   pass 1  softmax_min_kernel : beta_g = min_k c_k                         (reads 4K bytes)
+//   pass 2  softmax_sum_kernel : w_k = exp(-(c_k - beta_g)/lambda), eta_g = sum w_k,
+//                                W_g[t][u] = sum_k w_k noise[k][t][u]       (reads 4K + 4*K*T*nu bytes)
+//           per-block partials, the last block to finish adds them in block order (deterministic).
+//   combine softmax_combine_kernel : beta = min beta_g, rescale by exp(-(beta_g-beta)/lambda),
+//                                U += W/eta, action = U[0]*u_scale.
+// HBM-bound streaming kernels: rows of noise are read as contiguous T*nu-float rows, 8 rows per block pass.
+#include "common.cuh"
+
+namespace nlc {
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+struct SoftWs {           // workspace header (device)
+  unsigned min_ord;       // ordered-uint encoding of the running min
+  unsigned ticket;        // blocks finished in pass 2
+};
+
+__global__ void softmax_init_kernel(SoftWs* ws) {
+  ws->min_ord = 0xffffffffu;
+  ws->ticket = 0u;
+}
+
+__global__ void __launch_bounds__(256) softmax_min_kernel(const float* __restrict__ cost, int K, SoftWs* ws) {
+  float m = INFINITY;
+  const int n4 = K >> 2;
+  const float4* c4 = reinterpret_cast<const float4*>(cost);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 v = __ldg(c4 + i);
+    m = fminf(fminf(m, fminf(v.x, v.y)), fminf(v.z, v.w));
+  }
+  for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) m = fminf(m, cost[i]);
+  m = warp_min(m);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : INFINITY;
+    m = warp_min(m);
+    if (threadIdx.x == 0) atomicMin(&ws->min_ord, f2ord(m));
+  }
+}
+
+// block = 256 threads laid out as (ry, j): j < TNp columns (TNp = T*nu rounded up to 32), ry rows per pass.
+__global__ void __launch_bounds__(256) softmax_sum_kernel(const float* __restrict__ cost, const float* __restrict__ noise,
+                                                          int K, int TN, int TNp, float inv_lambda, SoftWs* ws,
+                                                          float* partials /*[grid][1+TN]*/, float* triple,
+                                                          float* weights, int rows_per_block) {
+  extern __shared__ float red[];  // [RY][TNp] + [RY]
+  const int RY = 256 / TNp;
+  const int j = threadIdx.x % TNp, ry = threadIdx.x / TNp;
+  const float beta = ord2f(ws->min_ord);
+  const int kb = blockIdx.x * rows_per_block;
+  const int ke = min(K, kb + rows_per_block);
+  float acc = 0.0f, eta = 0.0f;
+  if (ry < RY) {
+    for (int k = kb + ry; k < ke; k += RY) {
+      const float w = exp_acc(-inv_lambda * (__ldg(cost + k) - beta));  // _ensure_non_zero, mppi_delay.py:12-13
+      if (j < TN) acc = fmaf(w, __ldg(noise + (size_t)k * TN + j), acc);
+      if (j == 0) {
+        eta += w;
+        if (weights) weights[k] = w;
+      }
+    }
+    red[ry * TNp + j] = acc;
+    if (j == 0) red[RY * TNp + ry] = eta;
+  }
+  __syncthreads();
+  float* my = partials + (size_t)blockIdx.x * (1 + TN);
+  if (threadIdx.x < TN) {
+    float s = 0.0f;
+    for (int r = 0; r < RY; ++r) s += red[r * TNp + threadIdx.x];
+    my[1 + threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int r = 0; r < RY; ++r) s += red[RY * TNp + r];
+    my[0] = s;
+  }
+  __threadfence();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {  // fixed block order => run-to-run identical sums
+    __threadfence();
+    for (int c = threadIdx.x; c < 1 + TN; c += blockDim.x) {
+      float s = 0.0f;
+      for (unsigned b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * (1 + TN) + c];
+      triple[1 + c] = s;
+    }
+    if (threadIdx.x == 0) triple[0] = beta;
+  }
+}
+
+__global__ void softmax_combine_kernel(const float* __restrict__ triples, int G, int TN, int nu, float inv_lambda,
+                                       float u_scale, float* U, float* action, float* stats) {
+  const int stride = 2 + TN;
+  float beta = INFINITY;
+  for (int g = 0; g < G; ++g) beta = fminf(beta, triples[g * stride]);
+  float eta = 0.0f;
+  for (int g = 0; g < G; ++g) eta = fmaf(triples[g * stride + 1], exp_acc(-inv_lambda * (triples[g * stride] - beta)), eta);
+  for (int c = threadIdx.x; c < TN; c += blockDim.x) {
+    float W = 0.0f;
+    for (int g = 0; g < G; ++g) W = fmaf(triples[g * stride + 2 + c], exp_acc(-inv_lambda * (triples[g * stride] - beta)), W);
+    const float u = U[c] + W / eta;  // mppi_delay.py:214-216
+    U[c] = u;
+    if (c < nu && action) action[c] = u * u_scale;  // :217-224
+  }
+  if (threadIdx.x == 0 && stats) { stats[0] = beta; stats[1] = eta; }
+}
+
+static int sum_grid(int K) {
+  int g = (K + 255) / 256;  // >= 256 rows per block
+  if (g > 148 * 4) g = 148 * 4;
+  if (g < 1) g = 1;
+  return g;
+}
+
+}  // namespace nlc
+
+using namespace nlc;
+
+extern "C" int64_t nlc_softmax_workspace_bytes(int K, int TN) {
+  return 256 + (int64_t)sum_grid(K) * (1 + TN) * (int64_t)sizeof(float);
+}
+
+extern "C" int nlc_softmax_partial(const float* cost_dev, const float* noise_dev, int K, int T, int nu, float lambda_,
+                                   float* triple_dev, float* weights_dev, void* workspace_dev, void* stream) {
+  NLC_REQUIRE(cost_dev && noise_dev && triple_dev && workspace_dev, NLC_ERR_ARG, "nlc_softmax_partial: null pointer");
+  NLC_REQUIRE(K >= 1 && T >= 1 && nu >= 1, NLC_ERR_ARG, "nlc_softmax_partial: K, T, nu must be positive");
+  const int TN = T * nu;
+  NLC_REQUIRE(TN <= 256, NLC_ERR_SHAPE, "nlc_softmax_partial: T*nu = %d exceeds 256", TN);
+  NLC_REQUIRE(lambda_ > 0.0f, NLC_ERR_ARG, "lambda must be positive");
+  NLC_REQUIRE((reinterpret_cast<uintptr_t>(cost_dev) & 15) == 0, NLC_ERR_ARG, "cost_dev must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SoftWs* ws = static_cast<SoftWs*>(workspace_dev);
+  float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace_dev) + 256);
+  softmax_init_kernel<<<1, 1, 0, s>>>(ws);
+  NLC_LAUNCH_OK("softmax_init_kernel");
+  int gmin = (K / 4 + 255) / 256;
+  if (gmin > 148 * 2) gmin = 148 * 2;
+  if (gmin < 1) gmin = 1;
+  softmax_min_kernel<<<gmin, 256, 0, s>>>(cost_dev, K, ws);
+  NLC_LAUNCH_OK("softmax_min_kernel");
+  const int grid = sum_grid(K);
+  const int rows_per_block = (K + grid - 1) / grid;
+  const int TNp = (TN + 31) / 32 * 32;
+  const int RY = 256 / TNp;
+  const size_t smem = (size_t)(RY * TNp + RY) * sizeof(float);
+  softmax_sum_kernel<<<grid, 256, smem, s>>>(cost_dev, noise_dev, K, TN, TNp, 1.0f / lambda_, ws, partials, triple_dev,
+                                             weights_dev, rows_per_block);
+  NLC_LAUNCH_OK("softmax_sum_kernel");
+  return NLC_OK;
+}
+
+extern "C" int nlc_softmax_combine(const float* triples_dev, int G, int T, int nu, float lambda_, float u_scale,
+                                   float* U_dev, float* action_dev, float* stats_dev, void* stream) {
+  NLC_REQUIRE(triples_dev && U_dev, NLC_ERR_ARG, "nlc_softmax_combine: null pointer");
+  NLC_REQUIRE(G >= 1 && T >= 1 && nu >= 1 && lambda_ > 0.0f, NLC_ERR_ARG, "nlc_softmax_combine: bad sizes");
+  softmax_combine_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(triples_dev, G, T * nu, nu, 1.0f / lambda_,
+                                                                           u_scale, U_dev, action_dev, stats_dev);
+  NLC_LAUNCH_OK("softmax_combine_kernel");
+  return NLC_OK;
+}

@@ -1,0 +1,330 @@
+"""``MPPIDelay`` with the reference's constructor, ``command(state, action_buffer)`` / ``reset`` /
+``get_rollouts`` signatures and post-call attributes (``planners/mppi_delay.py:52-381``), executed as a fixed
+sequence of sm_100a kernels behind ``libnlc_b200.so``.
+
+Differences a caller can see, all deliberate:
+
+* ``dynamics`` / ``running_cost`` must be the declarative handles of :mod:`neurallaplacecontrol_b200.closures`
+  (a fused kernel cannot call opaque Python; there is no CPU fallback, so anything else raises ``TypeError``).
+* Arithmetic is fp32 on the device; tensors left on the object (``noise``, ``perturbed_action``, ``cost_total``,
+  ``cost_total_non_zero``, ``omega``, ``states``, ``actions``, ``U``) are fp32 CUDA tensors (zero-copy views of the
+  planner's buffers); the returned action is cast to ``noise_sigma.dtype`` like the reference's.
+* Options the reference's callers never use and this path does not implement raise ``NotImplementedError``
+  instead of being silently ignored: ``terminal_state_cost``, ``step_dependent_dynamics``, ``rollout_samples > 1``
+  (legacy variance branch, ``:291-292,310``), ``encode_obs_time``.
+* Extra keyword arguments (not in the reference): ``process_group`` shards the K samples over the ranks of a
+  ``torch.distributed`` group (one all-gather of the (beta, eta, W) triple per control step), ``seed`` keys the
+  on-device Philox sampler, ``math_mode`` selects the contraction arithmetic, ``keep_states`` can drop the
+  ``states`` trajectory output.
+
+Noise injection for parity tests works as on the reference: replace ``planner.noise_dist.sample`` with a callable
+returning the ``(K, T, nu)`` tensor (it is called once per ``command`` with ``(K, T)``, ``mppi_delay.py:319``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from torch.distributions.multivariate_normal import MultivariateNormal
+
+from .. import _lib, sharding
+from ..closures import AnalyticDelayDynamics, EnvRunningCost, NLDynamics
+
+
+class _DevView:
+    """Zero-copy torch view of a raw device buffer through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _scalar_bound(x, name):
+    if x is None:
+        return None
+    t = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
+    if not bool((t == t[0]).all()):
+        raise NotImplementedError(f"{name}: per-dimension bounds are not used by the reference's callers "
+                                  "(mppi_with_model.py:227-228) and are not implemented")
+    return float(t[0])
+
+
+class MPPIDelay:
+    def __init__(self, dynamics, running_cost, nx, noise_sigma, num_samples=100, horizon=15, device="cpu",
+                 terminal_state_cost=None, lambda_=1.0, noise_mu=None, u_min=None, u_max=None, u_init=None,
+                 U_init=None, u_scale=1, u_per_command=1, step_dependent_dynamics=False, rollout_samples=1,
+                 rollout_var_cost=0, rollout_var_discount=0.95, dt=0.05, sample_null_action=False,
+                 noise_abs_cost=False, encode_obs_time=False, *, process_group=None, seed=0, math_mode="fp32",
+                 keep_states=True, action_buffer_size=4):
+        if not isinstance(dynamics, (NLDynamics, AnalyticDelayDynamics)):
+            raise TypeError("dynamics must be an NLDynamics or AnalyticDelayDynamics handle: the fused rollout kernel "
+                            "cannot call an opaque Python callable and this package has no CPU fallback")
+        if not isinstance(running_cost, EnvRunningCost):
+            raise TypeError("running_cost must be an EnvRunningCost handle (see neurallaplacecontrol_b200.closures)")
+        if terminal_state_cost is not None:
+            raise NotImplementedError("terminal_state_cost is not used on the reference path and is not implemented")
+        if step_dependent_dynamics:
+            raise NotImplementedError("step_dependent_dynamics is not implemented")
+        if rollout_samples != 1:
+            raise NotImplementedError("rollout_samples > 1 (legacy variance branch) is not implemented")
+        if encode_obs_time:
+            raise NotImplementedError("encode_obs_time=True is not implemented on this path yet")
+        if u_per_command != 1:
+            raise NotImplementedError("u_per_command != 1 is not implemented")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            if not torch.cuda.is_available():
+                raise RuntimeError("MPPIDelay (B200) needs a CUDA device; there is no CPU fallback")
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.d = dev
+        noise_sigma = torch.as_tensor(noise_sigma)
+        self.dtype = noise_sigma.dtype
+        self.K = num_samples
+        self.T = horizon
+        self.encode_obs_time = encode_obs_time
+        self.dt = dt
+        self.nx = nx
+        self.nu = 1 if noise_sigma.dim() == 0 else noise_sigma.shape[0]
+        self.lambda_ = lambda_
+        if noise_mu is None:
+            noise_mu = torch.zeros(self.nu, dtype=self.dtype)
+        if u_init is None:
+            u_init = torch.zeros_like(noise_mu)
+        if self.nu == 1:
+            noise_mu = noise_mu.view(-1)
+            noise_sigma = noise_sigma.view(-1, 1)
+        self.u_scale = u_scale
+        self.u_per_command = u_per_command
+        # mppi_delay.py:143-150: if one bound is given the other is its negative
+        lo, hi = _scalar_bound(u_min, "u_min"), _scalar_bound(u_max, "u_max")
+        if hi is not None and lo is None:
+            lo = -hi
+        if lo is not None and hi is None:
+            hi = -lo
+        self.u_min = None if lo is None else torch.tensor(lo, device=self.d)
+        self.u_max = None if hi is None else torch.tensor(hi, device=self.d)
+        self.noise_mu = noise_mu
+        self.noise_sigma = noise_sigma
+        self.noise_sigma_inv = torch.inverse(noise_sigma)
+        self.noise_dist = MultivariateNormal(noise_mu, covariance_matrix=noise_sigma)
+        self.u_init = u_init
+        self.F = dynamics
+        self.running_cost = running_cost
+        self.terminal_state_cost = None
+        self.sample_null_action = sample_null_action
+        self.noise_abs_cost = noise_abs_cost
+        self.state = None
+        self.M = rollout_samples
+        self.rollout_var_cost = rollout_var_cost
+        self.rollout_var_discount = rollout_var_discount
+        self.B = int(action_buffer_size)
+        self.math_mode = math_mode
+        self.keep_states = bool(keep_states)
+        self.seed = int(seed)
+
+        # ---- sharding of the K samples -------------------------------------------------------------
+        self.process_group = process_group
+        if process_group is not None:
+            import torch.distributed as dist
+
+            self.G = dist.get_world_size(process_group)
+            self.rank = dist.get_rank(process_group)
+        else:
+            self.G, self.rank = 1, 0
+        self.k_offset, self.K_local = sharding.shard_range(self.K, self.G, self.rank)
+
+        self._lib = _lib.load()
+        self._handle = None
+        self._handle_B = None
+        self._views = {}
+        if U_init is None:
+            U_init = self.noise_dist.sample((self.T,))  # mppi_delay.py:163-164
+        self._U_host = torch.as_tensor(U_init).detach().to("cpu", torch.float64).reshape(self.T, self.nu).clone()
+        self._U_dirty = True
+
+    # ---- device handle ---------------------------------------------------------------------------------------
+    def _ensure(self, B):
+        if self._handle is not None and self._handle_B == B:
+            return self._handle
+        self._destroy()
+        d = _lib.PlannerDesc()
+        mp = d.mppi
+        mp.K, mp.T, mp.nu, mp.B = self.K_local, self.T, self.nu, B
+        mp.k_offset, mp.k_total = self.k_offset, self.K
+        mp.lambda_, mp.u_scale = float(self.lambda_), float(self.u_scale)
+        mp.has_bounds = int(self.u_max is not None)
+        if self.u_max is not None:
+            mp.u_min, mp.u_max = float(self.u_min), float(self.u_max)
+        mp.sample_null_action, mp.noise_abs_cost = int(self.sample_null_action), int(self.noise_abs_cost)
+        sinv = self.noise_sigma_inv.to(torch.float64).reshape(self.nu, self.nu)
+        chol = torch.linalg.cholesky(self.noise_sigma.to(torch.float64).reshape(self.nu, self.nu))
+        for i in range(self.nu):
+            mp.noise_mu[i] = float(self.noise_mu.reshape(-1)[i])
+            mp.u_init[i] = float(torch.as_tensor(self.u_init).reshape(-1)[i])
+            for j in range(self.nu):
+                mp.sigma_inv[i * self.nu + j] = float(sinv[i, j])
+                mp.sigma_chol[i * self.nu + j] = float(chol[i, j])
+        ro = d.rollout
+        ro.env = _lib.ENV_IDS[self.running_cost.env_name]
+        ro.state_constraint = int(self.running_cost.state_constraint)
+        ro.goal_x = float(self.running_cost.goal_x)
+        ro.dynamics = self.F.kind
+        ro.delay = int(self.F.delay)
+        ro.dt = float(self.F.dt)
+        d.nx, d.n_shards, d.shard_index = self.nx, self.G, self.rank
+        d.math_mode = _lib.MATH_MODES[self.math_mode]
+        d.keep_states = int(self.keep_states)
+        d.seed = self.seed
+        model_h = None
+        if isinstance(self.F, NLDynamics):
+            if self.F.model._cuda_device is None:
+                self.F.model._cuda_device = self.d
+            model_h = self.F.model.set_prediction_time(self.F.dt)
+        h = C.c_void_p()
+        _lib.check(self._lib.nlc_planner_create(C.byref(h), model_h, C.byref(d), self.d.index), "nlc_planner_create")
+        self._handle, self._handle_B, self._views = h, B, {}
+        self._U_dirty = True
+        return h
+
+    def _destroy(self):
+        if self._handle is not None:
+            self._sync_U_to_host()
+            self._lib.nlc_planner_destroy(self._handle)
+            self._handle = None
+            self._views = {}
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                self._lib.nlc_planner_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _buf(self, which, shape):
+        """fp32 CUDA tensor aliasing one of the planner's device buffers."""
+        key = (which, tuple(shape))
+        if key not in self._views:
+            p, n = C.c_void_p(), C.c_int64()
+            _lib.check(self._lib.nlc_planner_buffer(self._handle, which, C.byref(p), C.byref(n)), "nlc_planner_buffer")
+            if p.value is None or n.value == 0:
+                return None
+            assert int(np.prod(shape)) == n.value, (which, shape, n.value)
+            self._views[key] = torch.as_tensor(_DevView(p.value, shape), device=self.d)
+        return self._views[key]
+
+    def _sync_U_to_host(self):
+        if self._handle is not None and not self._U_dirty:
+            arr = np.empty(self.T * self.nu, dtype=np.float64)
+            _lib.check(self._lib.nlc_planner_get_U(self._handle, arr.ctypes.data_as(C.POINTER(C.c_double))), "nlc_planner_get_U")
+            self._U_host = torch.from_numpy(arr).reshape(self.T, self.nu).clone()
+
+    def _push_U(self):
+        if self._U_dirty:
+            ptr, keep = _lib.as_double_array(self._U_host.numpy())
+            _lib.check(self._lib.nlc_planner_set_U(self._handle, ptr), "nlc_planner_set_U")
+            self._U_dirty = False
+
+    # ---- the reference's attributes ------------------------------------------------------------------------------
+    @property
+    def U(self):
+        if self._handle is None or self._U_dirty:
+            return self._U_host.to(self.dtype)
+        return self._buf(_lib.BUF_U, (self.T, self.nu))
+
+    @U.setter
+    def U(self, value):
+        self._U_host = torch.as_tensor(value).detach().to("cpu", torch.float64).reshape(self.T, self.nu).clone()
+        self._U_dirty = True
+
+    def _after(self, which, shape):
+        if self._handle is None or self._calls == 0:
+            return None
+        return self._buf(which, shape)
+
+    _calls = 0
+    noise = property(lambda self: self._after(_lib.BUF_NOISE, (self.K_local, self.T, self.nu)))
+    perturbed_action = property(lambda self: self._after(_lib.BUF_PERTURBED, (self.K_local, self.T, self.nu)))
+    cost_total = property(lambda self: self._after(_lib.BUF_COST_TOTAL, (self.K_local,)))
+    states = property(lambda self: self._after(_lib.BUF_STATES, (self.K_local, self.T, self.nx)) if self.keep_states else None)
+    actions = property(lambda self: self._after(_lib.BUF_ACTIONS, (self.K_local, self.T, self.nu)))
+
+    @property
+    def cost_total_non_zero(self):
+        """exp(-(c - beta)/lambda) with the GLOBAL beta (mppi_delay.py:210-211) for this shard's samples."""
+        if self._handle is None or self._calls == 0:
+            return None
+        w = self._buf(_lib.BUF_WEIGHTS, (self.K_local,))
+        beta_local = self._buf(_lib.BUF_TRIPLE, (2 + self.T * self.nu,))[0]
+        beta = self._buf(_lib.BUF_STATS, (2,))[0]
+        return w * torch.exp(-(beta_local - beta) / self.lambda_)
+
+    @property
+    def omega(self):
+        nz = self.cost_total_non_zero
+        return None if nz is None else nz / self._buf(_lib.BUF_STATS, (2,))[1]
+
+    # ---- MPPIDelay.command ---------------------------------------------------------------------------------------
+    def _injected_noise(self):
+        """The reference's tests inject noise by replacing ``noise_dist.sample`` (instance attribute)."""
+        fn = self.noise_dist.__dict__.get("sample")
+        if fn is None:
+            return None
+        nz = torch.as_tensor(fn((self.K, self.T)))
+        if tuple(nz.shape) != (self.K, self.T, self.nu):
+            raise ValueError(f"injected noise must have shape {(self.K, self.T, self.nu)}, got {tuple(nz.shape)}")
+        nz = nz[self.k_offset:self.k_offset + self.K_local]  # bit-exact sample indexing: global k = offset + local k
+        return nz.to(device=self.d, dtype=torch.float32).contiguous()
+
+    def command(self, state, action_buffer):
+        """:param state: (nx) or (K x nx) current state; :param action_buffer: (B x nu) past actions, env units.
+        :returns action: (nu) best action (``mppi_delay.py:193-224``)."""
+        action_buffer = torch.as_tensor(action_buffer)
+        B = action_buffer.shape[0]
+        h = self._ensure(B)
+        self._push_U()
+        if not torch.is_tensor(state):
+            state = torch.tensor(np.asarray(state))
+        self.state = state.to(dtype=self.dtype)
+        noise = self._injected_noise()
+        stream = _lib.current_stream_ptr()
+        per_sample = state.dim() == 2 and state.shape[0] != 1
+        with torch.cuda.device(self.d):
+            if not per_sample and noise is None and self.G == 1 and not state.is_cuda and not action_buffer.is_cuda:
+                # lowest-latency path: host buffers straight through the C ABI
+                sp, k1 = _lib.as_double_array(state.detach().reshape(-1).numpy())
+                bp, k2 = _lib.as_double_array(action_buffer.detach().reshape(-1).numpy())
+                out = np.empty(self.nu, dtype=np.float64)
+                _lib.check(self._lib.nlc_planner_command_host(h, sp, bp, None, out.ctypes.data_as(C.POINTER(C.c_double)), stream),
+                           "nlc_planner_command_host")
+                self._calls += 1
+                return torch.from_numpy(out).to(device=self.d, dtype=self.dtype)
+            st = self._buf(_lib.BUF_STATE, (self.K_local, self.nx))
+            if per_sample:
+                if state.shape[0] != self.K:
+                    raise ValueError("per-sample states must have K rows")
+                st.copy_(state[self.k_offset:self.k_offset + self.K_local].to(device=self.d, dtype=torch.float32))
+            else:
+                st[0].copy_(state.reshape(-1).to(device=self.d, dtype=torch.float32))
+            ab = self._buf(_lib.BUF_ACTION_BUFFER, (B, self.nu))
+            ab.copy_(action_buffer.reshape(B, self.nu).to(device=self.d, dtype=torch.float32))
+            _lib.check(self._lib.nlc_planner_rollout(h, st.data_ptr(), int(per_sample), ab.data_ptr(), _lib.ptr(noise), stream),
+                       "nlc_planner_rollout")
+            if self.G > 1:
+                triple = self._buf(_lib.BUF_TRIPLE, (2 + self.T * self.nu,))
+                allt = self._buf(_lib.BUF_ALL_TRIPLES, (self.G, 2 + self.T * self.nu))
+                sharding.gather_triples(triple, allt, group=self.process_group)
+            _lib.check(self._lib.nlc_planner_finish(h, stream), "nlc_planner_finish")
+            self._calls += 1
+            return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
+
+    def reset(self):
+        """Clear controller state after finishing a trial (``mppi_delay.py:226-230``)."""
+        self.U = self.noise_dist.sample((self.T,))
+
+    def get_rollouts(self, state, num_rollouts=1):
+        """Nominal rollout of ``U`` (``mppi_delay.py:358-381``).  The reference passes a single action, not a
+        history window, to the dynamics here, which the delay closures cannot consume; this
+        implementation keeps the signature and raises."""
+        raise NotImplementedError("get_rollouts is incompatible with history-window dynamics in the reference itself")

@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI / the drop-in classes) against the golden vectors produced by the
+reference's own code and against the CPU oracle on the same seeded inputs.
+
+Tolerances (relative to max |ref| of each tensor, `_util.relerr`):
+* stage 1 (`perturbed_action`, `noise`): BIT-EXACT against the same elementwise chain evaluated in fp32 by the oracle;
+  1e-6 against the fp64 reference (fp32 rounding of the inputs).
+* everything floating point downstream (states, costs, omega, U, action): 1e-4, the bound BASELINE.json's north_star
+  states for the fp32 path.  The fp32 CPU oracle itself differs from the fp64 one by ~1e-6..1e-5 on these cases.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import DT, ENVS, S_TERMS, load, relerr, short, weights
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+TOL = 1e-4
+
+
+def _nlc():
+    import neurallaplacecontrol_b200 as nlc
+
+    return nlc
+
+
+def make_model(env, calibrated, **kw):
+    from oracle import costs
+
+    nlc = _nlc()
+    nx, nu = costs.ENV_DIMS[env]
+    m = nlc.NeuralLaplaceModel(nx, nu, nx, hidden_units=128, s_recon_terms=S_TERMS, ilt_algorithm="fourier",
+                               encode_obs_time=False, state_mean=np.zeros(nx), state_std=np.ones(nx),
+                               action_mean=np.array([0] * nu), action_std=np.array([1.0]), normalize=True,
+                               normalize_time=True, dt=DT, **kw).double()
+    missing = m.load_state_dict(weights(env, calibrated=calibrated))
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m
+
+
+def make_planner(env, model, K, T, U_init, dynamics=None, **kw):
+    from oracle import costs
+
+    nlc = _nlc()
+    nx, nu = costs.ENV_DIMS[env]
+    ah = np.float32(costs.ENV_ACT_HIGH[env])
+    dyn = dynamics if dynamics is not None else nlc.NLDynamics(model, DT)
+    return nlc.MPPIDelay(dyn, nlc.EnvRunningCost(env), nx, nlc.noise_sigma_for(nu), num_samples=K, horizon=T,
+                         device="cuda:0", lambda_=1.0, u_min=torch.tensor(-ah), u_max=torch.tensor(ah), u_scale=ah,
+                         U_init=torch.as_tensor(U_init).clone(), **kw)
+
+
+def test_library_is_native_and_counts_launches():
+    lib = _nlc()._lib.load()
+    assert lib.nlc_device_check(0) == 0, lib.nlc_last_error()
+    before = lib.nlc_launch_count()
+    t = torch.tensor([0.05, 0.1], device="cuda")
+    F = torch.randn(4, 2, 17, dtype=torch.complex64, device="cuda")
+    _nlc().fourier_ilt(F, t)
+    assert lib.nlc_launch_count() == before + 1
+
+
+@pytest.mark.parametrize("env", ENVS)
+def test_model_forward_matches_reference(env):
+    g = load("model_fwd_" + short(env))
+    m = make_model(env, calibrated=False)
+    obs, act = torch.from_numpy(g["obs"]).cuda(), torch.from_numpy(g["act"]).cuda()
+    out = m(obs, act, torch.from_numpy(g["ts_fixed"]).cuda())
+    assert out.dtype == torch.float64 and out.shape == g["out_fixed"].shape
+    assert relerr(g["p_action"], m.last_p_action) < 1e-5
+    assert relerr(g["out_fixed"], out) < TOL
+
+
+PLAN_KEYS = ("noise", "perturbed_action", "cost_total", "cost_total_non_zero", "omega", "states", "actions", "U", "action")
+
+
+def _run_plan(env, g, calibrated, n_calls=1, **kw):
+    from oracle import mppi
+
+    m = make_model(env, calibrated)
+    noise = torch.from_numpy(g["in_noise"])
+    K, T = noise.shape[-3], noise.shape[-2]
+    planner = make_planner(env, m, K, T, g["in_U"], **kw)
+    buf = torch.from_numpy(g["in_buffer"]).clone()
+    action = None
+    for c in range(n_calls):
+        nz = noise[c] if noise.dim() == 4 else noise
+        planner.noise_dist.sample = lambda shape, nz=nz: nz.clone()
+        action = planner.command(np.asarray(g["in_state"]), buf)
+        buf, _ = mppi.get_action(buf, action.cpu(), 1)
+    out = {k: getattr(planner, k) for k in PLAN_KEYS if k != "action"}
+    out["action"] = action
+    return planner, out
+
+
+@pytest.mark.parametrize("env", ENVS)
+@pytest.mark.parametrize("case", ["raw", "cal_calls1", "cal_calls2", "cal_stateK"])
+def test_plan_matches_reference(env, case):
+    name = f"plan_raw_{short(env)}" if case == "raw" else f"plan_{case.replace('cal_', 'cal_' + short(env) + '_')}"
+    g = load(name)
+    planner, out = _run_plan(env, g, calibrated=case != "raw", n_calls=2 if case.endswith("calls2") else 1)
+    assert out["action"].dtype == torch.float64
+    for k in PLAN_KEYS:
+        tol = 1e-6 if k in ("noise", "perturbed_action", "actions") else TOL
+        assert relerr(g[k], out[k]) < tol, (k, relerr(g[k], out[k]))
+    assert abs(float(out["omega"].sum()) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("env", ENVS)
+def test_stage1_bit_exact_vs_fp32_oracle(env):
+    """perturb/clamp chain op for op in fp32 (mppi_delay.py:321-328)."""
+    from oracle import costs, mppi
+
+    g = load(f"plan_cal_{short(env)}_calls1")
+    nx, nu = costs.ENV_DIMS[env]
+    ah = costs.ENV_ACT_HIGH[env]
+    planner, out = _run_plan(env, g, calibrated=True)
+    U = torch.roll(torch.from_numpy(g["in_U"]).float(), -1, dims=0)
+    U[-1] = 0
+    noise32 = torch.from_numpy(g["in_noise"][0]).float()
+    pert, nb, _ = mppi.perturb(U, noise32, torch.inverse(mppi.noise_sigma_for(nu)).float(), 1.0, np.float32(ah), -ah, ah)
+    assert pert.dtype == torch.float32
+    assert torch.equal(pert, out["perturbed_action"].cpu())
+    assert torch.equal(nb, out["noise"].cpu())
+    assert torch.equal((np.float32(ah) * pert) / np.float32(ah), out["actions"].cpu())
+
+
+def test_cfg1_pendulum_K1000_H20():
+    """BASELINE config 1 against the reference's own run (fixed injected noise)."""
+    from oracle.gen_golden import START_STATE, injected_noise
+
+    env = "oderl-pendulum"
+    g = load("plan_cfg1_pendulum_K1000_H20")
+    K, T, nu = 1000, 20, 1
+    gg = {"in_U": np.zeros((T, nu)), "in_buffer": np.zeros((4, nu)), "in_state": np.array(START_STATE[env]),
+          "in_noise": injected_noise(K, T, nu, seed=int(g["noise_seed"])).numpy()}
+    planner, out = _run_plan(env, gg, calibrated=True)
+    assert relerr(g["cost_total"], out["cost_total"]) < TOL
+    assert relerr(g["states_first16"], out["states"][:16]) < TOL
+    assert relerr(g["states_last"], out["states"][:, -1]) < TOL
+    assert relerr(g["omega"], out["omega"]) < TOL
+    assert relerr(g["U"], out["U"]) < TOL
+    assert relerr(g["action"], out["action"]) < TOL
+
+
+@pytest.mark.parametrize("env", ENVS)
+@pytest.mark.parametrize("delay", [0, 1, 3])
+def test_analytic_dynamics_plan_matches_reference(env, delay):
+    """reference oracle.py dynamics in the planner's dynamics slot."""
+    g = load(f"plan_oracledyn_{short(env)}_d{delay}")
+    dyn = _nlc().AnalyticDelayDynamics(env, delay, DT)
+    noise = torch.from_numpy(g["in_noise"])
+    planner = make_planner(env, None, noise.shape[0], noise.shape[1], g["in_U"], dynamics=dyn)
+    planner.noise_dist.sample = lambda shape: noise.clone()
+    action = planner.command(np.asarray(g["in_state"]), torch.from_numpy(g["in_buffer"]))
+    for k in ("cost_total", "states", "omega", "U"):
+        assert relerr(g[k], getattr(planner, k)) < TOL, k
+    assert relerr(g["action"], action) < TOL
+
+
+def test_rejects_opaque_callables_and_unsupported_options():
+    nlc = _nlc()
+    with pytest.raises(TypeError):
+        nlc.MPPIDelay(lambda s, a: s, nlc.EnvRunningCost("oderl-pendulum"), 3, nlc.noise_sigma_for(1), device="cuda:0")
+    m = make_model("oderl-pendulum", True)
+    with pytest.raises(TypeError):
+        nlc.MPPIDelay(nlc.NLDynamics(m), lambda s, a: 0, 3, nlc.noise_sigma_for(1), device="cuda:0")
+    with pytest.raises(NotImplementedError):
+        nlc.MPPIDelay(nlc.NLDynamics(m), nlc.EnvRunningCost("oderl-pendulum"), 3, nlc.noise_sigma_for(1), device="cuda:0",
+                      rollout_samples=2)
+    with pytest.raises(TypeError):
+        nlc.EnvRunningCost("oderl-pendulum", state_constraint=True)
+
+
+@pytest.mark.parametrize("env", ["oderl-cartpole"])
+def test_cartpole_cost_options(env):
+    """state_constraint / change_goal variants of the cartpole reward (ctcartpole.py:312-332) vs the oracle."""
+    from oracle import costs, mppi
+
+    nlc = _nlc()
+    nx, nu = costs.ENV_DIMS[env]
+    ah = costs.ENV_ACT_HIGH[env]
+    sd = weights(env, calibrated=True)
+    m = make_model(env, True)
+    K, T = 96, 6
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(K, T, nu, generator=g, dtype=torch.float64)
+    state = np.array([0.0, 0.0, -1.0, 0.0, 0.0]) + 0.01
+    buf = torch.zeros(4, nu, dtype=torch.float64)
+    for opts in ({"state_constraint": True}, {"change_goal": True}, {"change_goal": True, "change_goal_flipped": True}):
+        p = nlc.MPPIDelay(nlc.NLDynamics(m, DT), nlc.EnvRunningCost(env, **opts), nx, nlc.noise_sigma_for(nu), num_samples=K,
+                          horizon=T, device="cuda:0", u_min=torch.tensor(-ah), u_max=torch.tensor(ah), u_scale=ah,
+                          U_init=torch.zeros(T, nu, dtype=torch.float64))
+        p.noise_dist.sample = lambda shape: noise.clone()
+        a = p.command(state, buf)
+        ref = mppi.command(torch.zeros(T, nu, dtype=torch.float64), torch.from_numpy(state), buf, noise,
+                           mppi.make_nl_dynamics(sd, DT), costs.running_cost(env, **opts),
+                           noise_sigma=mppi.noise_sigma_for(nu), u_scale=ah, u_min=-ah, u_max=ah)
+        assert relerr(ref["cost_total"], p.cost_total) < TOL, opts
+        assert relerr(ref["action"], a) < TOL, opts
+
+
+def test_null_action_and_abs_cost_options():
+    from oracle import costs, mppi
+
+    nlc = _nlc()
+    env = "oderl-acrobot"
+    nx, nu = costs.ENV_DIMS[env]
+    ah = costs.ENV_ACT_HIGH[env]
+    m = make_model(env, True)
+    K, T = 64, 5
+    g = torch.Generator().manual_seed(11)
+    noise = torch.randn(K, T, nu, generator=g, dtype=torch.float64)
+    U0 = torch.randn(T, nu, generator=g, dtype=torch.float64) * 0.2
+    state = np.array([1.0, 0.0, 1.0, 0.0, 0.0, 0.0])
+    buf = torch.zeros(4, nu, dtype=torch.float64)
+    p = nlc.MPPIDelay(nlc.NLDynamics(m, DT), nlc.EnvRunningCost(env), nx, nlc.noise_sigma_for(nu), num_samples=K, horizon=T,
+                      device="cuda:0", u_min=torch.tensor(-ah), u_max=torch.tensor(ah), u_scale=ah, U_init=U0.clone(),
+                      sample_null_action=True, noise_abs_cost=True)
+    p.noise_dist.sample = lambda shape: noise.clone()
+    p.command(state, buf)
+    U = torch.roll(U0, -1, dims=0)
+    U[-1] = 0
+    pert, nb, pc = mppi.perturb(U, noise.clone(), torch.inverse(mppi.noise_sigma_for(nu)), 1.0, ah, -ah, ah,
+                                sample_null_action=True, noise_abs_cost=True)
+    assert relerr(pert, p.perturbed_action) < 1e-6
+    assert float(p.perturbed_action[-1].abs().max()) == 0.0
+    cost, _, _ = mppi.rollout_costs(mppi.make_nl_dynamics(weights(env, calibrated=True), DT), costs.running_cost(env),
+                                    torch.from_numpy(state), pert, buf, ah)
+    assert relerr(cost + pc, p.cost_total) < TOL

@@ -1,0 +1,199 @@
+"""Stage-level parity through the C ABI: on-device Philox sampling, the two-pass softmax update and its K-sharded
+combine, the generic Fourier ILT kernel, and size-independent properties at BASELINE.json's full sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from _util import DT, relerr, weights
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def _lib():
+    from neurallaplacecontrol_b200 import _lib as L
+
+    return L
+
+
+def _params(K, T, nu, B=4, k_offset=0, k_total=None, u_scale=2.0, bound=2.0, lam=1.0):
+    from oracle import mppi
+
+    L = _lib()
+    p = L.MppiParams()
+    p.K, p.T, p.nu, p.B = K, T, nu, B
+    p.k_offset, p.k_total = k_offset, K if k_total is None else k_total
+    p.lambda_, p.u_scale, p.has_bounds, p.u_min, p.u_max = lam, u_scale, 1, -bound, bound
+    sig = mppi.noise_sigma_for(nu)
+    sinv, chol = torch.inverse(sig), torch.linalg.cholesky(sig)
+    for i in range(nu):
+        for j in range(nu):
+            p.sigma_inv[i * nu + j] = float(sinv[i, j])
+            p.sigma_chol[i * nu + j] = float(chol[i, j])
+    return p, chol
+
+
+def _perturb(p, U, noise_in, buf, seed=0, call=0):
+    L = _lib()
+    lib = L.load()
+    K, T, nu, B = p.K, p.T, p.nu, p.B
+    dev = "cuda"
+    out = {k: torch.empty(K, T, nu, device=dev) for k in ("perturbed", "noise", "actions")}
+    out["hist"] = torch.empty(K, B - 1 + T, nu, device=dev)
+    out["pert_cost"] = torch.empty(K, device=dev)
+    Ud = U.to(dev, torch.float32).contiguous()
+    Uc = torch.empty_like(Ud)
+    bufd = buf.to(dev, torch.float32).contiguous()
+    L.check(lib.nlc_perturb(C.byref(p), Ud.data_ptr(), Uc.data_ptr(), 0, L.ptr(noise_in), seed, call, bufd.data_ptr(),
+                            out["perturbed"].data_ptr(), out["noise"].data_ptr(), out["hist"].data_ptr(),
+                            out["actions"].data_ptr(), out["pert_cost"].data_ptr(), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("nu", [1, 2])
+def test_philox_sampler_matches_oracle_and_is_shard_invariant(nu):
+    from oracle import philox
+
+    K, T = 512, 20
+    U = torch.zeros(T, nu)
+    buf = torch.zeros(4, nu)
+    p, chol = _params(K, T, nu, bound=1e9, u_scale=1.0)
+    full = _perturb(p, U, None, buf, seed=1234567890123, call=7)
+    ref = philox.sampled_noise(K, T, nu, 0, 1234567890123, 7, chol.numpy(), np.zeros(nu))
+    assert np.abs(full["noise"].cpu().numpy() - ref).max() < 2e-5
+    # a shard starting at global sample 128 draws exactly the same numbers (bit-exact sample indexing)
+    ps, _ = _params(64, T, nu, k_offset=128, k_total=K, bound=1e9, u_scale=1.0)
+    part = _perturb(ps, U, None, buf, seed=1234567890123, call=7)
+    assert torch.equal(part["noise"], full["noise"][128:192])
+    other = _perturb(ps, U, None, buf, seed=1234567890123, call=8)
+    assert not torch.equal(other["noise"], part["noise"])
+
+
+def _softmax(cost, noise, lam, G):
+    L = _lib()
+    lib = L.load()
+    K, T, nu = noise.shape
+    TN = T * nu
+    idx = torch.tensor_split(torch.arange(K), G)
+    triples = torch.empty(G, 2 + TN, device="cuda")
+    weights_out = torch.empty(K, device="cuda")
+    for g, ix in enumerate(idx):
+        c = cost[ix].contiguous()
+        n = noise[ix].contiguous()
+        ws = torch.empty(int(lib.nlc_softmax_workspace_bytes(len(ix), TN)), dtype=torch.uint8, device="cuda")
+        w = torch.empty(len(ix), device="cuda")
+        L.check(lib.nlc_softmax_partial(c.data_ptr(), n.data_ptr(), len(ix), T, nu, lam, triples[g].data_ptr(),
+                                        w.data_ptr(), ws.data_ptr(), L.current_stream_ptr()))
+        weights_out[ix.cuda()] = w
+    return triples, weights_out
+
+
+@pytest.mark.parametrize("K,T,nu", [(1, 1, 1), (7, 3, 2), (1000, 20, 1), (8192, 30, 1), (65536, 50, 2)])
+def test_softmax_update_and_shard_combine(K, T, nu):
+    from oracle import mppi
+
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator().manual_seed(K)
+    cost = (torch.rand(K, generator=g, dtype=torch.float64) * 40 - 5)
+    noise = torch.randn(K, T, nu, generator=g, dtype=torch.float64)
+    U = torch.randn(T, nu, generator=g, dtype=torch.float64)
+    lam = 0.7
+    U_ref, w_ref, omega_ref = mppi.softmax_update(U, cost, noise, lam)
+    c32, n32 = cost.float().cuda(), noise.float().cuda()
+    results = []
+    for G in (1, 2, 4, 8):
+        if K < G:
+            continue
+        triples, w = _softmax(c32, n32, lam, G)
+        Ud = U.float().cuda().contiguous()
+        action = torch.empty(nu, device="cuda")
+        stats = torch.empty(2, device="cuda")
+        L.check(lib.nlc_softmax_combine(triples.data_ptr(), G, T, nu, lam, 3.0, Ud.data_ptr(), action.data_ptr(),
+                                        stats.data_ptr(), L.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert relerr(U_ref, Ud) < 2e-5, (G, relerr(U_ref, Ud))
+        assert relerr(U_ref[0] * 3.0, action) < 2e-5
+        assert abs(float(stats[0]) - float(cost.float().min())) == 0.0  # min is exact
+        if G == 1:
+            assert relerr(w_ref, w) < 1e-5
+        results.append(Ud.clone())
+    for r in results[1:]:
+        assert relerr(results[0], r) < 1e-5  # sharding changes only the summation order
+
+
+@pytest.mark.parametrize("S", [17, 33, 64, 65, 129])
+@pytest.mark.parametrize("per_row", [False, True])
+def test_fourier_ilt_kernel_matches_oracle(S, per_row):
+    from neurallaplacecontrol_b200 import fourier_ilt
+    from oracle import ilt
+
+    N, n_t = 77, 13  # 1001 rows: 31 full 32-row chunks + a 9-row tail
+    g = torch.Generator().manual_seed(S)
+    F = torch.complex(torch.rand(N, n_t, S, generator=g) * 2 - 1, torch.rand(N, n_t, S, generator=g) * 2 - 1)
+    t = (torch.arange(n_t, dtype=torch.float32) + 1) * 0.05
+    if per_row:
+        t = 0.01 + torch.rand(N, n_t, generator=g) * 2.0
+    out = fourier_ilt(F.cuda(), t.cuda())
+    t64 = t.double().expand(N, n_t)
+    T64 = ilt.SCALE * (t64 + ilt.EPS)
+    ref = ilt.fourier_line_integrate(F.real.double(), F.imag.double(), t64, T64)
+    assert relerr(ref, out) < 2e-5, relerr(ref, out)
+
+
+def test_fourier_ilt_closed_form_pair():
+    """1/(s+1) <-> exp(-t) through the kernel with the oracle's s-points (truncation error of the series itself)."""
+    from neurallaplacecontrol_b200 import fourier_ilt
+    from oracle import ilt
+
+    t = torch.tensor([0.05, 0.1, 0.2, 0.5, 1.0], dtype=torch.float64)
+    S = 129
+    s_re, s_im, T = ilt.fourier_s_points(t, S)
+    Fs = 1.0 / (torch.complex(s_re, s_im) + 1.0)
+    out = fourier_ilt(Fs.to(torch.complex64).unsqueeze(0).cuda(), t.float().cuda())
+    want = ilt.fourier_ilt_of(lambda s: 1.0 / (s + 1.0), t, S)
+    assert relerr(want, out[0]) < 1e-4
+    assert (out[0].double().cpu() - torch.exp(-t)).abs().max() < 0.1
+
+
+def test_cfg3_full_size_properties():
+    """BASELINE config 3 shape (cartpole K=8192 H=30): size-independent properties + sharding invariance of the costs."""
+    import neurallaplacecontrol_b200 as nlc
+    from oracle import costs
+    from test_gpu_parity import make_model
+
+    env = "oderl-cartpole"
+    nx, nu = costs.ENV_DIMS[env]
+    ah = np.float32(costs.ENV_ACT_HIGH[env])
+    K, T = 8192, 30
+    m = make_model(env, True)
+    g = torch.Generator().manual_seed(1)
+    noise = torch.randn(K, T, nu, generator=g, dtype=torch.float64)
+    state = np.array([0.0, 0.0, -1.0, 1.2246467991473532e-16, 0.0])
+    buf = torch.zeros(4, nu, dtype=torch.float64)
+
+    def run(Kloc, off):
+        p = nlc.MPPIDelay(nlc.NLDynamics(m, DT), nlc.EnvRunningCost(env), nx, nlc.noise_sigma_for(nu), num_samples=Kloc,
+                          horizon=T, device="cuda:0", u_min=torch.tensor(-ah), u_max=torch.tensor(ah), u_scale=ah,
+                          U_init=torch.zeros(T, nu, dtype=torch.float64))
+        p.noise_dist.sample = lambda shape: noise[off:off + Kloc].clone()
+        a = p.command(state, buf)
+        return p, a
+
+    p, a = run(K, 0)
+    assert torch.isfinite(p.cost_total).all() and torch.isfinite(a).all()
+    assert abs(float(p.omega.sum()) - 1.0) < 1e-4
+    assert float(p.perturbed_action.abs().max()) * float(ah) <= float(ah) * (1 + 1e-6)
+    assert float(a.abs().max()) <= float(ah) * (1 + 1e-6)
+    # per-sample costs do not depend on which shard (which CTA tiling) computed them
+    p2, _ = run(K // 4, K // 2)
+    assert torch.equal(p2.cost_total, p.cost_total[K // 2:K // 2 + K // 4])
+    # a zero-noise plan leaves U at zero cost-weighted mean of zero noise
+    p.noise_dist.sample = lambda shape: torch.zeros(K, T, nu, dtype=torch.float64)
+    p.U = torch.zeros(T, nu)
+    p.command(state, buf)
+    assert float(p.U.abs().max()) == 0.0
+    assert float((p.cost_total - p.cost_total[0]).abs().max()) == 0.0
