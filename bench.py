@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the MPPI / Neural Laplace planning hot path (BASELINE.json metric: model rollout-steps/s and
+per-control-step plan latency).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg4|cfg3|cfg1]
+
+One "step" = one MPPI control step (``MPPIDelay.command``): K x H Neural Laplace rollout-steps.
+Default workload at every N: BASELINE config 4, acrobot-delay K=65536 H=50 (strong scaling: the K samples are
+sharded over the N GPUs, one all-gather of the (beta, eta, W) triple per step).  Synthetic inputs: random-init
+weights of the reference architecture (golden fixture, calibrated phi-bias), on-device Philox action noise.
+
+* ``value``   - device-timed (CUDA events), state/action-buffer already resident in HBM.
+* ``e2e``     - the same control step through the drop-in ``MPPIDelay.command(state, action_buffer)`` with HOST
+                buffers: host->device copies of the inputs and the device->host read of the action inside the timing.
+* ``roofline``- the dominant kernel (history encoder) timed alone with CUDA events: hoisted FLOPs / duration against
+                the measured bf16 tensor peak of MEASURED_PEAKS.json.
+* ``cpu_baseline`` / ``--impl reference`` - the CPU oracle port of the reference path (fp64, all host threads) on a
+                bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (env, K, H, description)
+    "cfg1": ("oderl-pendulum", 1000, 20, "oderl Pendulum-delay MPPI K=1000 H=20"),
+    "cfg3": ("oderl-cartpole", 8192, 30, "oderl Cartpole-delay MPPI K=8192 H=30"),
+    "cfg4": ("oderl-acrobot", 65536, 50, "oderl Acrobot-delay MPPI K=65536 H=50"),
+}
+START_STATE = {
+    "oderl-pendulum": [-1.0, 1.2246467991473532e-16, 1.0],
+    "oderl-cartpole": [0.0, 0.0, -1.0, 1.2246467991473532e-16, 0.0],
+    "oderl-acrobot": [1.0, 0.0, 1.0, 0.0, 0.0, 0.0],
+}
+# algorithmic work per rollout-step, FLOP = 2 MAC, "hoisted minimum" (SURVEY 8d / BASELINE.md 4)
+HOISTED_FLOP = {"oderl-pendulum": 307712, "oderl-cartpole": 325632, "oderl-acrobot": 336128}
+ENCODER_FLOP = 2 * 10 * 192 * 64  # ten 64x192 products per window: the hoisted GRU work (+ a 2x64 output layer)
+METRIC, UNIT = "mppi_rollout_steps_per_sec", "rollout-steps/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(env):
+    import numpy as np
+    import torch
+
+    from _util import DT, S_TERMS, weights
+    from oracle import costs
+
+    nx, nu = costs.ENV_DIMS[env]
+    return {"nx": nx, "nu": nu, "ah": float(costs.ENV_ACT_HIGH[env]), "sd": weights(env, calibrated=True), "dt": DT, "S": S_TERMS,
+            "state": np.array(START_STATE[env], dtype=np.float64), "buffer": torch.zeros(4, nu, dtype=torch.float64)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, env, K, H, desc):
+    """CPU arm: the oracle port of the reference's PyTorch CPU path, fp64, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import costs, mppi
+
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = build_inputs(env)
+    nu, ah = inp["nu"], inp["ah"]
+    Ks = min(K, args.cpu_samples)
+    sample = f"{Ks} of the {K} samples x H={H} per step, fp64, oracle port (reference classes are not on the GPU box)"
+    dyn, cost = mppi.make_nl_dynamics(inp["sd"], inp["dt"]), costs.running_cost(env)
+    sig = mppi.noise_sigma_for(nu)
+    chol = torch.linalg.cholesky(sig)
+    U = torch.zeros(H, nu, dtype=torch.float64)
+    g = torch.Generator().manual_seed(1)
+    times = []
+    for it in range(args.warmup + args.steps):
+        noise = torch.randn(Ks, H, nu, generator=g, dtype=torch.float64) @ chol.T
+        t0 = time.perf_counter()
+        out = mppi.command(U, torch.from_numpy(inp["state"]), inp["buffer"], noise, dyn, cost, noise_sigma=sig, u_scale=ah,
+                           u_min=-ah, u_max=ah)
+        dt_ = time.perf_counter() - t0
+        U = out["U"]
+        if it >= args.warmup:
+            times.append(dt_)
+    ms = 1e3 * sum(times) / len(times)
+    val = Ks * H / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "K": K, "H": H, "env": env, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(env, K, H, cpu_samples, budget_s=25.0):
+    import torch
+
+    from oracle import costs, mppi
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = build_inputs(env)
+    nu, ah = inp["nu"], inp["ah"]
+    Ks = min(K, cpu_samples)
+    dyn, cost = mppi.make_nl_dynamics(inp["sd"], inp["dt"]), costs.running_cost(env)
+    sig = mppi.noise_sigma_for(nu)
+    U = torch.zeros(H, nu, dtype=torch.float64)
+    g = torch.Generator().manual_seed(1)
+    times, t_start = [], time.perf_counter()
+    for it in range(6):
+        noise = torch.randn(Ks, H, nu, generator=g, dtype=torch.float64) @ torch.linalg.cholesky(sig).T
+        t0 = time.perf_counter()
+        out = mppi.command(U, torch.from_numpy(inp["state"]), inp["buffer"], noise, dyn, cost, noise_sigma=sig, u_scale=ah,
+                           u_min=-ah, u_max=ah)
+        if it >= 1:
+            times.append(time.perf_counter() - t0)
+        U = out["U"]
+        if time.perf_counter() - t_start > budget_s and times:
+            break
+    t = sum(times) / len(times)
+    return {"value": Ks * H / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} control steps of {Ks} of the {K} samples x H={H}, fp64 oracle port, {cores} threads",
+            "plan_latency_ms_sample": 1e3 * t}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu(args, env, K, H, desc):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import neurallaplacecontrol_b200 as nlc
+    from neurallaplacecontrol_b200 import _lib
+
+    torch.set_grad_enabled(False)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    inp = build_inputs(env)
+    nx, nu, ah = inp["nx"], inp["nu"], inp["ah"]
+    model = nlc.NeuralLaplaceModel(nx, nu, nx, hidden_units=128, s_recon_terms=inp["S"], state_mean=np.zeros(nx),
+                                   state_std=np.ones(nx), action_mean=np.array([0] * nu), action_std=np.array([1.0]),
+                                   normalize=True, normalize_time=True, dt=inp["dt"], device=dev).double()
+    model.load_state_dict(inp["sd"])
+    planner = nlc.MPPIDelay(nlc.NLDynamics(model, inp["dt"]), nlc.EnvRunningCost(env), nx, nlc.noise_sigma_for(nu), num_samples=K,
+                            horizon=H, device=dev, lambda_=1.0, u_min=torch.tensor(-ah), u_max=torch.tensor(ah), u_scale=ah,
+                            U_init=torch.zeros(H, nu, dtype=torch.float64), process_group=group, seed=1234, math_mode=args.math)
+    lib = _lib.load()
+    state_host, buf_host = inp["state"], inp["buffer"]
+    state_dev = torch.tensor(state_host, dtype=torch.float64, device=dev)
+    buf_dev = buf_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        wall = []
+        launches0 = lib.nlc_launch_count()
+        for s, e in ev:
+            flush.fill_(1)  # flush L2 between timed iterations (outside the timed span)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            wall.append(time.perf_counter() - t0)
+        launches = lib.nlc_launch_count() - launches0
+        barrier()
+        dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+        t = torch.tensor([dev_ms, 1e3 * sum(wall)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / steps, float(t[1]) / steps, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # (1) device-resident inputs, device-timed
+    ms_dev, _, launches = timed(lambda: planner.command(state_dev, buf_dev), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    # (2) end to end through the drop-in call with host buffers (wall clock around the call; it synchronises)
+    def e2e_step():
+        a = planner.command(state_host, buf_host)
+        return a.cpu()
+    _, ms_e2e, _ = timed(e2e_step, args.steps, args.warmup)
+    # (3) the dominant kernel alone: history encoder over the K_local x H windows
+    Kl, B = planner.K_local, 4
+    hist = planner._buf(_lib.BUF_HIST, (Kl, B - 1 + H, nu))
+    pbuf = planner._buf(_lib.BUF_P, (Kl, H, 2))
+    mh = model.set_prediction_time(inp["dt"])
+    mode = _lib.MATH_MODES[args.math]
+
+    def enc():
+        _lib.check(lib.nlc_encode_history(mh, hist.data_ptr(), Kl, H, B, pbuf.data_ptr(), mode, _lib.current_stream_ptr()))
+    ms_enc, _, _ = timed(enc, max(3, args.steps), 2)
+
+    if rank == 0:
+        peaks = load_peaks()
+        steps_per_plan = K * H
+        value = steps_per_plan / (ms_dev * 1e-3)
+        e2e = steps_per_plan / (ms_e2e * 1e-3)
+        enc_flop = ENCODER_FLOP * Kl * H
+        achieved = enc_flop / (ms_enc * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"encode_{args.math}_{args.workload}_n{world}")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "plan_latency_ms": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "env": env, "K": K, "H": H, "S": inp["S"], "hidden": 128, "history_window": B,
+                       "parallelism": f"K-sharded x{world}", "math": args.math, "noise": "on-device Philox4x32-10",
+                       "l2": "flushed between timed steps (256 MiB fill)", "keep_states": True},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 4 * (nx + B * nu),
+                    "d2h_bytes_per_step": 4 * nu},
+            "gpu_launches": launches * world,
+            "roofline": {"bound": "tensor", "kernel": "encode_gru_kernel" if args.math == "fp32" else "encode_tc_kernel",
+                         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"],
+                         "kernel_ms": ms_enc, "flop_per_launch": enc_flop,
+                         "whole_step_achieved": HOISTED_FLOP[env] * steps_per_plan / (ms_dev * 1e-3) / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(env, K, H, args.cpu_samples)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tc_split3", "tc_fp16"])
+    ap.add_argument("--cpu-samples", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    env, K, H, desc = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, env, K, H, desc)
+    else:
+        run_gpu(args, env, K, H, desc)
+
+
+if __name__ == "__main__":
+    main()

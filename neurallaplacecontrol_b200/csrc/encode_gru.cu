@@ -11,6 +11,8 @@
 // transposed (hT[unit][window]) and ping-pongs between two buffers: one __syncthreads per GRU cell.
 // Work skipped relative to the literal reference: products with the zero initial hidden state
 // ("hoisted" FLOP count of SURVEY 8d).
+#include <stddef.h>
+
 #include "common.cuh"
 
 namespace nlc {
@@ -34,12 +36,13 @@ struct EncSmem {
   float w_ih0[kG3 * kMaxNu];
   float b_ih0[kG3], b_hh0[kG3], b_ih1[kG3], b_hh1[kG3];
   float w_out[2 * kHg];
+  alignas(16) float h0[2][kHg * kEncRows];
+  alignas(16) float h1[2][kHg * kEncRows];
+  alignas(16) float act[kEncRows * 8 * kMaxNu];  // [row][B][gin], B <= 8
   float b_out[2];
   float act_mean[kMaxNu], act_inv_std[kMaxNu];
-  float h0[2][kHg * kEncRows];
-  float h1[2][kHg * kEncRows];
-  float act[kEncRows * 8 * kMaxNu];  // [row][B][gin], B <= 8
 };
+static_assert(offsetof(EncSmem, h0) % 16 == 0 && offsetof(EncSmem, h1) % 16 == 0 && offsetof(EncSmem, w_ih1) % 16 == 0, "float4 alignment");
 
 // acc[g][i][j] += sum_k aT[k][4rg+i] * WT[k][64g + 4ug + j]
 __device__ __forceinline__ void gemm3(const float* __restrict__ WT, const float* __restrict__ aT, int rg, int ug,

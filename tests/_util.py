@@ -33,7 +33,7 @@ def weights(env, calibrated=False, dtype=torch.float64, shift=-4.0):
 
 def relerr(ref, got):
     """max |ref-got| / max |ref|  (the tolerance form used for every floating-point bound)."""
-    ref = torch.as_tensor(ref, dtype=torch.float64)
+    ref = torch.as_tensor(ref).detach().cpu().to(torch.float64)
     got = torch.as_tensor(got).detach().cpu().to(torch.float64)
     denom = max(ref.abs().max().item(), 1e-30)
     return (ref - got.reshape(ref.shape)).abs().max().item() / denom
