@@ -243,6 +243,12 @@ int nlc_planner_command_host(nlc_planner_t p, const double* state_host, const do
 int nlc_ilt_fourier(const float* F_dev, const float* t_dev, int t_per_row, int64_t N, int n_t, int S,
                     float* out_dev, void* stream);
 
+/* Self-test of the tcgen05 operand layout used by the tensor-core encoder (no reference counterpart):
+ * D_dev[128][N] = A_dev[128][64] . B_dev[n_off : n_off+N][64]^T, fp32 in/out, operands split to fp16 hi(+lo) on
+ * the device exactly as the encoder does.                                                           */
+int nlc_selftest_umma_gemm(const float* A_dev, const float* B_dev, int n_rows_b, int n_off, int N, int split3,
+                           float* D_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

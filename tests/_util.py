@@ -37,3 +37,17 @@ def relerr(ref, got):
     got = torch.as_tensor(got).detach().cpu().to(torch.float64)
     denom = max(ref.abs().max().item(), 1e-30)
     return (ref - got.reshape(ref.shape)).abs().max().item() / denom
+
+
+def action_relerr(ref_action, got_action, ref_U, u_scale):
+    """|action - ref| relative to the magnitude of the planned control sequence it heads (max |U| * u_scale).
+
+    The returned action U[0]*u_scale is a softmax-weighted mean of O(1) noise samples that largely cancel; with costs of
+    magnitude ~50 at lambda = 1 one fp32 ulp of a cost (4e-6) moves its exponential weight by 4e-6, so an ABSOLUTE error
+    of ~1e-5 on the action is the floor of any 32-bit evaluation (the CPU oracle run in fp32 is 100x further away).  A
+    head that happens to be near zero would turn that floor into an arbitrarily large ratio to itself, so the action is
+    measured against the scale of the sequence, like every other tensor (`relerr` divides by max |ref|)."""
+    ref_action = torch.as_tensor(ref_action).detach().cpu().to(torch.float64).reshape(-1)
+    got = torch.as_tensor(got_action).detach().cpu().to(torch.float64).reshape(-1)
+    scale = float(torch.as_tensor(ref_U).detach().cpu().to(torch.float64).abs().max()) * float(u_scale)
+    return (ref_action - got).abs().max().item() / max(scale, 1e-30)

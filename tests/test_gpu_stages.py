@@ -197,3 +197,78 @@ def test_cfg3_full_size_properties():
     p.command(state, buf)
     assert float(p.U.abs().max()) == 0.0
     assert float((p.cost_total - p.cost_total[0]).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tcgen05 path
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,n_off,rows_b", [(64, 0, 64), (128, 0, 192), (192, 0, 192), (64, 128, 192), (256, 0, 256)])
+@pytest.mark.parametrize("split3", [0, 1])
+def test_umma_selftest_gemm(N, n_off, rows_b, split3):
+    """Operand layout / descriptors / TMEM addressing of the tensor-core encoder: D = A B[n_off:n_off+N]^T.
+    split3 (fp16 hi+lo, 3 MMAs, fp32 accumulate) must be fp32-class; the single pass carries fp16 input rounding."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator().manual_seed(N + n_off + split3)
+    A = (torch.rand(128, 64, generator=g, dtype=torch.float64) * 2 - 1)
+    Bm = (torch.randn(rows_b, 64, generator=g, dtype=torch.float64) * 0.3)
+    D = torch.full((128, N), float("nan"), device="cuda")
+    Ad, Bd = A.float().cuda().contiguous(), Bm.float().cuda().contiguous()
+    L.check(lib.nlc_selftest_umma_gemm(Ad.data_ptr(), Bd.data_ptr(), rows_b, n_off, N, split3, D.data_ptr(), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float().double() @ Bm.float().double()[n_off:n_off + N].T
+    err = relerr(ref, D)
+    assert err < (2e-6 if split3 else 2e-3), err
+
+
+@pytest.mark.parametrize("mode,tol", [("tc_split3", 2e-5), ("tc_fp16", 5e-3)])
+@pytest.mark.parametrize("env", ["oderl-pendulum", "oderl-acrobot"])
+def test_tc_encoder_matches_reference(env, mode, tol):
+    """ReverseGRUEncoder on tcgen05 vs the reference's own encoder output (golden p_action) and vs the FFMA kernel on
+    a multi-tile, ragged history (K*T = 3*128 + 37 windows)."""
+    import ctypes as C
+
+    from oracle import costs
+    from test_gpu_parity import make_model
+    from _util import load, short
+
+    L = _lib()
+    lib = L.load()
+    g = load("model_fwd_" + short(env))
+    m = make_model(env, calibrated=False, math_mode=mode)
+    obs, act = torch.from_numpy(g["obs"]).cuda(), torch.from_numpy(g["act"]).cuda()
+    m(obs, act, torch.from_numpy(g["ts_fixed"]).cuda())
+    assert relerr(g["p_action"], m.last_p_action) < tol, relerr(g["p_action"], m.last_p_action)
+    nx, nu = costs.ENV_DIMS[env]
+    K, T, B = 11, 38, 4  # 418 windows (ragged last tile)... plus a second shape below
+    gen = torch.Generator().manual_seed(3)
+    hist = ((torch.rand(K, B - 1 + T, nu, generator=gen) * 2 - 1) * costs.ENV_ACT_HIGH[env]).cuda().contiguous()
+    h = m.set_prediction_time(DT)
+    outs = {}
+    for name in ("fp32", mode):
+        p = torch.full((K, T, 2), float("nan"), device="cuda")
+        L.check(lib.nlc_encode_history(h, hist.data_ptr(), K, T, B, p.data_ptr(), L.MATH_MODES[name], L.current_stream_ptr()))
+        torch.cuda.synchronize()
+        outs[name] = p
+    assert torch.isfinite(outs[mode]).all()
+    assert relerr(outs["fp32"], outs[mode]) < tol, relerr(outs["fp32"], outs[mode])
+
+
+@pytest.mark.parametrize("mode,tol", [("tc_split3", 1e-4), ("tc_fp16", 2e-2)])
+def test_tc_plan_cfg1(mode, tol):
+    """BASELINE config 1 end to end with the tensor-core encoder.  tc_split3 holds the fp32 bound (1e-4); the
+    single-pass fp16 mode is the stated looser bound."""
+    from oracle.gen_golden import START_STATE, injected_noise
+    from test_gpu_parity import _run_plan
+    from _util import action_relerr, load
+
+    env = "oderl-pendulum"
+    g = load("plan_cfg1_pendulum_K1000_H20")
+    K, T, nu = 1000, 20, 1
+    gg = {"in_U": np.zeros((T, nu)), "in_buffer": np.zeros((4, nu)), "in_state": np.array(START_STATE[env]),
+          "in_noise": injected_noise(K, T, nu, seed=int(g["noise_seed"])).numpy()}
+    planner, out = _run_plan(env, gg, calibrated=True, math_mode=mode)
+    assert relerr(g["cost_total"], out["cost_total"]) < tol
+    assert relerr(g["states_last"], out["states"][:, -1]) < tol
+    assert relerr(g["U"], out["U"]) < tol * (1 if mode == "tc_split3" else 5)
+    assert action_relerr(g["action"], out["action"], g["U"], 2.0) < tol * (1 if mode == "tc_split3" else 5)
