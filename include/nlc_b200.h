@@ -249,6 +249,11 @@ int nlc_ilt_fourier(const float* F_dev, const float* t_dev, int t_per_row, int64
 int nlc_selftest_umma_gemm(const float* A_dev, const float* B_dev, int n_rows_b, int n_off, int N, int split3,
                            float* D_dev, void* stream);
 
+/* Same self-test with the A operand staged in tensor memory (the fused rollout's operand path):
+ * D_dev[128][N] = A_dev[128][Kdim] . B_dev[0:N][Kdim]^T, Kdim 64 or 128.                             */
+int nlc_selftest_umma_gemm_ts(const float* A_dev, const float* B_dev, int n_rows_b, int N, int Kdim, int split3,
+                              float* D_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,11 @@ struct ModelDev {
   // fp16 hi/lo splits of the three recurrent matrices in the tcgen05 canonical layout (see
   // encode_tc.cu); [3 matrices][2 (hi,lo)][3Hg * Hg] halves
   void* enc_tc_w;
+  // fp16 hi/lo operand images of the representation MLP for the tcgen05 rollout (rollout_tc.cu):
+  // mlp_tc_w2 [2 (hi,lo)][128 x 128], mlp_tc_w3 [2][N3t x 128] with the pair-permuted rows of w3_t, zero padded
+  void* mlp_tc_w2;
+  void* mlp_tc_w3;
+  float* b3_tc;     // [N3t] pair-permuted, zero padded
   // ---- representation MLP (w_nl.py:32-63) --------------------------------------------------
   float* w1_full_t; // [2S+nx+2][Hm]  unfolded first layer (per-sample-time forward)
   float* b1_raw;    // [Hm]
@@ -89,7 +94,7 @@ struct ModelHost {  // fp64 copies kept for re-folding at another prediction tim
 
 struct nlc_model_s {
   int device;
-  int nx, nu, gin, Hm, Hg, S, N3, N3p;
+  int nx, nu, gin, Hm, Hg, S, N3, N3p, N3t;  // N3t: N3 rounded up to the MMA's N granularity (16)
   int normalize, normalize_time, encode_obs_time;
   double dt, ts_pred, t_norm;
   nlc::ModelDev d;

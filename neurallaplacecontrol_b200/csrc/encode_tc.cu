@@ -16,8 +16,9 @@
 //                 epi A(s+1) || MMA B(s)   ->   epi B(s) || MMA A(s+2)   ->   ...
 //              Completion is tracked with tcgen05.commit on two mbarriers; shared-memory operands are single
 //              buffered (a state is overwritten only after the commit of every MMA that reads it).
-//   threads    8 warps; warp w owns TMEM lanes 32(w&3).. (its 32 windows) and hidden units 32(w>>2)..; each thread
-//              keeps its window's 32+32 fp32 hidden values in registers, so the fp16 images are write-only.
+//   threads    16 warps; warp w owns TMEM lanes 32(w&3).. (its 32 windows) and hidden units 16(w>>2)..; each thread
+//              keeps its window's 16+16 fp32 hidden values in registers, so the fp16 images are write-only.
+//              (The epilogue is MUFU/issue bound, not MMA bound: 16 warps double the latency hiding of 8.)
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -31,6 +32,8 @@ using namespace umma;
 constexpr int kTcRows = 128;
 constexpr int kTcHg = 64;
 constexpr int kTcG3 = 192;
+constexpr int kTcThreads = 512;
+constexpr int kTcUnits = 16;  // hidden units per thread
 constexpr uint32_t kOpBytes = kTcRows * kTcHg * 2;  // one fp16 A-operand image (16 KB)
 constexpr uint32_t kWBytes = kTcG3 * kTcHg * 2;     // one fp16 weight image (24 KB)
 constexpr uint32_t kLbo = 128, kSbo = (kTcHg / 8) * 128;  // K-major no-swizzle, K = 64
@@ -52,7 +55,7 @@ struct EncTcSmem {
   alignas(16) float w_ih0[kTcG3 * kMaxNu];
   alignas(16) float w_out[2 * kTcHg];
   alignas(16) float act[kTcRows * 8];  // [row][B*gin], B*gin <= 8
-  alignas(16) float pout[kTcRows * 2];
+  alignas(16) float pout[3][kTcRows * 2];
   float b_out[2];
   float act_mean[kMaxNu], act_inv_std[kMaxNu];
   alignas(8) uint64_t bar_a, bar_b;
@@ -66,6 +69,31 @@ __device__ __forceinline__ float sigmoid_fast(float x) {  // abs error <= ~3e-7 
   return r;
 }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, sigmoid_fast(2.0f * x), -1.0f); }
+__device__ __forceinline__ float tanh_mufu(float x) {  // one MUFU, |error| <= 2^-10.99: single-pass fp16 mode only
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GRU cell update for one hidden unit from the biased pre-activations.  kAccurate: 2 ex2 + 1 shared rcp for (r, z),
+// ex2 + rcp for n (5 MUFU, abs error ~3e-7); otherwise 3 tanh.approx (the fp16 single-pass mode's accuracy class).
+template <bool kAccurate>
+__device__ __forceinline__ float gru_unit(float pre_r, float pre_z, float gi_n, float gh_n, float h_old) {
+  float r, z, n;
+  if (kAccurate) {
+    const float ea = ex2_approx(-1.44269504088896f * pre_r), eb = ex2_approx(-1.44269504088896f * pre_z);
+    const float da = 1.0f + ea, db = 1.0f + eb;
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(da * db));
+    r = db * inv;
+    z = da * inv;
+    n = tanh_fast(fmaf(r, gh_n, gi_n));
+  } else {
+    r = fmaf(0.5f, tanh_mufu(0.5f * pre_r), 0.5f);
+    z = fmaf(0.5f, tanh_mufu(0.5f * pre_z), 0.5f);
+    n = tanh_mufu(fmaf(r, gh_n, gi_n));
+  }
+  return fmaf(z, h_old - n, n);  // (1 - z) n + z h
+}
 
 // 4 (x3) MMAs: D[128 x N] (+)= A[128 x 64] * B[N x 64]^T
 template <bool kSplit3>
@@ -85,9 +113,9 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint3
 
 // this thread's 32 hidden values -> fp16 hi (+lo) A-operand image rows
 template <bool kSplit3>
-__device__ __forceinline__ void store_operand(unsigned char* img_hi, unsigned char* img_lo, int row, int unit0, const float (&h)[32]) {
+__device__ __forceinline__ void store_operand(unsigned char* img_hi, unsigned char* img_lo, int row, int unit0, const float (&h)[kTcUnits]) {
 #pragma unroll
-  for (int g8 = 0; g8 < 4; ++g8) {
+  for (int g8 = 0; g8 < kTcUnits / 8; ++g8) {
     uint32_t ph[4], pl[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -106,31 +134,32 @@ __device__ __forceinline__ void store_operand(unsigned char* img_hi, unsigned ch
   }
 }
 
-template <bool kSplit3>
-__global__ void __launch_bounds__(256, 1) encode_tc_kernel(EncTcArgs a) {
+template <bool kSplit3, int GIN>
+__global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   EncTcSmem& s = *reinterpret_cast<EncTcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hf = warp >> 2;
-  const int row = 32 * q + lane;   // window within the tile == TMEM lane
-  const int unit0 = 32 * hf;       // first hidden unit this thread owns
-  const int B = a.B, gin = a.gin, BG = B * gin;
+  const int q = warp & 3, grp = warp >> 2;
+  const int row = 32 * q + lane;       // window within the tile == TMEM lane
+  const int unit0 = kTcUnits * grp;    // first hidden unit this thread owns
+  const int B = a.B, BG = B * GIN;
+  constexpr int gin = GIN;
 
   // ---- one-time setup: weight images, biases, barriers, TMEM ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.m.enc_tc_w);
     uint4* dst = reinterpret_cast<uint4*>(&s.w[0][0][0]);
-    for (int i = tid; i < (int)(3 * 2 * kWBytes / 16); i += 256) dst[i] = __ldg(src + i);
-    for (int i = tid; i < 128; i += 256) {
+    for (int i = tid; i < (int)(3 * 2 * kWBytes / 16); i += kTcThreads) dst[i] = __ldg(src + i);
+    for (int i = tid; i < 128; i += kTcThreads) {
       s.brz0[i] = a.m.b_ih0[i] + a.m.b_hh0[i];
       s.brz1[i] = a.m.b_ih1[i] + a.m.b_hh1[i];
     }
-    for (int i = tid; i < 64; i += 256) {
+    for (int i = tid; i < 64; i += kTcThreads) {
       s.bin0[i] = a.m.b_ih0[128 + i]; s.bhn0[i] = a.m.b_hh0[128 + i];
       s.bin1[i] = a.m.b_ih1[128 + i]; s.bhn1[i] = a.m.b_hh1[128 + i];
     }
-    for (int i = tid; i < kTcG3 * gin; i += 256) s.w_ih0[i] = a.m.w_ih0[i];
-    for (int i = tid; i < 2 * kTcHg; i += 256) s.w_out[i] = a.m.w_out[i];
+    for (int i = tid; i < kTcG3 * gin; i += kTcThreads) s.w_ih0[i] = a.m.w_ih0[i];
+    for (int i = tid; i < 2 * kTcHg; i += kTcThreads) s.w_out[i] = a.m.w_out[i];
     if (tid < 2) s.b_out[tid] = a.m.b_out[tid];
     if (tid < gin) { s.act_mean[tid] = a.m.act_mean[tid]; s.act_inv_std[tid] = a.m.act_inv_std[tid]; }
     if (tid == 0) { mbar_init(&s.bar_a, 1); mbar_init(&s.bar_b, 1); mbar_fence_init(); }
@@ -150,12 +179,12 @@ __global__ void __launch_bounds__(256, 1) encode_tc_kernel(EncTcArgs a) {
   const uint32_t n_rows_off = (128 / 8) * kSbo;  // weight rows 128..191 (the n gate)
 
   uint32_t pa = 0, pb = 0;  // mbarrier phase parities
-  float h0r[32], h1r[32];
+  float h0r[kTcUnits], h1r[kTcUnits];
 
   const long long n_tiles = (a.rows + kTcRows - 1) / kTcRows;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * kTcRows;
-    for (int i = tid; i < kTcRows * BG; i += 256) {  // normalised windows (w_nl.py:121), [row][j][u], j = 0 oldest
+    for (int i = tid; i < kTcRows * BG; i += kTcThreads) {  // normalised windows (w_nl.py:121), [row][j][u], j = 0 oldest
       const int r = i / BG, rem = i - r * BG, j = rem / gin, u = rem - j * gin;
       long long grow = row0 + r;
       if (grow >= a.rows) grow = a.rows - 1;
@@ -167,21 +196,20 @@ __global__ void __launch_bounds__(256, 1) encode_tc_kernel(EncTcArgs a) {
 
     // ================= A(0): layer 0, newest entry, zero state (no MMA) =================
     {
-      float x[kMaxNu];
-      for (int v = 0; v < gin; ++v) x[v] = s.act[row * 8 + (B - 1) * gin + v];
+      float x[GIN];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int v = 0; v < GIN; ++v) x[v] = s.act[row * 8 + (B - 1) * gin + v];
+#pragma unroll
+      for (int i = 0; i < kTcUnits; ++i) {
         const int u = unit0 + i;
-        float gr = 0.f, gz = 0.f, gn = 0.f;
-        for (int v = 0; v < gin; ++v) {
+        float gr = s.brz0[u], gz = s.brz0[64 + u], gn = s.bin0[u];
+#pragma unroll
+        for (int v = 0; v < GIN; ++v) {
           gr = fmaf(s.w_ih0[u * gin + v], x[v], gr);
           gz = fmaf(s.w_ih0[(64 + u) * gin + v], x[v], gz);
           gn = fmaf(s.w_ih0[(128 + u) * gin + v], x[v], gn);
         }
-        const float r = sigmoid_fast(gr + s.brz0[u]);
-        const float z = sigmoid_fast(gz + s.brz0[64 + u]);
-        const float n = tanh_fast(gn + s.bin0[u] + r * s.bhn0[u]);
-        h0r[i] = n - z * n;
+        h0r[i] = gru_unit<kSplit3>(gr, gz, gn, s.bhn0[u], 0.0f);
       }
     }
     store_operand<kSplit3>(s.h0[0], s.h0[1], row, unit0, h0r);
@@ -205,28 +233,26 @@ __global__ void __launch_bounds__(256, 1) encode_tc_kernel(EncTcArgs a) {
         // ================= epilogue A(st+1)  ||  MMA B(st) =================
         mbar_wait(&s.bar_a, pa); pa ^= 1;
         fence_after_sync();
-        float x[kMaxNu];
-        for (int v = 0; v < gin; ++v) x[v] = s.act[row * 8 + (B - 2 - st) * gin + v];
+        float x[GIN];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int v = 0; v < GIN; ++v) x[v] = s.act[row * 8 + (B - 2 - st) * gin + v];
+        {
           float ghr[16], ghz[16], ghn[16];
-          tmem_ld16(tlane + kColD0 + unit0 + 16 * c, ghr);
-          tmem_ld16(tlane + kColD0 + 64 + unit0 + 16 * c, ghz);
-          tmem_ld16(tlane + kColD0 + 128 + unit0 + 16 * c, ghn);
+          tmem_ld16(tlane + kColD0 + unit0, ghr);
+          tmem_ld16(tlane + kColD0 + 64 + unit0, ghz);
+          tmem_ld16(tlane + kColD0 + 128 + unit0, ghn);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int u = unit0 + 16 * c + i;
-            float gr = 0.f, gz = 0.f, gn = 0.f;
-            for (int v = 0; v < gin; ++v) {
+          for (int i = 0; i < kTcUnits; ++i) {
+            const int u = unit0 + i;
+            float gr = ghr[i] + s.brz0[u], gz = ghz[i] + s.brz0[64 + u], gn = s.bin0[u];
+#pragma unroll
+            for (int v = 0; v < GIN; ++v) {
               gr = fmaf(s.w_ih0[u * gin + v], x[v], gr);
               gz = fmaf(s.w_ih0[(64 + u) * gin + v], x[v], gz);
               gn = fmaf(s.w_ih0[(128 + u) * gin + v], x[v], gn);
             }
-            const float r = sigmoid_fast(gr + ghr[i] + s.brz0[u]);
-            const float z = sigmoid_fast(gz + ghz[i] + s.brz0[64 + u]);
-            const float n = tanh_fast(gn + s.bin0[u] + r * (ghn[i] + s.bhn0[u]));
-            h0r[16 * c + i] = fmaf(z, h0r[16 * c + i] - n, n);
+            h0r[i] = gru_unit<kSplit3>(gr, gz, gn, ghn[i] + s.bhn0[u], h0r[i]);
           }
         }
         // h0's image is still being read by MMA B(st): wait for its commit before overwriting
@@ -246,23 +272,19 @@ __global__ void __launch_bounds__(256, 1) encode_tc_kernel(EncTcArgs a) {
         fence_after_sync();
       }
       // ================= epilogue B(st)  ||  MMA A(st+2) =================
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         float sr[16], sz[16], gn[16], hn[16];
-        tmem_ld16(tlane + kColRz + unit0 + 16 * c, sr);
-        tmem_ld16(tlane + kColRz + 64 + unit0 + 16 * c, sz);
-        tmem_ld16(tlane + kColIn + unit0 + 16 * c, gn);
-        if (st > 0) tmem_ld16(tlane + kColHn + unit0 + 16 * c, hn);
+        tmem_ld16(tlane + kColRz + unit0, sr);
+        tmem_ld16(tlane + kColRz + 64 + unit0, sz);
+        tmem_ld16(tlane + kColIn + unit0, gn);
+        if (st > 0) tmem_ld16(tlane + kColHn + unit0, hn);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int u = unit0 + 16 * c + i;
-          const float r = sigmoid_fast(sr[i] + s.brz1[u]);
-          const float z = sigmoid_fast(sz[i] + s.brz1[64 + u]);
+        for (int i = 0; i < kTcUnits; ++i) {
+          const int u = unit0 + i;
           const float hh = st > 0 ? hn[i] : 0.0f;
-          const float n = tanh_fast(gn[i] + s.bin1[u] + r * (hh + s.bhn1[u]));
-          const float hold = st > 0 ? h1r[16 * c + i] : 0.0f;
-          h1r[16 * c + i] = fmaf(z, hold - n, n);
+          const float hold = st > 0 ? h1r[i] : 0.0f;
+          h1r[i] = gru_unit<kSplit3>(sr[i] + s.brz1[u], sz[i] + s.brz1[64 + u], gn[i] + s.bin1[u], hh + s.bhn1[u], hold);
         }
       }
       if (st + 1 < B) {
@@ -283,15 +305,17 @@ __global__ void __launch_bounds__(256, 1) encode_tc_kernel(EncTcArgs a) {
     // ================= linear_out on the top layer's last state (w_nl.py:29) =================
     float o0 = 0.f, o1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < kTcUnits; ++i) {
       o0 = fmaf(s.w_out[unit0 + i], h1r[i], o0);
       o1 = fmaf(s.w_out[kTcHg + unit0 + i], h1r[i], o1);
     }
-    if (hf == 1) { s.pout[row * 2] = o0; s.pout[row * 2 + 1] = o1; }
+    if (grp > 0) { s.pout[grp - 1][row * 2] = o0; s.pout[grp - 1][row * 2 + 1] = o1; }
     fence_before_sync();  // this tile's TMEM loads are ordered before the next tile's MMAs
     __syncthreads();
-    if (hf == 0 && row0 + row < a.rows) {
-      float2 o = make_float2(o0 + s.pout[row * 2] + s.b_out[0], o1 + s.pout[row * 2 + 1] + s.b_out[1]);
+    if (grp == 0 && row0 + row < a.rows) {
+      float2 o;
+      o.x = ((o0 + s.pout[0][row * 2]) + s.pout[1][row * 2]) + s.pout[2][row * 2] + s.b_out[0];
+      o.y = ((o1 + s.pout[0][row * 2 + 1]) + s.pout[1][row * 2 + 1]) + s.pout[2][row * 2 + 1] + s.b_out[1];
       *reinterpret_cast<float2*>(a.p_out + (row0 + row) * 2) = o;
     }
     // the next tile's first barrier (after the window load) separates these pout/act reads from their rewrites
@@ -307,16 +331,13 @@ int launch_encode_tc(nlc_model_s* m, const float* hist, int K, int T, int B, flo
   a.rows = (long long)K * T;
   a.m = m->d;
   const int smem = (int)sizeof(EncTcSmem) + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NLC_CUDA_OK(cudaFuncSetAttribute(encode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    NLC_CUDA_OK(cudaFuncSetAttribute(encode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  NLC_REQUIRE(m->gin == 1 || m->gin == 2, NLC_ERR_SHAPE, "tcgen05 encoder: GRU input width %d has no instantiation", m->gin);
+  void (*kern)(EncTcArgs) = split3 ? (m->gin == 1 ? encode_tc_kernel<true, 1> : encode_tc_kernel<true, 2>)
+                                   : (m->gin == 1 ? encode_tc_kernel<false, 1> : encode_tc_kernel<false, 2>);
+  NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long n_tiles = (a.rows + kTcRows - 1) / kTcRows;
   const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
-  if (split3) encode_tc_kernel<true><<<grid, 256, smem, stream>>>(a);
-  else encode_tc_kernel<false><<<grid, 256, smem, stream>>>(a);
+  kern<<<grid, kTcThreads, smem, stream>>>(a);
   NLC_LAUNCH_OK("encode_tc_kernel");
   return NLC_OK;
 }
@@ -374,9 +395,95 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// Same product with the A operand staged in TENSOR MEMORY (tcgen05.st by the owning threads, tcgen05.mma reading
+// [a_tmem]): the operand path of the fused rollout kernel.  K = 128 here (two 64-wide halves of A are given).
+template <bool kSplit3>
+__global__ void __launch_bounds__(128, 1) umma_selftest_ts_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                                  int n_rows_b, int N, int Kdim, float* __restrict__ D) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* b_img[2] = {smem_raw, smem_raw + 256 * 128 * 2};
+  __shared__ alignas(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < n_rows_b * Kdim; i += 128) {
+    const int r = i / Kdim, k = i - r * Kdim;
+    const float v = Bm[i];
+    const __half h = __float2half_rn(v);
+    reinterpret_cast<__half*>(b_img[0])[tc_core_offset(r, k, Kdim)] = h;
+    reinterpret_cast<__half*>(b_img[1])[tc_core_offset(r, k, Kdim)] = __float2half_rn(v - __half2float(h));
+  }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t tlane = tmem + ((uint32_t)(32 * warp) << 16);
+  // A operand: columns [256, 256+Kdim/2) hi, [384, 384+Kdim/2) lo ; accumulator at columns [0, N)
+  const uint32_t colAhi = 256, colAlo = 384;
+  const int row = 32 * warp + lane;
+  for (int c0 = 0; c0 < Kdim / 2; c0 += 16) {
+    uint32_t ph[16], pl[16];
+    for (int i = 0; i < 16; ++i) {
+      const float x0 = A[(size_t)row * Kdim + 2 * (c0 + i)], x1 = A[(size_t)row * Kdim + 2 * (c0 + i) + 1];
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half2 hh = __halves2half2(h0, h1);
+      const __half2 ll = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+      ph[i] = *reinterpret_cast<const uint32_t*>(&hh);
+      pl[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    tmem_st16(tlane + colAhi + c0, ph);
+    tmem_st16(tlane + colAlo + c0, pl);
+  }
+  tmem_st_wait();
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    fence_after_sync();
+    const uint32_t idesc = idesc_f16_f32(kTcRows, N);
+    const uint32_t sbo = (uint32_t)(Kdim / 8) * 128;
+    for (int ks = 0; ks < Kdim / 16; ++ks) {
+      const uint32_t boff = ks * 2 * kLbo;
+      mma_f16_ts(tmem, tmem + colAhi + 8 * ks, smem_desc(smem_u32(b_img[0]) + boff, kLbo, sbo), idesc, ks > 0 ? 1u : 0u);
+      if (kSplit3) {
+        mma_f16_ts(tmem, tmem + colAlo + 8 * ks, smem_desc(smem_u32(b_img[0]) + boff, kLbo, sbo), idesc, 1u);
+        mma_f16_ts(tmem, tmem + colAhi + 8 * ks, smem_desc(smem_u32(b_img[1]) + boff, kLbo, sbo), idesc, 1u);
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tlane + c0, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 16 && c0 + i < N; ++i) D[(size_t)row * N + c0 + i] = v[i];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace nlc
 
 using namespace nlc;
+
+extern "C" int nlc_selftest_umma_gemm_ts(const float* A_dev, const float* B_dev, int n_rows_b, int N, int Kdim, int split3,
+                                         float* D_dev, void* stream) {
+  NLC_REQUIRE(A_dev && B_dev && D_dev, NLC_ERR_ARG, "nlc_selftest_umma_gemm_ts: null pointer");
+  NLC_REQUIRE(n_rows_b % 8 == 0 && n_rows_b <= 256 && N % 16 == 0 && N >= 16 && N <= n_rows_b && (Kdim == 64 || Kdim == 128),
+              NLC_ERR_SHAPE, "nlc_selftest_umma_gemm_ts: bad shape");
+  const int smem = 2 * 256 * 128 * 2 + 128;
+  NLC_CUDA_OK(cudaFuncSetAttribute(umma_selftest_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  NLC_CUDA_OK(cudaFuncSetAttribute(umma_selftest_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (split3) umma_selftest_ts_kernel<true><<<1, 128, smem, s>>>(A_dev, B_dev, n_rows_b, N, Kdim, D_dev);
+  else umma_selftest_ts_kernel<false><<<1, 128, smem, s>>>(A_dev, B_dev, n_rows_b, N, Kdim, D_dev);
+  NLC_LAUNCH_OK("umma_selftest_ts_kernel");
+  return NLC_OK;
+}
 
 extern "C" int nlc_selftest_umma_gemm(const float* A_dev, const float* B_dev, int n_rows_b, int n_off, int N, int split3,
                                       float* D_dev, void* stream) {

@@ -130,10 +130,10 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
                         d->enc_out_w, d->enc_out_b, d->mlp_w0, d->mlp_b0, d->mlp_w2, d->mlp_b2, d->mlp_w4, d->mlp_b4};
   for (const void* p : ptrs) NLC_REQUIRE(p != nullptr, NLC_ERR_ARG, "null weight pointer in nlc_model_desc");
 
-  const int Hg = Hm / 2, G3 = 3 * Hg, L = nx + 2, in0 = 2 * S + L, N3 = 2 * nx * S, N3p = (N3 + 3) / 4 * 4;
+  const int Hg = Hm / 2, G3 = 3 * Hg, L = nx + 2, in0 = 2 * S + L, N3 = 2 * nx * S, N3p = (N3 + 3) / 4 * 4, N3t = (N3 + 15) / 16 * 16;
   nlc_model_s* m = new nlc_model_s();
   memset(&m->d, 0, sizeof(m->d));
-  m->device = device; m->nx = nx; m->nu = nu; m->gin = gin; m->Hm = Hm; m->Hg = Hg; m->S = S; m->N3 = N3; m->N3p = N3p;
+  m->device = device; m->nx = nx; m->nu = nu; m->gin = gin; m->Hm = Hm; m->Hg = Hg; m->S = S; m->N3 = N3; m->N3p = N3p; m->N3t = N3t;
   m->normalize = d->normalize; m->normalize_time = d->normalize_time; m->encode_obs_time = d->encode_obs_time;
   m->dt = d->dt; m->arena = nullptr;
 
@@ -149,6 +149,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   // tensor-core operand image of the three recurrent GRU matrices: fp16 hi/lo, UMMA canonical layout
   const size_t tc_halves = (size_t)3 * 2 * G3 * Hg;
   size_t o_tc = A.add(tc_halves / 2);
+  size_t o_tc_w2 = A.add((size_t)2 * Hm * Hm / 2), o_tc_w3 = A.add((size_t)2 * N3t * Hm / 2), o_b3tc = A.add(N3t);
 
   for (int i = 0; i < G3 * gin; ++i) put(o_w_ih0, i, d->gru_w_ih_l0[i]);
   for (int i = 0; i < G3; ++i) {
@@ -201,6 +202,21 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
       nlc::tc_pack_weight_split(mats[w], G3, Hg, tc + (size_t)w * 2 * G3 * Hg, tc + (size_t)w * 2 * G3 * Hg + (size_t)G3 * Hg);
   }
 
+  {
+    uint16_t* w2i = reinterpret_cast<uint16_t*>(A.data.data() + o_tc_w2);
+    nlc::tc_pack_weight_split(d->mlp_w2, Hm, Hm, w2i, w2i + (size_t)Hm * Hm);
+    std::vector<double> w3p((size_t)N3t * Hm, 0.0);
+    for (int c = 0; c < nx; ++c)
+      for (int k = 0; k < S; ++k)
+        for (int part = 0; part < 2; ++part) {
+          const int src = (part * nx + c) * S + k, dst = 2 * (c * S + k) + part;
+          for (int h = 0; h < Hm; ++h) w3p[(size_t)dst * Hm + h] = d->mlp_w4[(size_t)src * Hm + h];
+          put(o_b3tc, dst, d->mlp_b4[src]);
+        }
+    uint16_t* w3i = reinterpret_cast<uint16_t*>(A.data.data() + o_tc_w3);
+    nlc::tc_pack_weight_split(w3p.data(), N3t, Hm, w3i, w3i + (size_t)N3t * Hm);
+  }
+
   m->h.w0 = new double[(size_t)Hm * in0];
   m->h.b0 = new double[Hm];
   memcpy(m->h.w0, d->mlp_w0, sizeof(double) * Hm * in0);
@@ -219,7 +235,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   m->d.w_ih0 = base + o_w_ih0; m->d.b_ih0 = base + o_b_ih0; m->d.b_hh0 = base + o_b_hh0;
   m->d.w_hh0_t = base + o_hh0; m->d.w_ih1_t = base + o_ih1; m->d.w_hh1_t = base + o_hh1;
   m->d.b_ih1 = base + o_b_ih1; m->d.b_hh1 = base + o_b_hh1; m->d.w_out = base + o_wout; m->d.b_out = base + o_bout;
-  m->d.enc_tc_w = base + o_tc;
+  m->d.enc_tc_w = base + o_tc; m->d.mlp_tc_w2 = base + o_tc_w2; m->d.mlp_tc_w3 = base + o_tc_w3; m->d.b3_tc = base + o_b3tc;
   m->d.w1_full_t = base + o_w1full; m->d.b1_raw = base + o_b1raw; m->d.w1x_t = base + o_w1x; m->d.b1_fold = base + o_b1f;
   m->d.w2_t = base + o_w2; m->d.b2 = base + o_b2; m->d.w3_t = base + o_w3; m->d.b3 = base + o_b3;
   m->d.ilt_phase = base + o_phase; m->d.ilt_weight = base + o_weight;

@@ -11,6 +11,8 @@
 // 128->128, L3 128->2*nx*S with the sphere->complex map and the Fourier weights applied in the epilogue
 // (term = w_k * tan(phi/2+pi/4) * cos(theta + k*pi*t/T)), a deterministic fixed-order sum over k, the
 // residual state update and the env cost.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "env_cost.cuh"
 
@@ -236,6 +238,23 @@ int launch_rollout_fp32(nlc_model_s* m, const nlc_rollout_opts* o, const float* 
   return NLC_OK;
 }
 
+int launch_rollout_tc(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
+                      const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
+                      float* delta_out, int split3, int groups, cudaStream_t stream);
+
+// math_mode dispatch: the tensor-core kernel when it has an instantiation for (nx, S), else the FFMA kernel
+static int launch_rollout(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
+                          const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
+                          float* delta_out, int math_mode, cudaStream_t stream) {
+  if (math_mode != NLC_MATH_FP32 && 2 * m->nx * m->S <= 256) {
+    const char* g = getenv("NLC_ROLLOUT_GROUPS");
+    int rc = launch_rollout_tc(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out,
+                               math_mode == NLC_MATH_TC_SPLIT3, (g && atoi(g) == 2) ? 2 : 4, stream);
+    if (rc != NLC_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_rollout_fp32(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out, stream);
+}
+
 int launch_rollout_analytic(const nlc_rollout_opts* o, int nx, const float* state, int sps, const float* hist,
                             const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
                             cudaStream_t stream);
@@ -266,10 +285,8 @@ extern "C" int nlc_rollout_cost(nlc_model_t m, const nlc_rollout_opts* o, const 
   NLC_REQUIRE(m->nx == env_nx[o->env] && m->nu == nu, NLC_ERR_SHAPE, "model dims (%d,%d) do not match env %d", m->nx, m->nu, o->env);
   NLC_REQUIRE(math_mode == NLC_MATH_FP32 || math_mode == NLC_MATH_TC_SPLIT3 || math_mode == NLC_MATH_TC_FP16, NLC_ERR_ARG,
               "unknown math_mode %d", math_mode);
-  // The rollout's MLP runs on the FFMA path in every mode for now; math_mode selects the encoder's
-  // arithmetic (the tcgen05 rollout is tracked in DESIGN.md).
-  return launch_rollout_fp32(m, o, state_dev, state_per_sample, p_dev, hist_dev, pert_cost_dev, K, T, B, nu,
-                             cost_total_dev, states_dev, nullptr, s);
+  return launch_rollout(m, o, state_dev, state_per_sample, p_dev, hist_dev, pert_cost_dev, K, T, B, nu, cost_total_dev,
+                        states_dev, nullptr, math_mode, s);
 }
 
 // NeuralLaplaceModel.forward (w_nl.py:117-145) at the folded prediction time: encoder over the one
@@ -284,6 +301,6 @@ extern "C" int nlc_model_forward(nlc_model_t m, const float* obs_dev, const floa
   nlc_rollout_opts o;
   o.env = m->nx == 3 ? NLC_ENV_PENDULUM : (m->nx == 5 ? NLC_ENV_CARTPOLE : NLC_ENV_ACROBOT);
   o.state_constraint = 0; o.goal_x = 0.0f; o.dynamics = NLC_DYN_NEURAL_LAPLACE; o.delay = 0; o.dt = (float)m->dt;
-  return launch_rollout_fp32(m, &o, obs_dev, 1, p_action_dev, act_dev, nullptr, K, 1, B, m->gin, nullptr, nullptr, out_dev,
-                             static_cast<cudaStream_t>(stream));
+  return launch_rollout(m, &o, obs_dev, 1, p_action_dev, act_dev, nullptr, K, 1, B, m->gin, nullptr, nullptr, out_dev,
+                        math_mode, static_cast<cudaStream_t>(stream));
 }

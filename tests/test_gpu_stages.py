@@ -272,3 +272,21 @@ def test_tc_plan_cfg1(mode, tol):
     assert relerr(g["states_last"], out["states"][:, -1]) < tol
     assert relerr(g["U"], out["U"]) < tol * (1 if mode == "tc_split3" else 5)
     assert action_relerr(g["action"], out["action"], g["U"], 2.0) < tol * (1 if mode == "tc_split3" else 5)
+
+
+@pytest.mark.parametrize("N,Kdim,rows_b", [(64, 64, 64), (128, 128, 128), (208, 128, 208), (176, 128, 176), (112, 128, 112)])
+@pytest.mark.parametrize("split3", [0, 1])
+def test_umma_selftest_gemm_a_in_tmem(N, Kdim, rows_b, split3):
+    """A operand staged in tensor memory by tcgen05.st (operand path of the fused rollout kernel)."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator().manual_seed(N + Kdim + split3)
+    A = (torch.rand(128, Kdim, generator=g, dtype=torch.float64) * 2 - 1)
+    Bm = (torch.randn(rows_b, Kdim, generator=g, dtype=torch.float64) * 0.3)
+    D = torch.full((128, N), float("nan"), device="cuda")
+    Ad, Bd = A.float().cuda().contiguous(), Bm.float().cuda().contiguous()
+    L.check(lib.nlc_selftest_umma_gemm_ts(Ad.data_ptr(), Bd.data_ptr(), rows_b, N, Kdim, split3, D.data_ptr(), L.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float().double() @ Bm.float().double()[:N].T
+    err = relerr(ref, D)
+    assert err < (2e-6 if split3 else 2e-3), err
