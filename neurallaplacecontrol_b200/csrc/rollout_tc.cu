@@ -54,6 +54,29 @@ __device__ __forceinline__ float rt_sigmoid_fast(float x) {
 }
 __device__ __forceinline__ float rt_tanh_fast(float x) { return fmaf(2.0f, rt_sigmoid_fast(2.0f * x), -1.0f); }
 
+// tan(phi/2 + pi/4) with phi = (pi/2) tanh(u) = tan((pi/2) sigmoid(2u)), through s = sigmoid(-2|u|) in (0, 1/2] (see
+// common.cuh:sphere_radius for the derivation); MUFU ex2/rcp directly: relative error <= ~1.5e-6 for |u| <= 8.
+__device__ __forceinline__ float rt_sphere_radius(float u) {
+  const float e = ex2_approx(-2.88539008177793f * fabsf(u));
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.0f + e));
+  const float x = 1.57079632679489662f * (e * inv);  // (0, pi/4]
+  const float x2 = x * x;
+  const float sn = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.7557319224e-6f, -1.9841269841e-4f), 8.3333333333e-3f), -1.6666666667e-1f), 1.0f);
+  const float cs = fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 2.4801587302e-5f, -1.3888888889e-3f), 4.1666666667e-2f), -0.5f), 1.0f);
+  const float num = u <= 0.0f ? sn : cs, den = u <= 0.0f ? cs : sn;
+  float dinv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(dinv) : "f"(den));
+  return num * dinv;
+}
+// cos(pi * (y + c)) for y in (-1, 1), c in (-1, 1]: exact reduction of the argument to [-1, 1] half-turns, then
+// cos.approx (abs error 2^-21.4 on [-pi, pi]).
+__device__ __forceinline__ float rt_cospi_sum(float y, float c) {
+  float z = y + c;
+  z = fmaf(-2.0f, rintf(0.5f * z), z);
+  return __cosf(3.14159265358979f * z);
+}
+
 // 16 fp32 values -> 8 packed fp16 pairs (hi) and the fp16 residuals (lo)
 template <bool kSplit3>
 __device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&ph)[8], uint32_t (&pl)[8]) {
@@ -103,9 +126,9 @@ __device__ __forceinline__ void l3_chunk(uint32_t tlane, const float* __restrict
     const int pair = 8 * kChunk + i;
     if (pair < NX * S) {
       const int ch = pair / S, k = pair - ch * S;
-      const float theta = 3.14159265358979f * tanh_acc(v[2 * i] + b3[2 * pair]);   // w_nl.py:59
-      const float rad = sphere_radius(v[2 * i + 1] + b3[2 * pair + 1]);            // w_nl.py:60-62 + sphere_to_complex
-      delta[ch] += weight[k] * rad * cos_reduced(theta + phase[k]);
+      const float y = rt_tanh_fast(v[2 * i] + b3[2 * pair]);                       // theta = pi y, w_nl.py:59
+      const float rad = rt_sphere_radius(v[2 * i + 1] + b3[2 * pair + 1]);         // w_nl.py:60-62 + sphere_to_complex
+      delta[ch] = fmaf(weight[k] * rad, rt_cospi_sum(y, phase[k]), delta[ch]);     // phase[] holds k t/T in half-turns
     }
   }
 }
@@ -159,7 +182,7 @@ __global__ void __launch_bounds__(kGroups * 128, 1) rollout_tc_kernel(RollTcArgs
     for (int i = tid; i < Lp * kRtH; i += kThreads) s.w1x[i] = a.m.w1x_t[i];
     for (int i = tid; i < kRtH; i += kThreads) { s.b1[i] = a.m.b1_fold[i]; s.b2[i] = a.m.b2[i]; }
     for (int i = tid; i < N3t; i += kThreads) s.b3[i] = a.m.b3_tc[i];
-    for (int i = tid; i < S; i += kThreads) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
+    for (int i = tid; i < S; i += kThreads) { s.phase[i] = a.m.ilt_phase[i] * 0.318309886183791f; s.weight[i] = a.m.ilt_weight[i]; }
     if (tid < NX) { s.smean[tid] = a.m.state_mean[tid]; s.sinv[tid] = a.m.state_inv_std[tid]; }
     if (tid == 0) { mbar_init(&s.bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&s.tmem_base, kRtTmemCols);
