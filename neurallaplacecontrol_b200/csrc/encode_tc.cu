@@ -52,7 +52,7 @@ struct EncTcSmem {
   alignas(128) unsigned char h0[2][kOpBytes];   // [hi, lo]
   alignas(128) unsigned char h1[2][kOpBytes];
   alignas(16) float brz0[128], bin0[64], bhn0[64], brz1[128], bin1[64], bhn1[64];
-  alignas(16) float w_ih0[kTcG3 * kMaxNu];
+  alignas(16) float w_ih0[3 * kMaxNu * kTcHg];  // [gate][input v][unit]: contiguous over units for 16-byte loads
   alignas(16) float w_out[2 * kTcHg];
   alignas(16) float act[kTcRows * 8];  // [row][B*gin], B*gin <= 8
   alignas(16) float pout[3][kTcRows * 2];
@@ -93,6 +93,36 @@ __device__ __forceinline__ float gru_unit(float pre_r, float pre_z, float gi_n, 
     n = tanh_mufu(fmaf(r, gh_n, gi_n));
   }
   return fmaf(z, h_old - n, n);  // (1 - z) n + z h
+}
+
+__device__ __forceinline__ void lds16(const float* p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+  const float4 t0 = *reinterpret_cast<const float4*>(p), t1 = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+}
+__device__ __forceinline__ void bias_to_tmem8(uint32_t taddr, const float* b8) {
+  float v[8];
+  lds8(b8, v);
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+  tmem_st8(taddr, r);
+}
+// (re-)initialise 16 accumulator columns of this thread's TMEM lane with a bias vector: the next cell's MMAs
+// accumulate on top of it, so no bias is loaded or added in the gate epilogue
+__device__ __forceinline__ void bias_to_tmem(uint32_t taddr, const float* b16) {
+  float v[16];
+  lds16(b16, v);
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+  tmem_st16(taddr, r);
 }
 
 // 4 (x3) MMAs: D[128 x N] (+)= A[128 x 64] * B[N x 64]^T
@@ -158,7 +188,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
       s.bin0[i] = a.m.b_ih0[128 + i]; s.bhn0[i] = a.m.b_hh0[128 + i];
       s.bin1[i] = a.m.b_ih1[128 + i]; s.bhn1[i] = a.m.b_hh1[128 + i];
     }
-    for (int i = tid; i < kTcG3 * gin; i += kTcThreads) s.w_ih0[i] = a.m.w_ih0[i];
+    for (int i = tid; i < kTcG3 * gin; i += kTcThreads) {  // global [3*64][gin] -> [gate][v][unit]
+      const int gu = i / gin, v = i - gu * gin, g = gu >> 6, u = gu & 63;
+      s.w_ih0[(g * kMaxNu + v) * kTcHg + u] = a.m.w_ih0[i];
+    }
     for (int i = tid; i < 2 * kTcHg; i += kTcThreads) s.w_out[i] = a.m.w_out[i];
     if (tid < 2) s.b_out[tid] = a.m.b_out[tid];
     if (tid < gin) { s.act_mean[tid] = a.m.act_mean[tid]; s.act_inv_std[tid] = a.m.act_inv_std[tid]; }
@@ -177,6 +210,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
   const uint32_t w_ih1_hi = smem_u32(s.w[1][0]), w_ih1_lo = smem_u32(s.w[1][1]);
   const uint32_t w_hh1_hi = smem_u32(s.w[2][0]), w_hh1_lo = smem_u32(s.w[2][1]);
   const uint32_t n_rows_off = (128 / 8) * kSbo;  // weight rows 128..191 (the n gate)
+
+  // accumulator columns start out holding the biases (and are reset to them after every read, see bias_to_tmem)
+  bias_to_tmem(tlane + kColD0 + unit0, s.brz0 + unit0);
+  bias_to_tmem(tlane + kColD0 + 64 + unit0, s.brz0 + 64 + unit0);
+  bias_to_tmem(tlane + kColD0 + 128 + unit0, s.bhn0 + unit0);
+  bias_to_tmem(tlane + kColRz + unit0, s.brz1 + unit0);
+  bias_to_tmem(tlane + kColRz + 64 + unit0, s.brz1 + 64 + unit0);
+  bias_to_tmem(tlane + kColIn + unit0, s.bin1 + unit0);
+  bias_to_tmem(tlane + kColHn + unit0, s.bhn1 + unit0);
+  tmem_st_wait();
 
   uint32_t pa = 0, pb = 0;  // mbarrier phase parities
   float h0r[kTcUnits], h1r[kTcUnits];
@@ -200,31 +243,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
 #pragma unroll
       for (int v = 0; v < GIN; ++v) x[v] = s.act[row * 8 + (B - 1) * gin + v];
 #pragma unroll
-      for (int i = 0; i < kTcUnits; ++i) {
-        const int u = unit0 + i;
-        float gr = s.brz0[u], gz = s.brz0[64 + u], gn = s.bin0[u];
+      for (int c = 0; c < 2; ++c) {
+        const int u0 = unit0 + 8 * c;
+        float gr[8], gz[8], gn[8], bh[8];
+        lds8(s.brz0 + u0, gr);
+        lds8(s.brz0 + 64 + u0, gz);
+        lds8(s.bin0 + u0, gn);
+        lds8(s.bhn0 + u0, bh);
 #pragma unroll
         for (int v = 0; v < GIN; ++v) {
-          gr = fmaf(s.w_ih0[u * gin + v], x[v], gr);
-          gz = fmaf(s.w_ih0[(64 + u) * gin + v], x[v], gz);
-          gn = fmaf(s.w_ih0[(128 + u) * gin + v], x[v], gn);
+          float w[8];
+          lds8(s.w_ih0 + (0 * kMaxNu + v) * kTcHg + u0, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gr[i] = fmaf(w[i], x[v], gr[i]);
+          lds8(s.w_ih0 + (1 * kMaxNu + v) * kTcHg + u0, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gz[i] = fmaf(w[i], x[v], gz[i]);
+          lds8(s.w_ih0 + (2 * kMaxNu + v) * kTcHg + u0, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gn[i] = fmaf(w[i], x[v], gn[i]);
         }
-        h0r[i] = gru_unit<kSplit3>(gr, gz, gn, s.bhn0[u], 0.0f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h0r[8 * c + i] = gru_unit<kSplit3>(gr[i], gz[i], gn[i], bh[i], 0.0f);
       }
     }
     store_operand<kSplit3>(s.h0[0], s.h0[1], row, unit0, h0r);
     fence_proxy_async_smem();
+    tmem_st_wait();
     fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
       if (B > 1) {  // A(1): D0 = W_hh0 h0(0)
-        issue_gemm<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo, 192, false);
+        issue_gemm<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo, 192, true);
         mma_commit(&s.bar_a);
       }
       // B(0), input part only (h1 = 0): D1_rz = W_ih1[r,z] h0(0), D1_in = W_ih1[n] h0(0)
-      issue_gemm<kSplit3>(tmem + kColRz, a_h0_hi, a_h0_lo, w_ih1_hi, w_ih1_lo, 128, false);
-      issue_gemm<kSplit3>(tmem + kColIn, a_h0_hi, a_h0_lo, w_ih1_hi + n_rows_off, w_ih1_lo + n_rows_off, 64, false);
+      issue_gemm<kSplit3>(tmem + kColRz, a_h0_hi, a_h0_lo, w_ih1_hi, w_ih1_lo, 128, true);
+      issue_gemm<kSplit3>(tmem + kColIn, a_h0_hi, a_h0_lo, w_ih1_hi + n_rows_off, w_ih1_lo + n_rows_off, 64, true);
       mma_commit(&s.bar_b);
     }
 
@@ -236,35 +292,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
         float x[GIN];
 #pragma unroll
         for (int v = 0; v < GIN; ++v) x[v] = s.act[row * 8 + (B - 2 - st) * gin + v];
-        {
-          float ghr[16], ghz[16], ghn[16];
-          tmem_ld16(tlane + kColD0 + unit0, ghr);
-          tmem_ld16(tlane + kColD0 + 64 + unit0, ghz);
-          tmem_ld16(tlane + kColD0 + 128 + unit0, ghn);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {  // 8 units at a time keeps the transient registers low
+          const int u0 = unit0 + 8 * c;
+          float gr[8], gz[8], ghn[8], gn[8];
+          tmem_ld8(tlane + kColD0 + u0, gr);         // W_hr h + b_ir + b_hr
+          tmem_ld8(tlane + kColD0 + 64 + u0, gz);    // W_hz h + b_iz + b_hz
+          tmem_ld8(tlane + kColD0 + 128 + u0, ghn);  // W_hn h + b_hn
+          lds8(s.bin0 + u0, gn);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < kTcUnits; ++i) {
-            const int u = unit0 + i;
-            float gr = ghr[i] + s.brz0[u], gz = ghz[i] + s.brz0[64 + u], gn = s.bin0[u];
+          for (int v = 0; v < GIN; ++v) {
+            float w[8];
+            lds8(s.w_ih0 + (0 * kMaxNu + v) * kTcHg + u0, w);
 #pragma unroll
-            for (int v = 0; v < GIN; ++v) {
-              gr = fmaf(s.w_ih0[u * gin + v], x[v], gr);
-              gz = fmaf(s.w_ih0[(64 + u) * gin + v], x[v], gz);
-              gn = fmaf(s.w_ih0[(128 + u) * gin + v], x[v], gn);
-            }
-            h0r[i] = gru_unit<kSplit3>(gr, gz, gn, ghn[i] + s.bhn0[u], h0r[i]);
+            for (int i = 0; i < 8; ++i) gr[i] = fmaf(w[i], x[v], gr[i]);
+            lds8(s.w_ih0 + (1 * kMaxNu + v) * kTcHg + u0, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gz[i] = fmaf(w[i], x[v], gz[i]);
+            lds8(s.w_ih0 + (2 * kMaxNu + v) * kTcHg + u0, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gn[i] = fmaf(w[i], x[v], gn[i]);
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h0r[8 * c + i] = gru_unit<kSplit3>(gr[i], gz[i], gn[i], ghn[i], h0r[8 * c + i]);
+          bias_to_tmem8(tlane + kColD0 + u0, s.brz0 + u0);
+          bias_to_tmem8(tlane + kColD0 + 64 + u0, s.brz0 + 64 + u0);
+          bias_to_tmem8(tlane + kColD0 + 128 + u0, s.bhn0 + u0);
         }
         // h0's image is still being read by MMA B(st): wait for its commit before overwriting
         mbar_wait(&s.bar_b, pb); pb ^= 1;
         fence_after_sync();
         store_operand<kSplit3>(s.h0[0], s.h0[1], row, unit0, h0r);
         fence_proxy_async_smem();
+        tmem_st_wait();
         fence_before_sync();
         __syncthreads();
         if (tid == 0 && st + 2 < B) {  // A(st+2): D0 = W_hh0 h0(st+1)
           fence_after_sync();
-          issue_gemm<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo, 192, false);
+          issue_gemm<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo, 192, true);
           mma_commit(&s.bar_a);
         }
       } else {
@@ -272,32 +338,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
         fence_after_sync();
       }
       // ================= epilogue B(st)  ||  MMA A(st+2) =================
-      {
-        float sr[16], sz[16], gn[16], hn[16];
-        tmem_ld16(tlane + kColRz + unit0, sr);
-        tmem_ld16(tlane + kColRz + 64 + unit0, sz);
-        tmem_ld16(tlane + kColIn + unit0, gn);
-        if (st > 0) tmem_ld16(tlane + kColHn + unit0, hn);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int u0 = unit0 + 8 * c;
+        float sr[8], sz[8], gn[8], hn[8];
+        tmem_ld8(tlane + kColRz + u0, sr);       // W_ir x + W_hr h + b_ir + b_hr
+        tmem_ld8(tlane + kColRz + 64 + u0, sz);
+        tmem_ld8(tlane + kColIn + u0, gn);       // W_in x + b_in
+        tmem_ld8(tlane + kColHn + u0, hn);       // W_hn h + b_hn   (just b_hn at st == 0: no hidden product yet)
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < kTcUnits; ++i) {
-          const int u = unit0 + i;
-          const float hh = st > 0 ? hn[i] : 0.0f;
-          const float hold = st > 0 ? h1r[i] : 0.0f;
-          h1r[i] = gru_unit<kSplit3>(sr[i] + s.brz1[u], sz[i] + s.brz1[64 + u], gn[i] + s.bin1[u], hh + s.bhn1[u], hold);
-        }
+        for (int i = 0; i < 8; ++i) h1r[8 * c + i] = gru_unit<kSplit3>(sr[i], sz[i], gn[i], hn[i], st > 0 ? h1r[8 * c + i] : 0.0f);
+        bias_to_tmem8(tlane + kColRz + u0, s.brz1 + u0);
+        bias_to_tmem8(tlane + kColRz + 64 + u0, s.brz1 + 64 + u0);
+        bias_to_tmem8(tlane + kColIn + u0, s.bin1 + u0);
+        bias_to_tmem8(tlane + kColHn + u0, s.bhn1 + u0);
       }
       if (st + 1 < B) {
         store_operand<kSplit3>(s.h1[0], s.h1[1], row, unit0, h1r);
         fence_proxy_async_smem();
+        tmem_st_wait();
         fence_before_sync();
         __syncthreads();
         if (tid == 0) {  // B(st+1): input part from h0(st+1), hidden part from h1(st)
           fence_after_sync();
-          issue_gemm<kSplit3>(tmem + kColRz, a_h0_hi, a_h0_lo, w_ih1_hi, w_ih1_lo, 128, false);
+          issue_gemm<kSplit3>(tmem + kColRz, a_h0_hi, a_h0_lo, w_ih1_hi, w_ih1_lo, 128, true);
           issue_gemm<kSplit3>(tmem + kColRz, a_h1_hi, a_h1_lo, w_hh1_hi, w_hh1_lo, 128, true);
-          issue_gemm<kSplit3>(tmem + kColIn, a_h0_hi, a_h0_lo, w_ih1_hi + n_rows_off, w_ih1_lo + n_rows_off, 64, false);
-          issue_gemm<kSplit3>(tmem + kColHn, a_h1_hi, a_h1_lo, w_hh1_hi + n_rows_off, w_hh1_lo + n_rows_off, 64, false);
+          issue_gemm<kSplit3>(tmem + kColIn, a_h0_hi, a_h0_lo, w_ih1_hi + n_rows_off, w_ih1_lo + n_rows_off, 64, true);
+          issue_gemm<kSplit3>(tmem + kColHn, a_h1_hi, a_h1_lo, w_hh1_hi + n_rows_off, w_hh1_lo + n_rows_off, 64, true);
           mma_commit(&s.bar_b);
         }
       }
@@ -310,7 +378,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
       o1 = fmaf(s.w_out[kTcHg + unit0 + i], h1r[i], o1);
     }
     if (grp > 0) { s.pout[grp - 1][row * 2] = o0; s.pout[grp - 1][row * 2 + 1] = o1; }
-    fence_before_sync();  // this tile's TMEM loads are ordered before the next tile's MMAs
+    tmem_st_wait();
+    fence_before_sync();  // this tile's TMEM loads / bias resets are ordered before the next tile's MMAs
     __syncthreads();
     if (grp == 0 && row0 + row < a.rows) {
       float2 o;

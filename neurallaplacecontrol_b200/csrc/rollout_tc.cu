@@ -92,12 +92,6 @@ __device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&ph)[8], 
   }
 }
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-
 // D[128 x N] = A[128 x 128] (TMEM) * B[N x 128]^T (smem image)
 template <bool kSplit3>
 __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, int N) {
