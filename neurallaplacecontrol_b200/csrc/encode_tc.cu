@@ -54,7 +54,7 @@ struct EncTcSmem {
   alignas(16) float brz0[128], bin0[64], bhn0[64], brz1[128], bin1[64], bhn1[64];
   alignas(16) float w_ih0[3 * kMaxNu * kTcHg];  // [gate][input v][unit]: contiguous over units for 16-byte loads
   alignas(16) float w_out[2 * kTcHg];
-  alignas(16) float act[kTcRows * 8];  // [row][B*gin], B*gin <= 8
+  alignas(16) float act[2][kTcRows * 8];  // double-buffered [row][B*gin], B*gin <= 8
   alignas(16) float pout[3][kTcRows * 2];
   float b_out[2];
   float act_mean[kMaxNu], act_inv_std[kMaxNu];
@@ -225,48 +225,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
   float h0r[kTcUnits], h1r[kTcUnits];
 
   const long long n_tiles = (a.rows + kTcRows - 1) / kTcRows;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row0 = tile * kTcRows;
-    for (int i = tid; i < kTcRows * BG; i += kTcThreads) {  // normalised windows (w_nl.py:121), [row][j][u], j = 0 oldest
+
+  // normalised action windows of a tile (w_nl.py:121): act[buf][row][j][u], j = 0 oldest
+  auto load_windows = [&](long long tile_, int buf_) {
+    const long long row0_ = tile_ * kTcRows;
+    for (int i = tid; i < kTcRows * BG; i += kTcThreads) {
       const int r = i / BG, rem = i - r * BG, j = rem / gin, u = rem - j * gin;
-      long long grow = row0 + r;
+      long long grow = row0_ + r;
       if (grow >= a.rows) grow = a.rows - 1;
       const long long k = grow / a.T;
       const int t = (int)(grow - k * a.T);
-      s.act[r * 8 + rem] = (a.hist[((size_t)k * a.L + t + j) * gin + u] - s.act_mean[u]) * s.act_inv_std[u];
+      s.act[buf_][r * 8 + rem] = (a.hist[((size_t)k * a.L + t + j) * gin + u] - s.act_mean[u]) * s.act_inv_std[u];
     }
-    __syncthreads();
-
-    // ================= A(0): layer 0, newest entry, zero state (no MMA) =================
-    {
-      float x[GIN];
+  };
+  // A(0): layer 0 on the newest window entry (reversed order, w_nl.py:27) from the zero state - no MMA
+  auto cell_a0 = [&](int buf_) {
+    float x[GIN];
 #pragma unroll
-      for (int v = 0; v < GIN; ++v) x[v] = s.act[row * 8 + (B - 1) * gin + v];
+    for (int v = 0; v < GIN; ++v) x[v] = s.act[buf_][row * 8 + (B - 1) * gin + v];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int u0 = unit0 + 8 * c;
-        float gr[8], gz[8], gn[8], bh[8];
-        lds8(s.brz0 + u0, gr);
-        lds8(s.brz0 + 64 + u0, gz);
-        lds8(s.bin0 + u0, gn);
-        lds8(s.bhn0 + u0, bh);
+    for (int c = 0; c < 2; ++c) {
+      const int u0 = unit0 + 8 * c;
+      float gr[8], gz[8], gn[8], bh[8];
+      lds8(s.brz0 + u0, gr);
+      lds8(s.brz0 + 64 + u0, gz);
+      lds8(s.bin0 + u0, gn);
+      lds8(s.bhn0 + u0, bh);
 #pragma unroll
-        for (int v = 0; v < GIN; ++v) {
-          float w[8];
-          lds8(s.w_ih0 + (0 * kMaxNu + v) * kTcHg + u0, w);
+      for (int v = 0; v < GIN; ++v) {
+        float w[8];
+        lds8(s.w_ih0 + (0 * kMaxNu + v) * kTcHg + u0, w);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gr[i] = fmaf(w[i], x[v], gr[i]);
-          lds8(s.w_ih0 + (1 * kMaxNu + v) * kTcHg + u0, w);
+        for (int i = 0; i < 8; ++i) gr[i] = fmaf(w[i], x[v], gr[i]);
+        lds8(s.w_ih0 + (1 * kMaxNu + v) * kTcHg + u0, w);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gz[i] = fmaf(w[i], x[v], gz[i]);
-          lds8(s.w_ih0 + (2 * kMaxNu + v) * kTcHg + u0, w);
+        for (int i = 0; i < 8; ++i) gz[i] = fmaf(w[i], x[v], gz[i]);
+        lds8(s.w_ih0 + (2 * kMaxNu + v) * kTcHg + u0, w);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gn[i] = fmaf(w[i], x[v], gn[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h0r[8 * c + i] = gru_unit<kSplit3>(gr[i], gz[i], gn[i], bh[i], 0.0f);
+        for (int i = 0; i < 8; ++i) gn[i] = fmaf(w[i], x[v], gn[i]);
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h0r[8 * c + i] = gru_unit<kSplit3>(gr[i], gz[i], gn[i], bh[i], 0.0f);
     }
+  };
+  // publish h0r as the A operand, then (one thread) start A(1): D0 += W_hh0 h0(0)
+  auto publish_h0_and_issue_a1 = [&]() {
     store_operand<kSplit3>(s.h0[0], s.h0[1], row, unit0, h0r);
     fence_proxy_async_smem();
     tmem_st_wait();
@@ -274,15 +277,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
-      if (B > 1) {  // A(1): D0 = W_hh0 h0(0)
-        issue_gemm<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo, 192, true);
-        mma_commit(&s.bar_a);
-      }
-      // B(0), input part only (h1 = 0): D1_rz = W_ih1[r,z] h0(0), D1_in = W_ih1[n] h0(0)
+      issue_gemm<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo, 192, true);
+      mma_commit(&s.bar_a);
+    }
+  };
+  // B(0), input part only (h1 = 0): D1_rz += W_ih1[r,z] h0(0), D1_in += W_ih1[n] h0(0)
+  auto issue_b0 = [&]() {
+    if (tid == 0) {
+      fence_after_sync();
       issue_gemm<kSplit3>(tmem + kColRz, a_h0_hi, a_h0_lo, w_ih1_hi, w_ih1_lo, 128, true);
       issue_gemm<kSplit3>(tmem + kColIn, a_h0_hi, a_h0_lo, w_ih1_hi + n_rows_off, w_ih1_lo + n_rows_off, 64, true);
       mma_commit(&s.bar_b);
     }
+  };
+
+  // Tiles are software-pipelined: the head of tile i+1 (window load, A(0), MMA A(1)) runs under the tail of tile i
+  // (MMA B(B-1) and its epilogue), so no MMA latency is exposed between tiles.
+  int buf = 0;
+  if ((long long)blockIdx.x < n_tiles) {
+    load_windows(blockIdx.x, 0);
+    __syncthreads();
+    cell_a0(0);
+    publish_h0_and_issue_a1();
+    issue_b0();
+  }
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const long long row0 = tile * kTcRows;
+    const long long next_tile = tile + gridDim.x;
+    const bool has_next = next_tile < n_tiles;
 
     for (int st = 0; st < B; ++st) {
       if (st + 1 < B) {
@@ -291,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
         fence_after_sync();
         float x[GIN];
 #pragma unroll
-        for (int v = 0; v < GIN; ++v) x[v] = s.act[row * 8 + (B - 2 - st) * gin + v];
+        for (int v = 0; v < GIN; ++v) x[v] = s.act[buf][row * 8 + (B - 2 - st) * gin + v];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // 8 units at a time keeps the transient registers low
           const int u0 = unit0 + 8 * c;
@@ -334,8 +356,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
           mma_commit(&s.bar_a);
         }
       } else {
+        if (has_next) {  // head of the next tile, under MMA B(B-1)
+          load_windows(next_tile, buf ^ 1);
+          __syncthreads();
+          cell_a0(buf ^ 1);
+        }
         mbar_wait(&s.bar_b, pb); pb ^= 1;
         fence_after_sync();
+        if (has_next) publish_h0_and_issue_a1();  // h0(B-1)'s readers (MMA B(B-1)) are done; D0 was reset after A(B-1)
       }
       // ================= epilogue B(st)  ||  MMA A(st+2) =================
 #pragma unroll
@@ -387,7 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
       o.y = ((o1 + s.pout[0][row * 2 + 1]) + s.pout[1][row * 2 + 1]) + s.pout[2][row * 2 + 1] + s.b_out[1];
       *reinterpret_cast<float2*>(a.p_out + (row0 + row) * 2) = o;
     }
-    // the next tile's first barrier (after the window load) separates these pout/act reads from their rewrites
+    if (has_next) issue_b0();  // D1 is free (read and reset above, ordered by the barrier)
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
@@ -395,6 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
 
 int launch_encode_tc(nlc_model_s* m, const float* hist, int K, int T, int B, float* p, int split3, cudaStream_t stream) {
   NLC_REQUIRE(B * m->gin <= 8, NLC_ERR_SHAPE, "tcgen05 encoder: window_length * input_width = %d exceeds 8", B * m->gin);
+  NLC_REQUIRE(B >= 2, NLC_ERR_SHAPE, "tcgen05 encoder: window_length must be >= 2");
   EncTcArgs a;
   a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.gin = m->gin;
   a.rows = (long long)K * T;

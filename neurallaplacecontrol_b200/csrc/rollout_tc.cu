@@ -41,6 +41,7 @@ struct RollTcArgs {
   const float* hist;
   const float* pert_cost;
   int K, T, B, L, nu, N3t;
+  int rows_per_cta;  // 128, or 64 when K is too small to fill the SMs with full tiles (upper TMEM lanes idle)
   float* cost_total;
   float* states;
   float* delta_out;
@@ -162,9 +163,9 @@ __global__ void __launch_bounds__(kGroups * 128, 1) rollout_tc_kernel(RollTcArgs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, grp = warp >> 2;
   const int row = 32 * q + lane;
-  const int k0 = blockIdx.x * kRtRows;
+  const int k0 = blockIdx.x * a.rows_per_cta;
   const int kk = min(k0 + row, a.K - 1);
-  const bool live = k0 + row < a.K;
+  const bool live = row < a.rows_per_cta && k0 + row < a.K;
 
   {
     const uint4* s2 = reinterpret_cast<const uint4*>(a.m.mlp_tc_w2);
@@ -315,7 +316,7 @@ static int launch_one(const RollTcArgs& a, cudaStream_t stream) {
   NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
   auto kern = rollout_tc_kernel<NX, S, kGroups, kSplit3>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (a.K + kRtRows - 1) / kRtRows;
+  const int grid = (a.K + a.rows_per_cta - 1) / a.rows_per_cta;
   kern<<<grid, kGroups * 128, smem, stream>>>(a);
   NLC_LAUNCH_OK("rollout_tc_kernel");
   return NLC_OK;
@@ -327,6 +328,9 @@ int launch_rollout_tc(nlc_model_s* m, const nlc_rollout_opts* o, const float* st
                       float* delta_out, int split3, int groups, cudaStream_t stream) {
   RollTcArgs a;
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
+  // the horizon is sequential per tile, so a plan with fewer than ~one wave of 128-sample tiles runs faster on twice as
+  // many half-filled tiles (the MMA costs the same, the epilogue halves)
+  a.rows_per_cta = ((K + kRtRows - 1) / kRtRows <= 74) ? 64 : kRtRows;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.N3t = m->N3t; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
 #define NLC_RT_CASE(NX_, S_)                                                                         \
   if (m->nx == NX_ && m->S == S_) {                                                                  \
