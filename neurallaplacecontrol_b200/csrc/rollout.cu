@@ -33,6 +33,10 @@ struct RollArgs {
   float* cost_total;
   float* states;
   float* delta_out;  // forward-only mode (nlc_model_forward): write the model output, skip the cost
+  // per-sample prediction times (nlc_model_forward_ts): first-layer bias with that sample's s-points folded in, and
+  // the sample's normalised time; null on the planner path (one folded time for every sample)
+  const float* row_b1;  // [K][128]
+  const float* row_tn;  // [K]
   int termRows;  // rows of the a1/term buffer
 };
 
@@ -75,6 +79,8 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
   float* st = in + R * Lp;                // [R][nx]   state, env units
   float* smean = st + R * nx;             // [nx]
   float* sinv = smean + nx;               // [nx]
+  float* rdelta = sinv + nx;              // [R] per-row pi/2 - pi t/T   (per-sample-time mode)
+  float* rscale = rdelta + R;             // [R] per-row exp(gamma t)/T
   const int ldt = a.termRows;             // row stride of a1 / term
 
   const int tid = threadIdx.x;
@@ -100,6 +106,13 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
     const int k = min(k0 + r, a.K - 1);
     in[r * Lp + nx + o] = a.p[((size_t)k * a.T) * 2 + o];
   }
+  if (a.row_tn)
+    for (int r = tid; r < R; r += 256) {  // torchlaplace Fourier constants of this sample's time (oracle/ilt.py)
+      const float tn = a.row_tn[min(k0 + r, a.K - 1)];
+      const float T = 2.0f * (tn + 1.0e-6f);
+      rdelta[r] = 3.14159265358979f * 1.0e-6f / T;
+      rscale[r] = expf((1.0e-3f + 4.605170185988091f / T) * tn) / T;
+    }
   __syncthreads();
 
   float cost_acc = 0.0f;
@@ -113,7 +126,7 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
     // ---- L1: a1 = tanh(b1' + W1x . in) ----
     for (int i = tid; i < R * kH; i += 256) {
       const int r = i >> 7, n = i & (kH - 1);
-      float acc = b1[n];
+      float acc = a.row_b1 ? a.row_b1[(size_t)min(k0 + r, a.K - 1) * kH + n] : b1[n];
       for (int j = 0; j < Lp; ++j) acc = fmaf(w1x[j * kH + n], in[r * Lp + j], acc);
       a1[r * ldt + n] = tanh_acc(acc);
     }
@@ -166,9 +179,15 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
         const int pair = pair0 + h;
         if (pair < nP) {
           const int kk = pair % S;
-          const float ph = phase[kk], wt = weight[kk];
+          float ph = phase[kk], wt = weight[kk];
+          // k pi t/T = k (pi/2 - delta): the quarter turns are exact, reduced to (-pi, pi]
+          const float quarter = (kk & 3) == 0 ? 0.0f : ((kk & 3) == 1 ? 1.57079632679489662f : ((kk & 3) == 2 ? 3.14159265358979f : -1.57079632679489662f));
 #pragma unroll
           for (int i = 0; i < kRT; ++i) {
+            if (a.row_tn) {
+              ph = quarter - (float)kk * rdelta[rg * kRT + i];
+              wt = rscale[rg * kRT + i] * (kk == 0 ? 0.5f : 1.0f);
+            }
             const float theta = 3.14159265358979f * tanh_acc(acc[i][2 * h]);  // w_nl.py:59
             const float rad = sphere_radius(acc[i][2 * h + 1]);               // w_nl.py:60-62 + sphere_to_complex
             a1[(rg * kRT + i) * ldt + pair] = wt * rad * cos_reduced(theta + ph);
@@ -207,14 +226,15 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
 static size_t rollout_smem_floats(int nx, int S, int N3p, int R, int termRows) {
   const int Lp = nx + 2;
   return (size_t)kH * kH + (size_t)kH * N3p + (size_t)R * termRows + (size_t)R * kH + (size_t)Lp * kH + 2 * kH + N3p +
-         2 * S + (size_t)R * Lp + (size_t)R * nx + 2 * nx + 8;
+         2 * S + (size_t)R * Lp + (size_t)R * nx + 2 * nx + 2 * (size_t)R + 8;
 }
 
 int launch_rollout_fp32(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                         const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost,
-                        float* states, float* delta_out, cudaStream_t stream) {
+                        float* states, float* delta_out, cudaStream_t stream, const float* row_b1 = nullptr,
+                        const float* row_tn = nullptr) {
   RollArgs a;
-  a.delta_out = delta_out;
+  a.delta_out = delta_out; a.row_b1 = row_b1; a.row_tn = row_tn;
   a.m = m->d; a.nx = m->nx; a.S = m->S; a.N3p = m->N3p; a.nu = nu; a.o = *o;
   a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.cost_total = cost; a.states = states;
@@ -303,4 +323,56 @@ extern "C" int nlc_model_forward(nlc_model_t m, const float* obs_dev, const floa
   o.state_constraint = 0; o.goal_x = 0.0f; o.dynamics = NLC_DYN_NEURAL_LAPLACE; o.delay = 0; o.dt = (float)m->dt;
   return launch_rollout(m, &o, obs_dev, 1, p_action_dev, act_dev, nullptr, K, 1, B, m->gin, nullptr, nullptr, out_dev,
                         math_mode, static_cast<cudaStream_t>(stream));
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NeuralLaplaceModel.forward with a per-sample prediction time (the irregular-time form of training / validation,
+// train_utils.py:401-404, overlay.py:664-737).  The s-points are then per sample: a prep kernel evaluates their sphere
+// coordinates and folds them into a per-sample first-layer bias; the encoder and the MLP/ILT kernel are shared with the
+// planner path (fp32 FFMA forms).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace nlc {
+
+__global__ void __launch_bounds__(128) forward_ts_prep_kernel(ModelDev m, int S, int Lp, int norm_time, float dt, const float* __restrict__ ts,
+                                                              int K, float* __restrict__ row_b1, float* __restrict__ row_tn) {
+  __shared__ float th[kMaxS], ph[kMaxS];
+  const int k = blockIdx.x, n = threadIdx.x;
+  float tn = ts[k];
+  if (norm_time) tn = tn / (dt * 8.0f);  // w_nl.py:123
+  const float T = 2.0f * (tn + 1.0e-6f);
+  const float gamma = 1.0e-3f + 4.605170185988091f / T;
+  for (int j = n; j < S; j += 128) {  // oracle/ilt.py: fourier_s_points + complex_to_sphere
+    const float im = 3.14159265358979f * (float)j / T;
+    th[j] = atan2f(im, gamma);
+    // phi = asin((r^2-1)/(r^2+1)) = 2 atan(r) - pi/2 (the asin form cancels for large r)
+    ph[j] = 2.0f * atanf(sqrtf(fmaf(gamma, gamma, im * im))) - 1.57079632679489662f;
+  }
+  __syncthreads();
+  float acc = m.b1_raw[n];
+  for (int j = 0; j < S; ++j) acc = fmaf(m.w1_full_t[(size_t)j * kH + n], th[j], acc);
+  for (int j = 0; j < S; ++j) acc = fmaf(m.w1_full_t[(size_t)(S + j) * kH + n], ph[j], acc);
+  row_b1[(size_t)k * kH + n] = acc;
+  if (n == 0) row_tn[k] = tn;
+}
+
+}  // namespace nlc
+
+extern "C" int nlc_model_forward_ts(nlc_model_t m, const float* obs_dev, const float* act_dev, const float* ts_dev, int K,
+                                    int B, float* out_dev, float* scratch_dev, void* stream) {
+  NLC_REQUIRE(m && obs_dev && act_dev && ts_dev && out_dev && scratch_dev, NLC_ERR_ARG, "nlc_model_forward_ts: null pointer");
+  NLC_REQUIRE(K >= 1, NLC_ERR_ARG, "nlc_model_forward_ts: K must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* p_action = scratch_dev;                 // [K][2]
+  float* row_tn = scratch_dev + 2 * (size_t)K;   // [K]
+  float* row_b1 = scratch_dev + 4 * (size_t)K;   // [K][128]   (offset keeps 16-byte alignment)
+  int rc = nlc_encode_history(m, act_dev, K, 1, B, p_action, NLC_MATH_FP32, stream);
+  if (rc != NLC_OK) return rc;
+  forward_ts_prep_kernel<<<K, 128, 0, s>>>(m->d, m->S, m->nx + 2, m->normalize && m->normalize_time, (float)m->dt, ts_dev, K, row_b1, row_tn);
+  NLC_LAUNCH_OK("forward_ts_prep_kernel");
+  nlc_rollout_opts o;
+  o.env = m->nx == 3 ? NLC_ENV_PENDULUM : (m->nx == 5 ? NLC_ENV_CARTPOLE : NLC_ENV_ACROBOT);
+  o.state_constraint = 0; o.goal_x = 0.0f; o.dynamics = NLC_DYN_NEURAL_LAPLACE; o.delay = 0; o.dt = (float)m->dt;
+  return launch_rollout_fp32(m, &o, obs_dev, 1, p_action, act_dev, nullptr, K, 1, B, m->gin, nullptr, nullptr, out_dev, s, row_b1,
+                             row_tn);
 }

@@ -69,6 +69,10 @@ def test_model_forward_matches_reference(env):
     assert out.dtype == torch.float64 and out.shape == g["out_fixed"].shape
     assert relerr(g["p_action"], m.last_p_action) < 1e-5
     assert relerr(g["out_fixed"], out) < TOL
+    # per-sample (irregular) prediction times, the training/validation form (train_utils.py:401-404)
+    out_irreg = m(obs, act, torch.from_numpy(g["ts_irreg"]).cuda())
+    assert out_irreg.shape == g["out_irreg"].shape
+    assert relerr(g["out_irreg"], out_irreg) < TOL, relerr(g["out_irreg"], out_irreg)
 
 
 PLAN_KEYS = ("noise", "perturbed_action", "cost_total", "cost_total_non_zero", "omega", "states", "actions", "U", "action")
