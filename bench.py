@@ -5,8 +5,10 @@ per-control-step plan latency).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg4|cfg3|cfg1]
 
 One "step" = one MPPI control step (``MPPIDelay.command``): K x H Neural Laplace rollout-steps.
-Default workload at every N: BASELINE config 4, acrobot-delay K=65536 H=50 (strong scaling: the K samples are
-sharded over the N GPUs, one all-gather of the (beta, eta, W) triple per step).  Synthetic inputs: random-init
+Default workload at every N: BASELINE config 4, acrobot-delay K=65536 H=50 per GPU.  The K samples shard over the
+GPUs with one all-gather of the (beta, eta, W) triple per step and no other exchange, so the default is weak scaling
+(K_total = N x 65536); `--scaling strong` keeps K_total = 65536 and shards it N ways (8192 samples per GPU at N=8,
+which is latency-bound: the horizon is sequential).  Synthetic inputs: random-init
 weights of the reference architecture (golden fixture, calibrated phi-bias), on-device Philox action noise.
 
 * ``value``   - device-timed (CUDA events), state/action-buffer already resident in HBM.
@@ -149,7 +151,7 @@ def run_reference(args, env, K, H, desc):
     ms = 1e3 * sum(times) / len(times)
     val = Ks * H / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "K": K, "H": H, "env": env, "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -307,10 +309,10 @@ def run_gpu(args, env, K, H, desc):
                 traffic = json.load(f).get(f"{kernels[dom]['name']}_{args.math}_{args.workload}")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev, "plan_latency_ms": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_dev, "plan_latency_ms": ms_dev, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "env": env, "K": K, "H": H, "S": inp["S"], "hidden": 128, "history_window": B,
-                       "parallelism": f"K-sharded x{world}", "math": args.math, "noise": "on-device Philox4x32-10",
+                       "parallelism": f"K-sharded x{world}", "K_per_gpu": K // world, "math": args.math, "noise": "on-device Philox4x32-10",
                        "l2": "flushed between timed steps (256 MiB fill)", "keep_states": True},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 4 * (nx + B * nu),
@@ -341,12 +343,19 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--math", default="tc_split3", choices=["fp32", "tc_split3", "tc_fp16"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the named K is the PER-GPU shard (K_total = N*K); strong: K_total = K sharded N ways")
     ap.add_argument("--cpu-samples", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     env, K, H, desc = WORKLOADS[args.workload]
+    if args.scaling == "weak" and args.gpus > 1:
+        # the K samples shard with no data-path collective (one 408-byte all-gather per step), so N GPUs plan N times
+        # the samples: each rank owns the named K (config.py's sweep contemplates K up to 262144)
+        K = K * args.gpus
+        desc = desc.replace(f"K={K // args.gpus}", f"K={K} ({K // args.gpus} per GPU x {args.gpus})")
     if args.impl == "reference":
         run_reference(args, env, K, H, desc)
     else:
