@@ -302,6 +302,17 @@ def run_gpu(args, env, K, H, desc):
             kv["tflops"] = kv["flop"] / (kv["ms"] * 1e-3) / 1e12
             kv["frac"] = kv["tflops"] / peaks["bf16_tflops_sustained"]
         achieved = kernels[dom]["tflops"]
+        # secondary roofline: transcendental (MUFU / XU pipe) throughput.  Counts per rollout-step from the kernels' code:
+        # encoder 8 GRU cells x 64 units x (2 ex2 + 1 shared rcp for r,z; ex2 + rcp for n) = 2560 (3 tanh.approx in tc_fp16);
+        # rollout 2 x 128 tanh (ex2 + rcp) + nx*S pairs x (tanh 2 + sphere radius 3 + cos 1).  Peak: 16 /clk/SM measured
+        # by tools/mufu_bench.cu (15.9) x 148 SMs x the SM clock seen during the run.
+        if args.math != "fp32":
+            sm_hz = 1e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
+            mufu_peak = 15.9 * 148 * sm_hz
+            per_step = {"encoder": 8 * 64 * (5 if args.math == "tc_split3" else 3), "rollout": 4 * 128 + nx * inp["S"] * 6}
+            for name, kv in kernels.items():
+                kv["mufu_per_s"] = per_step[name] * Kl * H / (kv["ms"] * 1e-3)
+                kv["mufu_frac"] = kv["mufu_per_s"] / mufu_peak
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
