@@ -23,6 +23,10 @@ class NLDynamics:
 
     def __call__(self, state, window):
         ts = torch.full((state.shape[0], 1), self.dt, dtype=torch.float64, device=state.device)
+        if self.model.encode_obs_time:  # mppi_with_model.py:110-119: window position B-1 .. 0 as an extra channel
+            B = window.shape[1]
+            tchan = torch.flip(torch.arange(B, device=window.device), (0,)).view(1, B, 1).to(window.dtype)
+            window = torch.cat((window, tchan.repeat(window.shape[0], 1, 1)), dim=2)
         out = self.model(state, window, ts)
         return state + out.reshape(state.shape).to(state.dtype)
 

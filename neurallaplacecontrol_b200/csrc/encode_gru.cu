@@ -25,6 +25,7 @@ struct EncArgs {
   const float* hist;  // [K][L][gin] env units
   float* p_out;       // [K*T][2]
   int K, T, B, L, gin;
+  int hist_ch;  // channels stored in hist: gin, or gin-1 when the time channel of encode_obs_time is synthesised
   long long rows;
   ModelDev m;
 };
@@ -147,7 +148,9 @@ __global__ void __launch_bounds__(256, 1) encode_gru_kernel(EncArgs a) {
       if (row >= a.rows) row = a.rows - 1;
       const long long k = row / a.T;
       const int t = (int)(row - k * a.T);
-      const float v = a.hist[((size_t)k * a.L + t + j) * gin + u];
+      // encode_obs_time: the extra channel is the window position counted from the newest entry, B-1 .. 0
+      // (mppi_with_model.py:110-119), not stored in the history
+      const float v = u < a.hist_ch ? a.hist[((size_t)k * a.L + t + j) * a.hist_ch + u] : (float)(B - 1 - j);
       s.act[i] = (v - s.act_mean[u]) * s.act_inv_std[u];
     }
     __syncthreads();
@@ -187,8 +190,9 @@ __global__ void __launch_bounds__(256, 1) encode_gru_kernel(EncArgs a) {
   }
 }
 
-int launch_encode_fp32(nlc_model_s* m, const float* hist, int K, int T, int B, float* p, cudaStream_t stream) {
+int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, cudaStream_t stream) {
   EncArgs a;
+  a.hist_ch = hist_ch;
   a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.gin = m->gin;
   a.rows = (long long)K * T;
   a.m = m->d;
@@ -205,7 +209,26 @@ int launch_encode_fp32(nlc_model_s* m, const float* hist, int K, int T, int B, f
   return NLC_OK;
 }
 
-int launch_encode_tc(nlc_model_s* m, const float* hist, int K, int T, int B, float* p, int split3, cudaStream_t stream);
+int launch_encode_tc(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream);
+
+// hist_ch: channels stored per history entry (model gin for nlc_model_forward, whose caller supplies the time channel
+// like the reference's forward; action_dim on the planner path, where encode_obs_time's channel is synthesised)
+int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K, int T, int B, float* p_dev, int math_mode,
+                        cudaStream_t s) {
+  NLC_REQUIRE(m && hist_dev && p_dev, NLC_ERR_ARG, "nlc_encode_history: null pointer");
+  NLC_REQUIRE(K >= 1 && T >= 1, NLC_ERR_ARG, "nlc_encode_history: K and T must be positive");
+  NLC_REQUIRE(B >= 1 && B <= 8, NLC_ERR_SHAPE, "nlc_encode_history: window length %d outside [1,8]", B);
+  NLC_REQUIRE(m->Hg == kHg, NLC_ERR_SHAPE, "encoder hidden size must be 64");
+  switch (math_mode) {
+    case NLC_MATH_FP32: return launch_encode_fp32(m, hist_dev, hist_ch, K, T, B, p_dev, s);
+    case NLC_MATH_TC_SPLIT3:
+    case NLC_MATH_TC_FP16:
+      // shapes without a tensor-core instantiation run on the fp32 kernel
+      if (B < 2 || B * m->gin > 8 || m->gin > 2) return launch_encode_fp32(m, hist_dev, hist_ch, K, T, B, p_dev, s);
+      return launch_encode_tc(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
+    default: set_error("nlc_encode_history: unknown math_mode %d", math_mode); return NLC_ERR_ARG;
+  }
+}
 
 }  // namespace nlc
 
@@ -213,15 +236,6 @@ using namespace nlc;
 
 extern "C" int nlc_encode_history(nlc_model_t m, const float* hist_dev, int K, int T, int B, float* p_dev,
                                   int math_mode, void* stream) {
-  NLC_REQUIRE(m && hist_dev && p_dev, NLC_ERR_ARG, "nlc_encode_history: null pointer");
-  NLC_REQUIRE(K >= 1 && T >= 1, NLC_ERR_ARG, "nlc_encode_history: K and T must be positive");
-  NLC_REQUIRE(B >= 1 && B <= 8, NLC_ERR_SHAPE, "nlc_encode_history: window length %d outside [1,8]", B);
-  NLC_REQUIRE(m->Hg == kHg, NLC_ERR_SHAPE, "encoder hidden size must be 64");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (math_mode) {
-    case NLC_MATH_FP32: return launch_encode_fp32(m, hist_dev, K, T, B, p_dev, s);
-    case NLC_MATH_TC_SPLIT3: return launch_encode_tc(m, hist_dev, K, T, B, p_dev, 1, s);
-    case NLC_MATH_TC_FP16: return launch_encode_tc(m, hist_dev, K, T, B, p_dev, 0, s);
-    default: set_error("nlc_encode_history: unknown math_mode %d", math_mode); return NLC_ERR_ARG;
-  }
+  NLC_REQUIRE(m != nullptr, NLC_ERR_ARG, "nlc_encode_history: null model");
+  return encode_history_impl(m, hist_dev, m->nu, K, T, B, p_dev, math_mode, static_cast<cudaStream_t>(stream));
 }

@@ -42,7 +42,7 @@ constexpr uint32_t kColD0 = 0, kColRz = 192, kColIn = 320, kColHn = 384, kTmemCo
 struct EncTcArgs {
   const float* hist;
   float* p_out;
-  int K, T, B, L, gin;
+  int K, T, B, L, gin, hist_ch;
   long long rows;
   ModelDev m;
 };
@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
       if (grow >= a.rows) grow = a.rows - 1;
       const long long k = grow / a.T;
       const int t = (int)(grow - k * a.T);
-      s.act[buf_][r * 8 + rem] = (a.hist[((size_t)k * a.L + t + j) * gin + u] - s.act_mean[u]) * s.act_inv_std[u];
+      const float v = u < a.hist_ch ? a.hist[((size_t)k * a.L + t + j) * a.hist_ch + u] : (float)(B - 1 - j);  // encode_obs_time channel
+      s.act[buf_][r * 8 + rem] = (v - s.act_mean[u]) * s.act_inv_std[u];
     }
   };
   // A(0): layer 0 on the newest window entry (reversed order, w_nl.py:27) from the zero state - no MMA
@@ -421,11 +422,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) encode_tc_kernel(EncTcArgs a) {
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
-int launch_encode_tc(nlc_model_s* m, const float* hist, int K, int T, int B, float* p, int split3, cudaStream_t stream) {
+int launch_encode_tc(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream) {
   NLC_REQUIRE(B * m->gin <= 8, NLC_ERR_SHAPE, "tcgen05 encoder: window_length * input_width = %d exceeds 8", B * m->gin);
   NLC_REQUIRE(B >= 2, NLC_ERR_SHAPE, "tcgen05 encoder: window_length must be >= 2");
   EncTcArgs a;
-  a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.gin = m->gin;
+  a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.gin = m->gin; a.hist_ch = hist_ch;
   a.rows = (long long)K * T;
   a.m = m->d;
   const int smem = (int)sizeof(EncTcSmem) + 128;

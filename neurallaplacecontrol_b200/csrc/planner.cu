@@ -39,7 +39,7 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   if (d->rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
     NLC_REQUIRE(model != nullptr, NLC_ERR_ARG, "planner: Neural Laplace dynamics need a model handle");
     NLC_REQUIRE(model->device == device, NLC_ERR_ARG, "planner: model lives on device %d, planner on %d", model->device, device);
-    NLC_REQUIRE(model->nx == d->nx && model->gin == mp.nu, NLC_ERR_SHAPE, "planner: model dims do not match");
+    NLC_REQUIRE(model->nx == d->nx && model->nu == mp.nu, NLC_ERR_SHAPE, "planner: model dims do not match");
   }
   nlc_planner_s* p = new nlc_planner_s();
   p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;

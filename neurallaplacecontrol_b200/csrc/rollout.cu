@@ -258,6 +258,8 @@ int launch_rollout_fp32(nlc_model_s* m, const nlc_rollout_opts* o, const float* 
   return NLC_OK;
 }
 
+int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K, int T, int B, float* p_dev, int math_mode,
+                        cudaStream_t s);
 int launch_rollout_tc(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                       const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
                       float* delta_out, int split3, int groups, cudaStream_t stream);
@@ -316,7 +318,7 @@ extern "C" int nlc_model_forward(nlc_model_t m, const float* obs_dev, const floa
   NLC_REQUIRE(m && obs_dev && act_dev && out_dev, NLC_ERR_ARG, "nlc_model_forward: null pointer");
   NLC_REQUIRE(p_action_dev != nullptr, NLC_ERR_ARG, "nlc_model_forward: p_action_dev scratch [K][2] is required");
   NLC_REQUIRE(K >= 1, NLC_ERR_ARG, "nlc_model_forward: K must be positive");
-  int rc = nlc_encode_history(m, act_dev, K, 1, B, p_action_dev, math_mode, stream);
+  int rc = encode_history_impl(m, act_dev, m->gin, K, 1, B, p_action_dev, math_mode, static_cast<cudaStream_t>(stream));
   if (rc != NLC_OK) return rc;
   nlc_rollout_opts o;
   o.env = m->nx == 3 ? NLC_ENV_PENDULUM : (m->nx == 5 ? NLC_ENV_CARTPOLE : NLC_ENV_ACROBOT);
@@ -366,7 +368,7 @@ extern "C" int nlc_model_forward_ts(nlc_model_t m, const float* obs_dev, const f
   float* p_action = scratch_dev;                 // [K][2]
   float* row_tn = scratch_dev + 2 * (size_t)K;   // [K]
   float* row_b1 = scratch_dev + 4 * (size_t)K;   // [K][128]   (offset keeps 16-byte alignment)
-  int rc = nlc_encode_history(m, act_dev, K, 1, B, p_action, NLC_MATH_FP32, stream);
+  int rc = encode_history_impl(m, act_dev, m->gin, K, 1, B, p_action, NLC_MATH_FP32, s);
   if (rc != NLC_OK) return rc;
   forward_ts_prep_kernel<<<K, 128, 0, s>>>(m->d, m->S, m->nx + 2, m->normalize && m->normalize_time, (float)m->dt, ts_dev, K, row_b1, row_tn);
   NLC_LAUNCH_OK("forward_ts_prep_kernel");

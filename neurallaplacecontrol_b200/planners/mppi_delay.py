@@ -11,7 +11,9 @@ Differences a caller can see, all deliberate:
   planner's buffers); the returned action is cast to ``noise_sigma.dtype`` like the reference's.
 * Options the reference's callers never use and this path does not implement raise ``NotImplementedError``
   instead of being silently ignored: ``terminal_state_cost``, ``step_dependent_dynamics``, ``rollout_samples > 1``
-  (legacy variance branch, ``:291-292,310``), ``encode_obs_time``.
+  (legacy variance branch, ``:291-292,310``), planner-level ``encode_obs_time`` with a Neural Laplace model (a model built
+  with ``encode_obs_time=True`` is supported: the closure-level time channel of ``mppi_with_model.py:110-119`` is
+  synthesised inside the encoder kernels).
 * Extra keyword arguments (not in the reference): ``process_group`` shards the K samples over the ranks of a
   ``torch.distributed`` group (one all-gather of the (beta, eta, W) triple per control step), ``seed`` keys the
   on-device Philox sampler, ``math_mode`` selects the contraction arithmetic, ``keep_states`` can drop the
@@ -67,8 +69,11 @@ class MPPIDelay:
             raise NotImplementedError("step_dependent_dynamics is not implemented")
         if rollout_samples != 1:
             raise NotImplementedError("rollout_samples > 1 (legacy variance branch) is not implemented")
-        if encode_obs_time:
-            raise NotImplementedError("encode_obs_time=True is not implemented on this path yet")
+        if encode_obs_time and not isinstance(dynamics, AnalyticDelayDynamics):
+            # mppi_delay.py:261-287 appends a running time channel to the window it hands to `dynamics`; the reference
+            # only uses that with the analytic dynamics (mppi_dataset_collector.py:166-180), which ignore the channel.
+            # A Neural Laplace model with encode_obs_time gets its channel from the closure instead (NLDynamics).
+            raise NotImplementedError("planner-level encode_obs_time is implemented for AnalyticDelayDynamics only")
         if u_per_command != 1:
             raise NotImplementedError("u_per_command != 1 is not implemented")
         dev = torch.device(device)
@@ -281,6 +286,8 @@ class MPPIDelay:
         """:param state: (nx) or (K x nx) current state; :param action_buffer: (B x nu) past actions, env units.
         :returns action: (nu) best action (``mppi_delay.py:193-224``)."""
         action_buffer = torch.as_tensor(action_buffer)
+        if self.encode_obs_time:
+            action_buffer = action_buffer[:, :self.nu]  # the time column is not read by the analytic dynamics (oracle.py:23)
         B = action_buffer.shape[0]
         h = self._ensure(B)
         self._push_U()

@@ -158,6 +158,38 @@ def main():
                         "in_buffer": buf, "delay": delay})
             np.savez_compressed(os.path.join(GOLDEN_DIR, f"plan_oracledyn_{short}_d{delay}.npz"), **_np(out))
 
+    # --- encode_obs_time=True models: the closure of mppi_with_model.py:110-119 appends the window position
+    #     B-1..0 as an extra GRU input channel; only nu = 1 envs broadcast through the reference's normalisation ----------
+    for env in ("oderl-pendulum", "oderl-cartpole"):
+        nx, nu = costs.ENV_DIMS[env]
+        short = env.split("-")[1]
+        model = ref_harness.build_reference_model(env, seed=1, s_recon_terms=S_TERMS, dt=DT, encode_obs_time=True)
+        sd = calibrate_({k: v.detach().clone() for k, v in model.state_dict().items()}, nx)
+        model.load_state_dict(sd)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"weights_eot_{short}.npz"), **_np(sd))
+        g = torch.Generator().manual_seed(30)
+        K, T, B = 100, 6, 4
+        tchan = torch.flip(torch.arange(B), (0,)).view(1, B, 1).to(torch.float64)
+        obs = torch.randn(K, nx, generator=g, dtype=torch.float64) * torch.tensor(costs.ENV_STATE_STD[env])
+        act = (torch.rand(K, B, nu, generator=g, dtype=torch.float64) * 2 - 1) * costs.ENV_ACT_HIGH[env]
+        act_t = torch.cat((act, tchan.repeat(K, 1, 1)), dim=2)
+        ts_fixed = torch.full((K, 1), DT, dtype=torch.float64)
+        out = {"obs": obs, "act": act_t, "out_fixed": model(obs, act_t, ts_fixed),
+               "p_action": model.action_encoder((act_t - model.action_mean) / model.action_std)}
+        noise = injected_noise(K, T, nu, seed=31)
+        U0 = torch.randn(T, nu, generator=g, dtype=torch.float64) * 0.3
+        buf = (torch.rand(B, nu, generator=g, dtype=torch.float64) * 2 - 1) * costs.ENV_ACT_HIGH[env]
+        ts_pred = torch.full((K, 1), DT, dtype=torch.float64)
+
+        def dyn(state, window, model=model, ts_pred=ts_pred, tchan=tchan):
+            w = torch.cat((window, tchan.repeat(window.shape[0], 1, 1)), dim=2)
+            return state + model(state, w, ts_pred)
+
+        plan = reference_plan(None, env, K, T, U0, START_STATE[env], buf, noise, dynamics=dyn)
+        out.update({"plan_" + k: v for k, v in plan.items()})
+        out.update({"in_noise": noise, "in_U": U0, "in_state": np.array(START_STATE[env]), "in_buffer": buf})
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"eot_{short}.npz"), **_np(out))
+
     # --- BASELINE config 1: pendulum K=1000 H=20 (calibrated weights), trimmed outputs ----------
     env = "oderl-pendulum"
     nx, nu = costs.ENV_DIMS[env]

@@ -120,12 +120,17 @@ def get_action(action_buffer, action, action_delay):
     return action_buffer, action_buffer[-(action_delay + 1)]
 
 
-def make_nl_dynamics(sd, dt):
-    """The ``dynamics`` closure of ``mppi_with_model.py:103-122`` over the oracle model."""
+def make_nl_dynamics(sd, dt, encode_obs_time=False):
+    """The ``dynamics`` closure of ``mppi_with_model.py:103-122`` over the oracle model.  With ``encode_obs_time`` the
+    window gets the extra channel ``B-1 .. 0`` (``:110-119``)."""
     from . import nl_model
 
     def dynamics(state, window):
         ts = torch.full((state.shape[0], 1), dt, dtype=state.dtype)
+        if encode_obs_time:
+            B = window.shape[1]
+            tchan = torch.flip(torch.arange(B), (0,)).view(1, B, 1).to(window.dtype).repeat(window.shape[0], 1, 1)
+            window = torch.cat((window, tchan), dim=2)
         return state + nl_model.nl_forward(sd, state, window, ts)
 
     return dynamics

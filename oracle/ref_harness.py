@@ -54,7 +54,7 @@ def load():
     return mppi_mod.MPPIDelay, w_nl, ref_oracle
 
 
-def build_reference_model(env_name, seed=0, hidden_units=128, s_recon_terms=17, dt=0.05, out_scale=1.0):
+def build_reference_model(env_name, seed=0, hidden_units=128, s_recon_terms=17, dt=0.05, out_scale=1.0, encode_obs_time=False):
     """Random-init reference ``NeuralLaplaceModel`` as ``train_utils.get_nl_model`` builds it
     (``train_utils.py:29-54,183-200``), ``.double()`` as ``mppi_with_model.py:101``.
 
@@ -69,7 +69,7 @@ def build_reference_model(env_name, seed=0, hidden_units=128, s_recon_terms=17, 
     torch.manual_seed(seed)
     model = w_nl.NeuralLaplaceModel(
         nx, nu, nx, hidden_units=hidden_units, s_recon_terms=s_recon_terms, ilt_algorithm="fourier",
-        encode_obs_time=False, state_mean=np.zeros(nx), state_std=np.array(ENV_STATE_STD[env_name]),
+        encode_obs_time=encode_obs_time, state_mean=np.zeros(nx), state_std=np.array(ENV_STATE_STD[env_name]),
         action_mean=np.array([0] * nu), action_std=np.array([ENV_ACT_HIGH[env_name] / 2.0]),
         normalize=True, normalize_time=True, dt=dt,
     ).double()

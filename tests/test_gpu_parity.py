@@ -264,3 +264,47 @@ def test_null_action_and_abs_cost_options():
     cost, _, _ = mppi.rollout_costs(mppi.make_nl_dynamics(weights(env, calibrated=True), DT), costs.running_cost(env),
                                     torch.from_numpy(state), pert, buf, ah)
     assert relerr(cost + pc, p.cost_total) < TOL
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc_split3"])
+@pytest.mark.parametrize("env", ["oderl-pendulum", "oderl-cartpole"])
+def test_encode_obs_time_model(env, mode):
+    """A model built with encode_obs_time=True (extra GRU input channel B-1..0, mppi_with_model.py:110-119): forward with
+    the caller-supplied channel and a plan where the encoder kernels synthesise it."""
+    from oracle import costs
+
+    nlc = _nlc()
+    nx, nu = costs.ENV_DIMS[env]
+    ah = np.float32(costs.ENV_ACT_HIGH[env])
+    g = load("eot_" + short(env))
+    m = nlc.NeuralLaplaceModel(nx, nu, nx, hidden_units=128, s_recon_terms=S_TERMS, encode_obs_time=True, state_mean=np.zeros(nx),
+                               state_std=np.ones(nx), action_mean=np.array([0] * nu), action_std=np.array([1.0]), normalize=True,
+                               normalize_time=True, dt=DT, math_mode=mode).double()
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in load("weights_eot_" + short(env)).items()})
+    obs, act = torch.from_numpy(g["obs"]).cuda(), torch.from_numpy(g["act"]).cuda()
+    out = m(obs, act, torch.full((obs.shape[0], 1), DT, dtype=torch.float64).cuda())
+    assert relerr(g["p_action"], m.last_p_action) < 2e-5
+    assert relerr(g["out_fixed"], out) < TOL
+    noise = torch.from_numpy(g["in_noise"])
+    p = nlc.MPPIDelay(nlc.NLDynamics(m, DT), nlc.EnvRunningCost(env), nx, nlc.noise_sigma_for(nu), num_samples=noise.shape[0],
+                      horizon=noise.shape[1], device="cuda:0", u_min=torch.tensor(-ah), u_max=torch.tensor(ah), u_scale=ah,
+                      U_init=torch.from_numpy(g["in_U"]).clone(), math_mode=mode)
+    p.noise_dist.sample = lambda shape: noise.clone()
+    a = p.command(g["in_state"], torch.from_numpy(g["in_buffer"]))
+    for k in ("cost_total", "states", "U"):
+        assert relerr(g["plan_" + k], getattr(p, k)) < TOL, k
+    assert action_relerr(g["plan_action"], a, g["plan_U"], ah) < TOL
+
+
+def test_planner_level_encode_obs_time_with_analytic_dynamics():
+    """mppi_dataset_collector.py:166-180: encode_obs_time=True with the analytic dynamics; the buffer's time column is ignored."""
+    nlc = _nlc()
+    env = "oderl-pendulum"
+    g = load("plan_oracledyn_pendulum_d1")
+    noise = torch.from_numpy(g["in_noise"])
+    dyn = nlc.AnalyticDelayDynamics(env, 1, DT)
+    p = make_planner(env, None, noise.shape[0], noise.shape[1], g["in_U"], dynamics=dyn, encode_obs_time=True)
+    p.noise_dist.sample = lambda shape: noise.clone()
+    buf = torch.cat((torch.from_numpy(g["in_buffer"]), torch.arange(4, dtype=torch.float64).view(4, 1) * DT), dim=1)
+    a = p.command(np.asarray(g["in_state"]), buf)
+    assert relerr(g["cost_total"], p.cost_total) < TOL and relerr(g["action"], a) < TOL

@@ -114,3 +114,20 @@ def test_live_reference_plan(env):
     out = _run_oracle_plan(env, g, sd)
     for k in PLAN_KEYS:
         assert relerr(ref[k], out[k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("env", ["oderl-pendulum", "oderl-cartpole"])
+def test_encode_obs_time_model_matches_reference(env):
+    """encode_obs_time=True (mppi_with_model.py:110-119): extra GRU input channel B-1..0."""
+    g = load("eot_" + short(env))
+    sd = {k: torch.from_numpy(v.copy()).to(torch.float64) for k, v in load("weights_eot_" + short(env)).items()}
+    nu = costs.ENV_DIMS[env][1]
+    ah = costs.ENV_ACT_HIGH[env]
+    out, p_action = nl_model.nl_forward(sd, torch.from_numpy(g["obs"]), torch.from_numpy(g["act"]),
+                                        torch.full((g["obs"].shape[0], 1), DT, dtype=torch.float64), return_parts=True)
+    assert relerr(g["out_fixed"], out) < TIGHT and relerr(g["p_action"], p_action) < TIGHT
+    plan = mppi.command(torch.from_numpy(g["in_U"]).clone(), torch.from_numpy(g["in_state"]), torch.from_numpy(g["in_buffer"]),
+                        torch.from_numpy(g["in_noise"]), mppi.make_nl_dynamics(sd, DT, encode_obs_time=True),
+                        costs.running_cost(env), noise_sigma=mppi.noise_sigma_for(nu), u_scale=ah, u_min=-ah, u_max=ah)
+    for k in ("cost_total", "states", "U", "action"):
+        assert relerr(g["plan_" + k], plan[k]) < 1e-9, k
