@@ -125,7 +125,7 @@ def test_softmax_update_and_shard_combine(K, T, nu):
         assert relerr(results[0], r) < 1e-5  # sharding changes only the summation order
 
 
-@pytest.mark.parametrize("S", [17, 33, 64, 65, 129])
+@pytest.mark.parametrize("S", [1, 2, 17, 18, 33, 34, 48, 64, 65, 129, 200, 300])
 @pytest.mark.parametrize("per_row", [False, True])
 def test_fourier_ilt_kernel_matches_oracle(S, per_row):
     from neurallaplacecontrol_b200 import fourier_ilt
@@ -141,6 +141,22 @@ def test_fourier_ilt_kernel_matches_oracle(S, per_row):
     t64 = t.double().expand(N, n_t)
     T64 = ilt.SCALE * (t64 + ilt.EPS)
     ref = ilt.fourier_line_integrate(F.real.double(), F.imag.double(), t64, T64)
+    assert relerr(ref, out) < 2e-5, relerr(ref, out)
+
+
+@pytest.mark.parametrize("N,n_t", [(1, 5), (2, 16), (3, 32), (40, 700)])
+def test_fourier_ilt_ragged_shapes(N, n_t):
+    """fewer than 32 rows, exactly whole 32-row blocks, and a time grid longer than the kernel's constant table"""
+    from neurallaplacecontrol_b200 import fourier_ilt
+    from oracle import ilt
+
+    S = 33
+    g = torch.Generator().manual_seed(N * 1000 + n_t)
+    F = torch.complex(torch.rand(N, n_t, S, generator=g) * 2 - 1, torch.rand(N, n_t, S, generator=g) * 2 - 1)
+    t = (torch.arange(n_t, dtype=torch.float32) + 1) * 0.01
+    out = fourier_ilt(F.cuda(), t.cuda())
+    t64 = t.double().expand(N, n_t)
+    ref = ilt.fourier_line_integrate(F.real.double(), F.imag.double(), t64, ilt.SCALE * (t64 + ilt.EPS))
     assert relerr(ref, out) < 2e-5, relerr(ref, out)
 
 
