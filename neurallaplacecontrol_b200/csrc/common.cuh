@@ -62,6 +62,11 @@ struct ModelDev {
   // fp16 hi/lo splits of the three recurrent matrices in the tcgen05 canonical layout (see
   // encode_tc.cu); [3 matrices][2 (hi,lo)][3Hg * Hg] halves
   void* enc_tc_w;
+  // encode_tc2.cu: the same three matrices with -log2(e) (r, z rows) and -2 log2(e) (n rows) folded in so that the gate
+  // epilogue feeds ex2 directly, W_ih1 with its rows ordered [n | r | z] (one N=192 product into adjacent accumulator
+  // columns); and the matching fp32 constants (biases, layer-0 input weights, output layer), layout kE2* below
+  void* enc2_w;
+  float* enc2_c;
   // fp16 hi/lo operand images of the representation MLP for the tcgen05 rollout (rollout_tc.cu):
   // mlp_tc_w2 [2 (hi,lo)][128 x 128], mlp_tc_w3 [2][N3t x 128] with the pair-permuted rows of w3_t, zero padded
   void* mlp_tc_w2;
@@ -84,6 +89,16 @@ struct ModelDev {
   float* act_mean;   // [gin]
   float* act_inv_std;// [gin]
 };
+
+// float offsets inside ModelDev::enc2_c
+constexpr int kE2Brz0 = 0;     // [128] -log2e (b_ih0 + b_hh0)[r, z]
+constexpr int kE2Bin0 = 128;   // [64]  -2 log2e b_ih0[n]
+constexpr int kE2Bhn0 = 192;   // [64]  -2 log2e b_hh0[n]
+constexpr int kE2B1 = 256;     // [256] layer 1 in accumulator order [in | r | z | hn]
+constexpr int kE2Wih0 = 512;   // [3][kMaxNu][64] scaled layer-0 input weights, [gate][input][unit]
+constexpr int kE2Wout = 512 + 3 * kMaxNu * 64;  // [2][64]
+constexpr int kE2Bout = kE2Wout + 128;          // [2]
+constexpr int kE2Count = kE2Bout + 8;
 
 struct ModelHost {  // fp64 copies kept for re-folding at another prediction time
   double* w0 = nullptr;  // [Hm][2S+nx+2]

@@ -12,6 +12,7 @@
 // Work skipped relative to the literal reference: products with the zero initial hidden state
 // ("hoisted" FLOP count of SURVEY 8d).
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -210,6 +211,7 @@ int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, in
 }
 
 int launch_encode_tc(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream);
+int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream);
 
 // hist_ch: channels stored per history entry (model gin for nlc_model_forward, whose caller supplies the time channel
 // like the reference's forward; action_dim on the planner path, where encode_obs_time's channel is synthesised)
@@ -225,7 +227,12 @@ int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K
     case NLC_MATH_TC_FP16:
       // shapes without a tensor-core instantiation run on the fp32 kernel
       if (B < 2 || B * m->gin > 8 || m->gin > 2) return launch_encode_fp32(m, hist_dev, hist_ch, K, T, B, p_dev, s);
-      return launch_encode_tc(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
+      {
+        // NLC_ENCODER_V1=1 selects the first (lock-step) tcgen05 form for A/B measurements; default is the two-chain form
+        static const bool v1 = [] { const char* e = getenv("NLC_ENCODER_V1"); return e && e[0] == '1'; }();
+        if (v1) return launch_encode_tc(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
+        return launch_encode_tc2(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
+      }
     default: set_error("nlc_encode_history: unknown math_mode %d", math_mode); return NLC_ERR_ARG;
   }
 }

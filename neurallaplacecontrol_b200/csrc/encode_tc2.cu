@@ -1,0 +1,517 @@
+// Delayed-history encoder (ReverseGRUEncoder.forward, w_nl.py:25-29) on the 5th-generation tensor cores: the default
+// form.  (encode_tc.cu is the first, lock-step form, kept for A/B measurements behind NLC_ENCODER_V1=1 and for the UMMA
+// self-tests; encode_gru.cu is the fp32 CUDA-core anchor.)
+//
+// Dataflow as in encode_gru.cu: all K*T windows of a plan in one wide pass, M = 128 windows per tile, persistent CTAs,
+// zero-state products skipped; the ten 64x192 recurrent products of a window are tcgen05.mma (kind::f16) with fp32
+// accumulators in TMEM, the gate nonlinearities run on the CUDA cores.  What this form does differently, each item
+// from a measurement (profiles/r1_encoder_*.md):
+//   * a dedicated MMA warp.  tcgen05.mma issue is back-pressured by MMA execution (~95 clk per instruction measured
+//     with tools/trace_encoder.py), so an epilogue thread that also issues loses the whole MMA time every cell and the
+//     other warps end up waiting for it: a third of every step went into those waits.  16 epilogue warps + 1 MMA warp,
+//     coupled only by mbarriers (one arrival per warp); no CTA-wide barrier in the steady state;
+//   * -log2(e) / -2 log2(e) folded into the weight images, biases and layer-0 input weights on the host (model.cu):
+//     pre-activations feed ex2 directly;
+//   * gate arithmetic in packed fp32x2 (FFMA2/FADD2/FMUL2: half the issue slots, f32x2.cuh);
+//   * the (r, z) reciprocal is a Newton iteration on the FMA pipe instead of a MUFU.RCP: 4 MUFU per hidden unit
+//     instead of 5 (tools/pipe_bench.cu: 34 vs 41.5 clk per warp-unit on the bare gate);
+//   * W_ih1 rows ordered [n | r | z] and accumulator columns [in | r | z | hn]: a layer-1 cell is two N=192 products
+//     (24 MMA instructions instead of 48);
+//   * every thread prefetches its own window entry for the next cell straight from global memory (no staging barrier).
+//
+//   operands   fp16 hi (+ lo) images, K-major no-swizzle canonical layout; NLC_MATH_TC_SPLIT3: A_hi B_hi + A_lo B_hi +
+//              A_hi B_lo, fp32 accumulate (fp32-class);  NLC_MATH_TC_FP16: A_hi B_hi only.
+//   TMEM       D0[192] = [r | z | hn] of layer 0;  D1[256] = [in | r | z | hn] of layer 1.  Accumulators hold the
+//              biases between cells (re-written after every read), so MMAs always accumulate.
+//   schedule   layer 0 runs one cell ahead of layer 1, so every MMA burst runs under the other layer's gate epilogue:
+//                 epi A(s+1) || MMA B(s)   ->   epi B(s) || MMA A(s+2)   ->   ...        (tiles software-pipelined)
+//   barriers   bar_a / bar_b: MMA A / B complete (tcgen05.commit);  h0_ready / h1_ready: all 16 epilogue warps stored
+//              their operand slice and re-armed their accumulator columns.
+//   threads    epilogue warp w < 16: TMEM lanes 32 (w & 3).. (its 32 windows), hidden units 16 (w >> 2).. +15 of both
+//              layers; warp 16: MMA issue.  544 threads -> 96 registers per thread.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "f32x2.cuh"
+#include "tc_umma.cuh"
+
+namespace nlc {
+
+using namespace umma;
+
+namespace enc2 {
+
+constexpr int kRows = 128, kHg = 64, kG3 = 192, kThreads = 512;
+constexpr uint32_t kOpBytes = kRows * kHg * 2;  // one fp16 A-operand image (16 KB)
+constexpr uint32_t kWBytes = kG3 * kHg * 2;     // one fp16 weight image (24 KB)
+constexpr uint32_t kLbo = 128, kSbo = (kHg / 8) * 128;
+constexpr uint32_t kColD0 = 0, kColD1 = 192, kTmemCols = 512;
+
+struct Args {
+  const float* hist;
+  float* p_out;
+  int K, T, B, L, hist_ch;
+  int ablate;  // measurement only (NLC_ENC_ABLATE): 1 no MMA/waits, 2 no operand store, 4 no bias re-arm, 8 no gate math, 16 no TMEM loads
+  long long rows;
+  long long* trace;  // measurement only: clock64 timeline of CTA 0, [step][warp][8 events]
+  ModelDev m;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+  const float4 t0 = *reinterpret_cast<const float4*>(p), t1 = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+}
+__device__ __forceinline__ void lds8p(const float* p, f2_t (&v)[4]) {
+  float t[8];
+  lds8(p, t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = pk2(t[2 * i], t[2 * i + 1]);
+}
+__device__ __forceinline__ void ldtm8p(uint32_t taddr, f2_t (&v)[4]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = pk2u(r[2 * i], r[2 * i + 1]);
+}
+// re-arm 8 accumulator columns of this thread's TMEM lane with a bias vector
+__device__ __forceinline__ void bias_to_tmem8(uint32_t taddr, const float* b8) {
+  float v[8];
+  lds8(b8, v);
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+  tmem_st8(taddr, r);
+}
+
+// GRU cell update of two hidden units from pre-activations that already carry the exponent scales:
+//   pr, pz = -log2e (W_r. + b_r), -log2e (W_z. + b_z);   gi, gh = -2 log2e (W_in x + b_in), -2 log2e (W_hn h + b_hn)
+//   r = 1/(1 + 2^pr), z = 1/(1 + 2^pz) through ONE reciprocal of the product;  n = 2/(1 + 2^(gi + r gh)) - 1;
+//   h' = n + z (h - n).   Arguments of ex2 are clamped so that the shared-reciprocal product stays finite.
+template <int RZ, int NN>
+__device__ __forceinline__ f2_t gru_pair(f2_t pr, f2_t pz, f2_t gi, f2_t gh, f2_t h_old) {
+  float a0, a1, b0, b1;
+  upk2(pr, a0, a1);
+  upk2(pz, b0, b1);
+  const f2_t one = pk2(1.0f, 1.0f);
+  const f2_t da = add2(pk2(mufu_ex2(fminf(a0, 60.0f)), mufu_ex2(fminf(a1, 60.0f))), one);
+  const f2_t db = add2(pk2(mufu_ex2(fminf(b0, 60.0f)), mufu_ex2(fminf(b1, 60.0f))), one);
+  const f2_t inv = rcp2<RZ>(mul2(da, db));
+  const f2_t r = mul2(db, inv), z = mul2(da, inv);
+  float x0, x1;
+  upk2(fma2(r, gh, gi), x0, x1);
+  const f2_t dn = add2(pk2(mufu_ex2(fminf(x0, 120.0f)), mufu_ex2(fminf(x1, 120.0f))), one);
+  const f2_t invn = rcp2<NN>(dn);
+  const f2_t n = fma2(pk2(2.0f, 2.0f), invn, pk2(-1.0f, -1.0f));
+  const f2_t hm = fma2(pk2(-2.0f, -2.0f), invn, add2(h_old, one));  // h - n = (h + 1) - 2 invn
+  return fma2(z, hm, n);
+}
+
+// 8 hidden values of this thread's row -> one 16-byte slice of the fp16 hi (+ lo) A-operand image
+template <bool kSplit3>
+__device__ __forceinline__ void store_operand8(unsigned char* img_hi, unsigned char* img_lo, int row, int u0, const f2_t (&h)[4]) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float x0, x1;
+    upk2(h[i], x0, x1);
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    if (kSplit3) {
+      const float2 back = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
+      pl[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+  }
+  const uint32_t off = (uint32_t)(row >> 3) * kSbo + (uint32_t)(u0 >> 3) * kLbo + (uint32_t)(row & 7) * 16;
+  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  if (kSplit3) *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// D[128 x 192] += A[128 x 64] * B[192 x 64]^T : 4 (x3) MMA instructions
+template <bool kSplit3>
+__device__ __forceinline__ void issue_gemm192(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+  const uint32_t idesc = idesc_f16_f32(kRows, kG3);
+#pragma unroll
+  for (int ks = 0; ks < kHg / 16; ++ks) {
+    const uint32_t off = ks * 2 * kLbo;  // 16 K-elements = two core matrices
+    mma_f16_ss(d_tmem, smem_desc(a_hi + off, kLbo, kSbo), smem_desc(b_hi + off, kLbo, kSbo), idesc, 1u);
+    if (kSplit3) {
+      mma_f16_ss(d_tmem, smem_desc(a_lo + off, kLbo, kSbo), smem_desc(b_hi + off, kLbo, kSbo), idesc, 1u);
+      mma_f16_ss(d_tmem, smem_desc(a_hi + off, kLbo, kSbo), smem_desc(b_lo + off, kLbo, kSbo), idesc, 1u);
+    }
+  }
+}
+
+constexpr int kThreadsAll = kThreads + 32;  // 16 epilogue warps + the MMA warp
+
+struct Smem {
+  alignas(128) unsigned char w[3][2][kWBytes];
+  alignas(128) unsigned char h0[2][kOpBytes];
+  alignas(128) unsigned char h1[2][kOpBytes];
+  alignas(16) float c[kE2Count];
+  alignas(16) float pout[3][kRows * 2];
+  alignas(8) uint64_t bar_a, bar_b, h0_ready, h1_ready;
+  uint32_t tmem_base;
+};
+
+template <bool kSplit3, int GIN, int RZ, int NN>
+__global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, grp = warp >> 2;
+  const int row = 32 * q + lane;   // window within the tile == TMEM lane
+  const int ubase = 16 * grp;      // first of the 16 hidden units (per layer) this thread owns
+  const int B = a.B;
+  const int abl = a.ablate;
+  int tstep = 0;
+  auto mark = [&](int ev) {
+    if (a.trace && blockIdx.x == 0 && lane == 0 && tstep < 32) a.trace[(tstep * 16 + warp) * 8 + ev] = clock64();
+  };
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.m.enc2_w);
+    uint4* dst = reinterpret_cast<uint4*>(&s.w[0][0][0]);
+    for (int i = tid; i < (int)(3 * 2 * kWBytes / 16); i += kThreadsAll) dst[i] = __ldg(src + i);
+    for (int i = tid; i < kE2Count; i += kThreadsAll) s.c[i] = a.m.enc2_c[i];
+    if (tid == 0) {
+      mbar_init(&s.bar_a, 1); mbar_init(&s.bar_b, 1);
+      mbar_init(&s.h0_ready, kThreads / 32); mbar_init(&s.h1_ready, kThreads / 32);  // one arrival per epilogue warp
+      mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&s.tmem_base, kTmemCols);
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+  const float* cst = s.c;
+
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {  // accumulator columns start out holding the biases
+    if (warp >= 16) break;
+    const int u0 = ubase + 8 * c;
+    bias_to_tmem8(tlane + kColD0 + u0, cst + kE2Brz0 + u0);
+    bias_to_tmem8(tlane + kColD0 + 64 + u0, cst + kE2Brz0 + 64 + u0);
+    bias_to_tmem8(tlane + kColD0 + 128 + u0, cst + kE2Bhn0 + u0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias_to_tmem8(tlane + kColD1 + 64 * g + u0, cst + kE2B1 + 64 * g + u0);
+  }
+  tmem_st_wait();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+
+  const uint32_t a_h0_hi = smem_u32(s.h0[0]), a_h0_lo = smem_u32(s.h0[1]);
+  const uint32_t a_h1_hi = smem_u32(s.h1[0]), a_h1_lo = smem_u32(s.h1[1]);
+  const uint32_t w_hh0_hi = smem_u32(s.w[0][0]), w_hh0_lo = smem_u32(s.w[0][1]);
+  const uint32_t w_ih1_hi = smem_u32(s.w[1][0]), w_ih1_lo = smem_u32(s.w[1][1]);
+  const uint32_t w_hh1_hi = smem_u32(s.w[2][0]), w_hh1_lo = smem_u32(s.w[2][1]);
+  const long long n_tiles = (a.rows + kRows - 1) / kRows;
+
+
+  if (warp == 16) {
+    // =====================================  MMA warp  =====================================
+    // mirrors the epilogue warps' publication order: h0 (-> layer-0 product of the next cell), then h1 / D1 re-armed
+    // (-> layer-1 product of the next cell: input part from h0, hidden part from h1)
+    uint32_t n_h0 = 0, n_h1 = 0;
+    auto issue_a = [&]() {
+      if (lane == 0) {
+        fence_after_sync();
+        if (!(abl & 1)) issue_gemm192<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo);
+        mma_commit(&s.bar_a);
+      }
+      __syncwarp();
+    };
+    auto issue_b = [&](bool with_h1) {
+      if (lane == 0) {
+        fence_after_sync();
+        if (!(abl & 1)) {
+          issue_gemm192<kSplit3>(tmem + kColD1, a_h0_hi, a_h0_lo, w_ih1_hi, w_ih1_lo);
+          if (with_h1) issue_gemm192<kSplit3>(tmem + kColD1 + 64, a_h1_hi, a_h1_lo, w_hh1_hi, w_hh1_lo);
+        }
+        mma_commit(&s.bar_b);
+      }
+      __syncwarp();
+    };
+    if ((long long)blockIdx.x < n_tiles) {
+      mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;
+      issue_a();
+      mbar_wait_sleep(&s.h1_ready, n_h1 & 1); ++n_h1;
+      issue_b(false);
+    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const bool has_next = tile + gridDim.x < n_tiles;
+      for (int st = 0; st < B; ++st) {
+        if (st + 1 < B || has_next) {
+          mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;
+          if (st + 2 < B || (st + 1 == B && has_next)) issue_a();
+        }
+        mbar_wait_sleep(&s.h1_ready, n_h1 & 1); ++n_h1;
+        if (st + 1 < B) issue_b(true);
+        else if (has_next) issue_b(false);
+      }
+    }
+  } else {
+  float amean[GIN], ainv[GIN];
+#pragma unroll
+  for (int v = 0; v < GIN; ++v) { amean[v] = a.m.act_mean[v]; ainv[v] = a.m.act_inv_std[v]; }
+
+  uint32_t n_a = 0, n_b = 0;    // waits completed on bar_a / bar_b
+  f2_t h0r[8], h1r[8];
+  f2_t xx[GIN] = {};            // the window entry of the NEXT layer-0 cell (normalised, both halves equal), prefetched
+
+  // window entry j of this thread's row in tile `tile_`: reversed order, cell st consumes entry B-1-st (w_nl.py:27)
+  // hist offset of this thread's window in a tile (one integer division per tile, not per cell)
+  auto window_base = [&](long long tile_) -> size_t {
+    long long grow = tile_ * kRows + row;
+    if (grow >= a.rows) grow = a.rows - 1;
+    long long k;
+    if (a.rows <= 0x7fffffffLL) k = (long long)((unsigned)grow / (unsigned)a.T); else k = grow / a.T;
+    const int t = (int)(grow - k * a.T);
+    return ((size_t)k * a.L + t) * a.hist_ch;
+  };
+  size_t base_cur = 0, base_next = 0;
+  auto fetch_x = [&](bool next_tile_, int st_) {
+    if (abl & 64) return;
+    const int j = B - 1 - st_;
+    const float* src = a.hist + (next_tile_ ? base_next : base_cur) + (size_t)j * a.hist_ch;
+#pragma unroll
+    for (int v = 0; v < GIN; ++v) {
+      // channels beyond hist_ch: the time channel of encode_obs_time (mppi_with_model.py:110-119)
+      const float x = v < a.hist_ch ? __ldg(src + v) : (float)(B - 1 - j);
+      const float xn_ = (x - amean[v]) * ainv[v];  // w_nl.py:121
+      xx[v] = pk2(xn_, xn_);
+    }
+  };
+  // layer-0 cell: gates from D0 (or from the biases alone when the state is zero) + the input products
+  auto cell_a = [&](bool from_zero) {
+    f2_t xc[GIN];
+#pragma unroll
+    for (int v = 0; v < GIN; ++v) xc[v] = xx[v];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int u0 = ubase + 8 * c;
+      f2_t gr[4], gz[4], gh[4], gn[4];
+      if (!from_zero && !(abl & 16)) {
+        ldtm8p(tlane + kColD0 + u0, gr);
+        ldtm8p(tlane + kColD0 + 64 + u0, gz);
+        ldtm8p(tlane + kColD0 + 128 + u0, gh);
+      } else {
+        lds8p(cst + kE2Brz0 + u0, gr);
+        lds8p(cst + kE2Brz0 + 64 + u0, gz);
+        lds8p(cst + kE2Bhn0 + u0, gh);
+      }
+      lds8p(cst + kE2Bin0 + u0, gn);
+      if (!from_zero) tmem_ld_wait();
+#pragma unroll
+      for (int v = 0; v < GIN; ++v) {
+        if (abl & 32) break;
+        f2_t w[4];
+        lds8p(cst + kE2Wih0 + (0 * kMaxNu + v) * kHg + u0, w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gr[i] = fma2(w[i], xc[v], gr[i]);
+        lds8p(cst + kE2Wih0 + (1 * kMaxNu + v) * kHg + u0, w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gz[i] = fma2(w[i], xc[v], gz[i]);
+        lds8p(cst + kE2Wih0 + (2 * kMaxNu + v) * kHg + u0, w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gn[i] = fma2(w[i], xc[v], gn[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (abl & 8) h0r[4 * c + i] = add2(add2(gr[i], gz[i]), add2(gn[i], gh[i]));
+        else h0r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], from_zero ? 0ull : h0r[4 * c + i]);
+      }
+      if (!from_zero && !(abl & 4)) {
+        bias_to_tmem8(tlane + kColD0 + u0, cst + kE2Brz0 + u0);
+        bias_to_tmem8(tlane + kColD0 + 64 + u0, cst + kE2Brz0 + 64 + u0);
+        bias_to_tmem8(tlane + kColD0 + 128 + u0, cst + kE2Bhn0 + u0);
+      }
+    }
+  };
+  // publish h0r as the A operand; the elected thread then issues `issue_a` (layer-0 product of the next cell)
+  auto publish_h0 = [&](bool issue_a) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (abl & 2) break;
+      const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h0r[4 * c]);
+      store_operand8<kSplit3>(s.h0[0], s.h0[1], row, ubase + 8 * c, hc);
+    }
+    fence_proxy_async_smem();
+    tmem_st_wait();
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.h0_ready);
+    (void)issue_a;
+  };
+  // after the layer-1 epilogue: everyone re-armed D1 (and stored h1 when `with_h1`); the elected thread issues the
+  // next layer-1 product: input part from the h0 image (published earlier in program order), hidden part from h1
+  auto publish_h1_and_issue_b = [&](bool with_h1, bool issue) {
+    if (with_h1 && !(abl & 2)) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h1r[4 * c]);
+        store_operand8<kSplit3>(s.h1[0], s.h1[1], row, ubase + 8 * c, hc);
+      }
+      fence_proxy_async_smem();
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.h1_ready);
+    (void)issue;
+  };
+
+  // ---- head of the first tile: layer-0 cell 0 from the zero state, then A(1) and the input part of B(0) ----
+  if ((long long)blockIdx.x < n_tiles) {
+    base_cur = window_base(blockIdx.x);
+    fetch_x(false, 0);
+    cell_a(true);
+    fetch_x(false, 1);
+    publish_h0(true);
+    // nothing of layer 1 exists yet: arm the "D1 free / h1 published" phase so that B(0) can be issued uniformly
+    publish_h1_and_issue_b(false, true);
+  }
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * kRows;
+    const long long next_tile = tile + gridDim.x;
+    const bool has_next = next_tile < n_tiles;
+    if (has_next) base_next = window_base(next_tile);
+    for (int st = 0; st < B; ++st) {
+      // ================= layer-0 epilogue A(st+1) (or the next tile's cell 0)  ||  MMA B(st) =================
+      if (st + 1 < B) {
+        mark(0);
+        mbar_wait_sleep(&s.bar_a, n_a & 1); ++n_a;
+        fence_after_sync();
+        mark(1);
+        cell_a(false);
+        if (st + 2 < B) fetch_x(false, st + 2); else if (has_next) fetch_x(true, 0);
+      } else if (has_next) {
+        cell_a(true);
+        fetch_x(true, 1);
+      }
+      // MMA B(st) reads the h0 image: wait for its commit before overwriting (it also gates the epilogue below)
+      mark(2);
+      mbar_wait_sleep(&s.bar_b, n_b & 1); ++n_b;
+      fence_after_sync();
+      mark(3);
+      if (st + 1 < B) publish_h0(st + 2 < B);
+      else if (has_next) publish_h0(true);
+      mark(4);
+      // ================= layer-1 epilogue B(st)  ||  MMA A(st+2) =================
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int u0 = ubase + 8 * c;
+        f2_t gn[4], gr[4], gz[4], gh[4];
+        if (!(abl & 16)) {
+          ldtm8p(tlane + kColD1 + u0, gn);
+          ldtm8p(tlane + kColD1 + 64 + u0, gr);
+          ldtm8p(tlane + kColD1 + 128 + u0, gz);
+          ldtm8p(tlane + kColD1 + 192 + u0, gh);
+          tmem_ld_wait();
+        } else {
+          lds8p(cst + kE2B1 + u0, gn); lds8p(cst + kE2B1 + 64 + u0, gr); lds8p(cst + kE2B1 + 128 + u0, gz); lds8p(cst + kE2B1 + 192 + u0, gh);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (abl & 8) h1r[4 * c + i] = add2(add2(gr[i], gz[i]), add2(gn[i], gh[i]));
+          else h1r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], st > 0 ? h1r[4 * c + i] : 0ull);
+        }
+        if (!(abl & 4)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) bias_to_tmem8(tlane + kColD1 + 64 * g + u0, cst + kE2B1 + 64 * g + u0);
+        }
+      }
+      mark(5);
+      if (st + 1 < B) {
+        publish_h1_and_issue_b(true, true);
+        mark(6);
+        ++tstep;
+      } else {
+        // ---------------- linear_out on the top layer's last state (w_nl.py:29) ----------------
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x0, x1;
+          upk2(h1r[i], x0, x1);
+          const float2 wa = *reinterpret_cast<const float2*>(cst + kE2Wout + ubase + 2 * i);
+          const float2 wb = *reinterpret_cast<const float2*>(cst + kE2Wout + kHg + ubase + 2 * i);
+          o0 = fmaf(wa.y, x1, fmaf(wa.x, x0, o0));
+          o1 = fmaf(wb.y, x1, fmaf(wb.x, x0, o1));
+        }
+        if (grp > 0) {
+          *reinterpret_cast<float2*>(&s.pout[grp - 1][row * 2]) = make_float2(o0, o1);
+          asm volatile("bar.arrive 1, 512;" ::: "memory");
+        } else {
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          const float2 p0 = *reinterpret_cast<const float2*>(&s.pout[0][row * 2]);
+          const float2 p1 = *reinterpret_cast<const float2*>(&s.pout[1][row * 2]);
+          const float2 p2 = *reinterpret_cast<const float2*>(&s.pout[2][row * 2]);
+          if (row0 + row < a.rows)
+            *reinterpret_cast<float2*>(a.p_out + (row0 + row) * 2) =
+                make_float2(((o0 + p0.x) + p1.x) + p2.x + cst[kE2Bout], ((o1 + p0.y) + p1.y) + p2.y + cst[kE2Bout + 1]);
+        }
+        // D1 is re-armed: the input part of the next tile's B(0) can go (its h0 image was published above)
+        publish_h1_and_issue_b(false, has_next);
+        mark(6);
+        ++tstep;
+      }
+    }
+    base_cur = base_next;
+  }
+  }  // epilogue warps
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace enc2
+
+// measurement hooks (tools/trace_encoder.py, tools/bench_encoder.py)
+static long long* g_enc_trace = nullptr;
+void set_encoder_trace(long long* p) { g_enc_trace = p; }
+
+int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream) {
+  using namespace enc2;
+  NLC_REQUIRE(B * m->gin <= 8, NLC_ERR_SHAPE, "tcgen05 encoder: window_length * input_width = %d exceeds 8", B * m->gin);
+  NLC_REQUIRE(B >= 2, NLC_ERR_SHAPE, "tcgen05 encoder: window_length must be >= 2");
+  NLC_REQUIRE(m->gin == 1 || m->gin == 2, NLC_ERR_SHAPE, "tcgen05 encoder: GRU input width %d has no instantiation", m->gin);
+  Args a;
+  a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.hist_ch = hist_ch;
+  a.rows = (long long)K * T;
+  a.m = m->d;
+  a.trace = g_enc_trace;
+  { const char* e = getenv("NLC_ENC_ABLATE"); a.ablate = e ? atoi(e) : 0; }
+  const int smem = (int)sizeof(Smem) + 128;
+  // fp32-class mode: Newton (3 steps) for the (r, z) reciprocal, MUFU for n  (pipe_bench "v3");
+  // single-pass fp16 mode: two Newton steps for both (relative error 2e-4, inside that mode's 2e-2 bound).
+  // NLC_ENC_RCP=<rz><nn> (digits 0 or 3) overrides the fp32-class choice for measurements.
+  static const int rcp_sel = [] { const char* e = getenv("NLC_ENC_RCP"); return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 30; }();
+  void (*kern)(Args);
+  if (!split3) kern = m->gin == 1 ? encode_tc2_kernel<false, 1, 2, 2> : encode_tc2_kernel<false, 2, 2, 2>;
+  else if (rcp_sel == 0) kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 0, 0> : encode_tc2_kernel<true, 2, 0, 0>;
+  else if (rcp_sel == 33) kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 3, 3> : encode_tc2_kernel<true, 2, 3, 3>;
+  else kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 3, 0> : encode_tc2_kernel<true, 2, 3, 0>;
+  NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long n_tiles = (a.rows + kRows - 1) / kRows;
+  const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
+  kern<<<grid, kThreadsAll, smem, stream>>>(a);
+  NLC_LAUNCH_OK("encode_tc2_kernel");
+  return NLC_OK;
+}
+
+}  // namespace nlc
+
+// measurement hook (tools/trace_encoder.py): device buffer of 32*16*8 int64 receiving CTA 0's clock64 timeline
+extern "C" void nlc_debug_set_encoder_trace(void* dev_ptr) { nlc::set_encoder_trace(static_cast<long long*>(dev_ptr)); }

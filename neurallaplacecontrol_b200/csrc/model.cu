@@ -149,6 +149,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   // tensor-core operand image of the three recurrent GRU matrices: fp16 hi/lo, UMMA canonical layout
   const size_t tc_halves = (size_t)3 * 2 * G3 * Hg;
   size_t o_tc = A.add(tc_halves / 2);
+  size_t o_enc2w = A.add(tc_halves / 2), o_enc2c = A.add(nlc::kE2Count);
   size_t o_tc_w2 = A.add((size_t)2 * Hm * Hm / 2), o_tc_w3 = A.add((size_t)2 * N3t * Hm / 2), o_b3tc = A.add(N3t);
 
   for (int i = 0; i < G3 * gin; ++i) put(o_w_ih0, i, d->gru_w_ih_l0[i]);
@@ -201,6 +202,37 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
     for (int w = 0; w < 3; ++w)
       nlc::tc_pack_weight_split(mats[w], G3, Hg, tc + (size_t)w * 2 * G3 * Hg, tc + (size_t)w * 2 * G3 * Hg + (size_t)G3 * Hg);
   }
+  {
+    // encode_tc2.cu operands: exponent scales folded (sigmoid(x) = 1/(1 + 2^(-log2e x)), tanh(x) = 2/(1 + 2^(-2 log2e x)) - 1)
+    const double cR = -1.4426950408889634, cN = 2.0 * cR;
+    auto gate_scale = [&](int row) { return row < 2 * Hg ? cR : cN; };
+    std::vector<double> w((size_t)G3 * Hg);
+    uint16_t* tc2 = reinterpret_cast<uint16_t*>(A.data.data() + o_enc2w);
+    const double* mats[3] = {d->gru_w_hh_l0, d->gru_w_ih_l1, d->gru_w_hh_l1};
+    for (int mi = 0; mi < 3; ++mi) {
+      for (int r = 0; r < G3; ++r) {
+        // destination row order: natural [r | z | n], except W_ih1 -> [n | r | z]
+        const int dst = (mi == 1) ? (r < 2 * Hg ? r + Hg : r - 2 * Hg) : r;
+        for (int k = 0; k < Hg; ++k) w[(size_t)dst * Hg + k] = gate_scale(r) * mats[mi][(size_t)r * Hg + k];
+      }
+      nlc::tc_pack_weight_split(w.data(), G3, Hg, tc2 + (size_t)mi * 2 * G3 * Hg, tc2 + (size_t)mi * 2 * G3 * Hg + (size_t)G3 * Hg);
+    }
+    for (int i = 0; i < 2 * Hg; ++i) put(o_enc2c, nlc::kE2Brz0 + i, cR * (d->gru_b_ih_l0[i] + d->gru_b_hh_l0[i]));
+    for (int u = 0; u < Hg; ++u) {
+      put(o_enc2c, nlc::kE2Bin0 + u, cN * d->gru_b_ih_l0[2 * Hg + u]);
+      put(o_enc2c, nlc::kE2Bhn0 + u, cN * d->gru_b_hh_l0[2 * Hg + u]);
+      put(o_enc2c, nlc::kE2B1 + u, cN * d->gru_b_ih_l1[2 * Hg + u]);
+      put(o_enc2c, nlc::kE2B1 + Hg + u, cR * (d->gru_b_ih_l1[u] + d->gru_b_hh_l1[u]));
+      put(o_enc2c, nlc::kE2B1 + 2 * Hg + u, cR * (d->gru_b_ih_l1[Hg + u] + d->gru_b_hh_l1[Hg + u]));
+      put(o_enc2c, nlc::kE2B1 + 3 * Hg + u, cN * d->gru_b_hh_l1[2 * Hg + u]);
+    }
+    for (int g = 0; g < 3; ++g)
+      for (int v = 0; v < gin; ++v)
+        for (int u = 0; u < Hg; ++u)
+          put(o_enc2c, nlc::kE2Wih0 + (size_t)(g * nlc::kMaxNu + v) * Hg + u, (g < 2 ? cR : cN) * d->gru_w_ih_l0[(size_t)(g * Hg + u) * gin + v]);
+    for (int i = 0; i < 2 * Hg; ++i) put(o_enc2c, nlc::kE2Wout + i, d->enc_out_w[i]);
+    for (int i = 0; i < 2; ++i) put(o_enc2c, nlc::kE2Bout + i, d->enc_out_b[i]);
+  }
 
   {
     uint16_t* w2i = reinterpret_cast<uint16_t*>(A.data.data() + o_tc_w2);
@@ -236,6 +268,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   m->d.w_hh0_t = base + o_hh0; m->d.w_ih1_t = base + o_ih1; m->d.w_hh1_t = base + o_hh1;
   m->d.b_ih1 = base + o_b_ih1; m->d.b_hh1 = base + o_b_hh1; m->d.w_out = base + o_wout; m->d.b_out = base + o_bout;
   m->d.enc_tc_w = base + o_tc; m->d.mlp_tc_w2 = base + o_tc_w2; m->d.mlp_tc_w3 = base + o_tc_w3; m->d.b3_tc = base + o_b3tc;
+  m->d.enc2_w = base + o_enc2w; m->d.enc2_c = base + o_enc2c;
   m->d.w1_full_t = base + o_w1full; m->d.b1_raw = base + o_b1raw; m->d.w1x_t = base + o_w1x; m->d.b1_fold = base + o_b1f;
   m->d.w2_t = base + o_w2; m->d.b2 = base + o_b2; m->d.w3_t = base + o_w3; m->d.b3 = base + o_b3;
   m->d.ilt_phase = base + o_phase; m->d.ilt_weight = base + o_weight;
