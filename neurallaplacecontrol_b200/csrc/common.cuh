@@ -67,6 +67,14 @@ struct ModelDev {
   // columns); and the matching fp32 constants (biases, layer-0 input weights, output layer), layout kE2* below
   void* enc2_w;
   float* enc2_c;
+  // rollout_tc2.cu: representation MLP with -2 log2(e) folded into every layer (all three feed tanh-like maps):
+  // mlp2_w1 [2 (hi,lo)][128 x 16]  first layer on the tensor cores, K = [obs_n | p_action | 1 (folded bias) | 0..]
+  //                                 (re-packed by nlc_model_set_prediction_time: the bias depends on the s-points);
+  // mlp2_w2 [2][128 x 128]; mlp2_w3 [2][N3t x 128] pair-permuted; mlp2_c = [b2 (128) | b3 (256)] scaled
+  void* mlp2_w1;
+  void* mlp2_w2;
+  void* mlp2_w3;
+  float* mlp2_c;
   // fp16 hi/lo operand images of the representation MLP for the tcgen05 rollout (rollout_tc.cu):
   // mlp_tc_w2 [2 (hi,lo)][128 x 128], mlp_tc_w3 [2][N3t x 128] with the pair-permuted rows of w3_t, zero padded
   void* mlp_tc_w2;

@@ -46,6 +46,24 @@ __device__ __forceinline__ float env_running_cost(const nlc_rollout_opts& o, con
   }
 }
 
+// Same cost for the tensor-core rollout (rollout_tc2.cu), where the acrobot's atan2 -> sincos round trip
+// (ctacrobot.py:153-166,233-255) sat on the critical path of every step: cos(atan2(s, c)) = c / sqrt(c^2 + s^2), so the
+// angles are never formed - an algebraic identity (difference ~1 ulp of fp32), pendulum and cartpole unchanged.
+__device__ __forceinline__ float env_running_cost_fast(const nlc_rollout_opts& o, const float* s, const float* u, int nu) {
+  if (o.env != NLC_ENV_ACROBOT) return env_running_cost(o, s, u, nu);
+  float ac = 0.0f;
+  for (int i = 0; i < nu; ++i) ac = fmaf(u[i], u[i], ac);
+  const float r1 = rsqrtf(fmaf(s[0], s[0], s[1] * s[1])), r2 = rsqrtf(fmaf(s[2], s[2], s[3] * s[3]));
+  const float c1 = s[0] * r1, s1 = s[1] * r1, c2 = s[2] * r2, s2 = s[3] * r2;
+  const float c12 = fmaf(c1, c2, -(s1 * s2)), s12 = fmaf(s1, c2, c1 * s2);
+  const float vel = -(s[4] * s[4]) - s[5] * s[5];
+  const float p2x = -c1 - c12, p2y = s1 + s12;
+  const float dx = p2x - 2.0f;
+  const float state_reward = -(dx * dx) - p2y * p2y;
+  const float reward = state_reward + 0.1f * vel + (-1e-4f * ac);
+  return -reward;
+}
+
 // One explicit-Euler step with the action delayed by `delay` entries (oracle.py:11-224, friction=False,
 // trigonometric observation form).  `u` points at window[-(delay+1)].
 __device__ __forceinline__ void env_analytic_step(const nlc_rollout_opts& o, float* s, const float* u) {

@@ -99,7 +99,23 @@ static int fold_prediction_time(nlc_model_s* m, double ts_pred) {
     for (int k = 0; k < S; ++k) acc += row[S + k] * ph[k];
     b1[n] = (float)acc;
   }
+  // first layer as a K = 16 tensor-core operand (rollout_tc2.cu): columns [obs_n | p_action | folded bias | 0..], -2 log2(e) folded
+  std::vector<uint16_t> w1img((size_t)2 * Hm * 16);
+  {
+    const double cN = -2.0 * 1.4426950408889634;
+    std::vector<double> w1((size_t)Hm * 16, 0.0);
+    for (int n = 0; n < Hm; ++n) {
+      double acc = m->h.b0[n];
+      const double* row = m->h.w0 + (size_t)n * in0;
+      for (int k = 0; k < S; ++k) acc += row[k] * th[k];
+      for (int k = 0; k < S; ++k) acc += row[S + k] * ph[k];
+      for (int j = 0; j < L; ++j) w1[(size_t)n * 16 + j] = cN * row[2 * S + j];
+      w1[(size_t)n * 16 + L] = cN * acc;
+    }
+    nlc::tc_pack_weight_split(w1.data(), Hm, 16, w1img.data(), w1img.data() + (size_t)Hm * 16);
+  }
   NLC_CUDA_OK(cudaSetDevice(m->device));
+  NLC_CUDA_OK(cudaMemcpy(m->d.mlp2_w1, w1img.data(), w1img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   NLC_CUDA_OK(cudaMemcpy(m->d.b1_fold, b1.data(), sizeof(float) * Hm, cudaMemcpyHostToDevice));
   NLC_CUDA_OK(cudaMemcpy(m->d.ilt_phase, phase.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
   NLC_CUDA_OK(cudaMemcpy(m->d.ilt_weight, weight.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
@@ -150,6 +166,8 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   const size_t tc_halves = (size_t)3 * 2 * G3 * Hg;
   size_t o_tc = A.add(tc_halves / 2);
   size_t o_enc2w = A.add(tc_halves / 2), o_enc2c = A.add(nlc::kE2Count);
+  size_t o_m2w1 = A.add((size_t)2 * Hm * 16 / 2), o_m2w2 = A.add((size_t)2 * Hm * Hm / 2), o_m2w3 = A.add((size_t)2 * N3t * Hm / 2);
+  size_t o_m2c = A.add(128 + 256);
   size_t o_tc_w2 = A.add((size_t)2 * Hm * Hm / 2), o_tc_w3 = A.add((size_t)2 * N3t * Hm / 2), o_b3tc = A.add(N3t);
 
   for (int i = 0; i < G3 * gin; ++i) put(o_w_ih0, i, d->gru_w_ih_l0[i]);
@@ -249,6 +267,25 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
     nlc::tc_pack_weight_split(w3p.data(), N3t, Hm, w3i, w3i + (size_t)N3t * Hm);
   }
 
+  if (N3t <= 256) {  // rollout_tc2.cu operands: -2 log2(e) folded
+    const double cN = -2.0 * 1.4426950408889634;
+    std::vector<double> w2s((size_t)Hm * Hm);
+    for (size_t i = 0; i < w2s.size(); ++i) w2s[i] = cN * d->mlp_w2[i];
+    uint16_t* w2i = reinterpret_cast<uint16_t*>(A.data.data() + o_m2w2);
+    nlc::tc_pack_weight_split(w2s.data(), Hm, Hm, w2i, w2i + (size_t)Hm * Hm);
+    std::vector<double> w3p((size_t)N3t * Hm, 0.0);
+    for (int c = 0; c < nx; ++c)
+      for (int k = 0; k < S; ++k)
+        for (int part = 0; part < 2; ++part) {
+          const int src = (part * nx + c) * S + k, dst = 2 * (c * S + k) + part;
+          for (int h = 0; h < Hm; ++h) w3p[(size_t)dst * Hm + h] = cN * d->mlp_w4[(size_t)src * Hm + h];
+          put(o_m2c, 128 + dst, cN * d->mlp_b4[src]);
+        }
+    uint16_t* w3i = reinterpret_cast<uint16_t*>(A.data.data() + o_m2w3);
+    nlc::tc_pack_weight_split(w3p.data(), N3t, Hm, w3i, w3i + (size_t)N3t * Hm);
+    for (int n = 0; n < Hm; ++n) put(o_m2c, n, cN * d->mlp_b2[n]);
+  }
+
   m->h.w0 = new double[(size_t)Hm * in0];
   m->h.b0 = new double[Hm];
   memcpy(m->h.w0, d->mlp_w0, sizeof(double) * Hm * in0);
@@ -269,6 +306,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   m->d.b_ih1 = base + o_b_ih1; m->d.b_hh1 = base + o_b_hh1; m->d.w_out = base + o_wout; m->d.b_out = base + o_bout;
   m->d.enc_tc_w = base + o_tc; m->d.mlp_tc_w2 = base + o_tc_w2; m->d.mlp_tc_w3 = base + o_tc_w3; m->d.b3_tc = base + o_b3tc;
   m->d.enc2_w = base + o_enc2w; m->d.enc2_c = base + o_enc2c;
+  m->d.mlp2_w1 = base + o_m2w1; m->d.mlp2_w2 = base + o_m2w2; m->d.mlp2_w3 = base + o_m2w3; m->d.mlp2_c = base + o_m2c;
   m->d.w1_full_t = base + o_w1full; m->d.b1_raw = base + o_b1raw; m->d.w1x_t = base + o_w1x; m->d.b1_fold = base + o_b1f;
   m->d.w2_t = base + o_w2; m->d.b2 = base + o_b2; m->d.w3_t = base + o_w3; m->d.b3 = base + o_b3;
   m->d.ilt_phase = base + o_phase; m->d.ilt_weight = base + o_weight;

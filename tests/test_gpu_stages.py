@@ -270,10 +270,12 @@ def test_tc_encoder_matches_reference(env, mode, tol):
     assert relerr(outs["fp32"], outs[mode]) < tol, relerr(outs["fp32"], outs[mode])
 
 
+@pytest.mark.parametrize("form", ["1", "2"])
 @pytest.mark.parametrize("mode,tol", [("tc_split3", 1e-4), ("tc_fp16", 2e-2)])
-def test_tc_plan_cfg1(mode, tol):
-    """BASELINE config 1 end to end with the tensor-core encoder.  tc_split3 holds the fp32 bound (1e-4); the
-    single-pass fp16 mode is the stated looser bound."""
+def test_tc_plan_cfg1(mode, tol, form, monkeypatch):
+    """BASELINE config 1 end to end with the tensor-core encoder and either form of the tensor-core rollout.  tc_split3
+    holds the fp32 bound (1e-4); the single-pass fp16 mode is the stated looser bound."""
+    monkeypatch.setenv("NLC_ROLLOUT_FORM", form)
     from oracle.gen_golden import START_STATE, injected_noise
     from test_gpu_parity import _run_plan
     from _util import action_relerr, load
@@ -288,6 +290,51 @@ def test_tc_plan_cfg1(mode, tol):
     assert relerr(g["states_last"], out["states"][:, -1]) < tol
     assert relerr(g["U"], out["U"]) < tol * (1 if mode == "tc_split3" else 5)
     assert action_relerr(g["action"], out["action"], g["U"], 2.0) < tol * (1 if mode == "tc_split3" else 5)
+
+
+@pytest.mark.parametrize("env,K,T", [("oderl-acrobot", 20011, 6), ("oderl-cartpole", 19000, 5), ("oderl-pendulum", 40000, 4)])
+def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
+    """Plans larger than one wave of 128-sample tiles take the two-tiles-per-CTA rollout (partially filled and ragged
+    last tiles, K not a multiple of 32): same costs and states as the one-tile form and as the fp32 anchor kernel."""
+    import ctypes as C
+
+    from oracle import costs
+    from test_gpu_parity import make_model
+
+    L = _lib()
+    lib = L.load()
+    nx, nu = costs.ENV_DIMS[env]
+    m = make_model(env, calibrated=True, math_mode="tc_split3")
+    h = m.set_prediction_time(DT)
+    B = 4
+    gen = torch.Generator().manual_seed(K)
+    hist = ((torch.rand(K, B - 1 + T, nu, generator=gen) * 2 - 1) * costs.ENV_ACT_HIGH[env]).cuda().contiguous()
+    state = (torch.tensor(costs_start(env), dtype=torch.float32) + 0.05 * torch.randn(K, nx, generator=gen)).cuda().contiguous()
+    p = torch.empty(K, T, 2, device="cuda")
+    L.check(lib.nlc_encode_history(h, hist.data_ptr(), K, T, B, p.data_ptr(), L.MATH_MODES["tc_split3"], L.current_stream_ptr()))
+    ro = L.RolloutOpts()
+    ro.env, ro.state_constraint, ro.goal_x, ro.dynamics, ro.delay, ro.dt = L.ENV_IDS[env], 0, 0.0, 0, 0, DT
+    outs = {}
+    for name, mode, form in (("fp32", "fp32", "1"), ("one_tile", "tc_split3", "1"), ("two_tiles", "tc_split3", "2"), ("auto", "tc_split3", "")):
+        if form:
+            monkeypatch.setenv("NLC_ROLLOUT_FORM", form)
+        else:
+            monkeypatch.delenv("NLC_ROLLOUT_FORM", raising=False)
+        cost = torch.full((K,), float("nan"), device="cuda")
+        states = torch.full((K, T, nx), float("nan"), device="cuda")
+        L.check(lib.nlc_rollout_cost(h, C.byref(ro), state.data_ptr(), 1, p.data_ptr(), hist.data_ptr(), None, K, T, B, nu,
+                                     cost.data_ptr(), states.data_ptr(), L.MATH_MODES[mode], L.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.isfinite(cost).all() and torch.isfinite(states).all(), name
+        outs[name] = (cost, states)
+    assert torch.equal(outs["auto"][0], outs["two_tiles"][0])  # the library picks the two-tile form for this size
+    for name in ("one_tile", "two_tiles"):
+        assert relerr(outs["fp32"][0], outs[name][0]) < 1e-4, (name, relerr(outs["fp32"][0], outs[name][0]))
+        assert relerr(outs["fp32"][1], outs[name][1]) < 1e-4, (name, relerr(outs["fp32"][1], outs[name][1]))
+
+
+def costs_start(env):
+    return {"oderl-pendulum": [-1.0, 0.0, 1.0], "oderl-cartpole": [0.0, 0.0, -1.0, 0.0, 0.0], "oderl-acrobot": [1.0, 0.0, 1.0, 0.0, 0.0, 0.0]}[env]
 
 
 @pytest.mark.parametrize("N,Kdim,rows_b", [(64, 64, 64), (128, 128, 128), (208, 128, 208), (176, 128, 176), (112, 128, 112)])
