@@ -295,21 +295,25 @@ def run_gpu(args, env, K, H, desc):
         e2e = steps_per_plan / (ms_e2e * 1e-3)
         enc_flop = ENCODER_FLOP * Kl * H
         roll_flop = (HOISTED_FLOP[env] - ENCODER_FLOP) * Kl * H
-        kernels = {"encoder": {"name": "encode_gru_kernel" if args.math == "fp32" else "encode_tc_kernel", "ms": ms_enc, "flop": enc_flop},
-                   "rollout": {"name": "rollout_nl_kernel" if args.math == "fp32" else "rollout_tc_kernel", "ms": ms_roll, "flop": roll_flop}}
+        two_tiles = (Kl + 127) // 128 > 148 and os.environ.get("NLC_ROLLOUT_FORM", "") != "1"  # the library's own choice
+        roll_name = "rollout_nl_kernel" if args.math == "fp32" else ("rollout_tc2_kernel" if two_tiles else "rollout_tc_kernel")
+        kernels = {"encoder": {"name": "encode_gru_kernel" if args.math == "fp32" else "encode_tc2_kernel", "ms": ms_enc, "flop": enc_flop},
+                   "rollout": {"name": roll_name, "ms": ms_roll, "flop": roll_flop}}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
         for kv in kernels.values():
             kv["tflops"] = kv["flop"] / (kv["ms"] * 1e-3) / 1e12
             kv["frac"] = kv["tflops"] / peaks["bf16_tflops_sustained"]
         achieved = kernels[dom]["tflops"]
         # secondary roofline: transcendental (MUFU / XU pipe) throughput.  Counts per rollout-step from the kernels' code:
-        # encoder 8 GRU cells x 64 units x (2 ex2 + 1 shared rcp for r,z; ex2 + rcp for n) = 2560 (3 tanh.approx in tc_fp16);
-        # rollout 2 x 128 tanh (ex2 + rcp) + nx*S pairs x (tanh 2 + sphere radius 3 + cos 1).  Peak: 16 /clk/SM measured
-        # by tools/mufu_bench.cu (15.9) x 148 SMs x the SM clock seen during the run.
+        # encoder 8 GRU cells x 64 units x (3 ex2 + 1 rcp; the (r,z) reciprocal is a Newton iteration on the FMA pipe) =
+        # 2048 (3 tanh.approx in tc_fp16); two-tile rollout 2 x 128 tanh (1 ex2 each) + nx*S pairs x (2 ex2 + cos + rcp);
+        # one-tile rollout 2 x 128 x 2 + nx*S x 6.  Peak: 16 /clk/SM measured by tools/mufu_bench.cu (15.9) x 148 SMs x the
+        # SM clock seen during the run.
         if args.math != "fp32":
             sm_hz = 1e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
             mufu_peak = 15.9 * 148 * sm_hz
-            per_step = {"encoder": 8 * 64 * (5 if args.math == "tc_split3" else 3), "rollout": 4 * 128 + nx * inp["S"] * 6}
+            per_step = {"encoder": 8 * 64 * (4 if args.math == "tc_split3" else 3),
+                        "rollout": (2 * 128 + nx * inp["S"] * 4) if two_tiles else (4 * 128 + nx * inp["S"] * 6)}
             for name, kv in kernels.items():
                 kv["mufu_per_s"] = per_step[name] * Kl * H / (kv["ms"] * 1e-3)
                 kv["mufu_frac"] = kv["mufu_per_s"] / mufu_peak
@@ -335,8 +339,8 @@ def run_gpu(args, env, K, H, desc):
                          "kernel_ms": kernels[dom]["ms"], "flop_per_launch": kernels[dom]["flop"], "kernels": kernels,
                          "note": "algorithmic (hoisted) FLOPs per launch / CUDA-event time; peak = measured sustained bf16 "
                                  "tensor TFLOP/s.  tc_split3 issues 3 fp16 MMAs per algorithmic product (fp32-class result), "
-                                 "so frac <= 1/3 by construction; both kernels are MUFU/issue bound in their epilogues "
-                                 "(see profiles/).",
+                                 "so frac <= 1/3 by construction; both kernels are bound by their CUDA-core gate / sphere-map "
+                                 "epilogues (MUFU + issue), not by the MMAs (see profiles/ and DESIGN.md 3).",
                          "whole_step_achieved": HOISTED_FLOP[env] * steps_per_plan / (ms_dev * 1e-3) / 1e12},
         }
         if world == 1 and not args.no_cpu_baseline:
