@@ -167,7 +167,8 @@ typedef struct {
 } nlc_rollout_opts;
 
 /* Stages 2+3: mppi_delay.py:232-313 with the closures of mppi_with_model.py:103-122,145-171.
- * state_dev [nx] or [K][nx] (state_per_sample), p_dev [K][T][2] from nlc_encode_history (NULL for
+ * state_dev [nx] (state_per_sample = 0), [K][nx] (= 1) or [ceil(K/n)][nx] (= n > 1: sample k starts from
+ * state k / n, the instance-batched form), p_dev [K][T][2] from nlc_encode_history (NULL for
  * analytic dynamics), hist_dev as written by nlc_perturb, pert_cost_dev [K] added to the result
  * (may be NULL).  cost_total_dev [K]; states_dev [K][T][nx] optional.                              */
 int nlc_rollout_cost(nlc_model_t m, const nlc_rollout_opts* o, const float* state_dev, int state_per_sample,
@@ -233,6 +234,36 @@ int nlc_planner_finish(nlc_planner_t p, void* stream);
  * runs both phases, copies the action [nu] back and synchronises the stream.                      */
 int nlc_planner_command_host(nlc_planner_t p, const double* state_host, const double* action_buffer_host,
                              const float* noise_in_dev, double* action_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Instance-batched planning and the closed loop (BASELINE config 5; the caller side of the path,
+ * mppi_with_model.py:193-216,244-317, for many env x seed instances of ONE environment at once).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct nlc_batch_planner_s* nlc_batch_planner_t;
+
+/* n_instances independent MPPIDelay objects (desc->mppi.K samples EACH, desc->n_shards must be 1) with
+ * their own control sequence, action buffer and sampler seed; seeds_host [n_instances].  Instance i
+ * reproduces nlc_planner_create(desc with seed = seeds[i]).                                         */
+int nlc_batch_planner_create(nlc_batch_planner_t* out, nlc_model_t model, const nlc_planner_desc* desc, int n_instances,
+                             const uint64_t* seeds_host, int device);
+int nlc_batch_planner_destroy(nlc_batch_planner_t p);
+/* U_host fp64 [n_instances][T][nu]                                                                  */
+int nlc_batch_planner_set_U(nlc_batch_planner_t p, const double* U_host);
+/* buffers are the single planner's, concatenated over instances (NLC_BUF_U .. NLC_BUF_P)            */
+int nlc_batch_planner_buffer(nlc_batch_planner_t p, int which, void** dev_ptr, int64_t* n_floats);
+/* MPPIDelay.command for every instance: state_dev [I][nx], action_buffer_dev [I][B][nu],
+ * noise_in_dev [I][K][T][nu] or NULL (on-device sampler), action_dev [I][nu] (env units).
+ * Stage 1 and 4 run per instance, the encoder and the rollout once over all I*K samples.            */
+int nlc_batch_planner_command(nlc_batch_planner_t p, const float* state_dev, const float* action_buffer_dev,
+                              const float* noise_in_dev, float* action_dev, void* stream);
+
+/* step_env (mppi_with_model.py:193-216) for I instances: action_buffer <- roll(action_buffer, -1),
+ * action_buffer[-1] <- action (get_action, :25-28); the delayed action action_buffer[-(o->delay+1)] drives
+ * one explicit-Euler step of the true dynamics (base_env.py:136-173 as stated by oracle.py:11-224,
+ * observation form); reward_dev [I] (optional) = reward of the new state with the applied action.
+ * state_dev [I][nx] and action_buffer_dev [I][B][nu] are updated in place.                          */
+int nlc_env_step(const nlc_rollout_opts* o, float* state_dev, float* action_buffer_dev, const float* action_dev,
+                 int I, int B, int nu, float* reward_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Generic Fourier-series inverse Laplace transform (torchlaplace's Fourier ILT as called from

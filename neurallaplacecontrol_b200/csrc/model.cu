@@ -33,14 +33,20 @@ int check_device_arch(int device) {
     set_error("device %d out of range (%d visible)", device, n);
     return NLC_ERR_ARCH;
   }
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
-    cudaGetLastError();
-    set_error("cudaGetDeviceProperties(%d) failed", device);
-    return NLC_ERR_ARCH;
+  // the answer cannot change while the process lives; cudaGetDeviceProperties costs milliseconds, so ask once per device
+  static std::atomic<int> cached_major[64];
+  int major = device < 64 ? cached_major[device].load(std::memory_order_relaxed) : 0, minor = 0;
+  if (major == 0) {
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaDeviceGetAttribute(%d) failed", device);
+      return NLC_ERR_ARCH;
+    }
+    if (device < 64) cached_major[device].store(major, std::memory_order_relaxed);
   }
-  if (prop.major != 10) {
-    set_error("device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+  if (major != 10) {
+    set_error("device %d is sm_%dx; the kernels are built for sm_100a only", device, major);
     return NLC_ERR_ARCH;
   }
   return NLC_OK;

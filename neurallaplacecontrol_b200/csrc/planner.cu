@@ -183,3 +183,147 @@ extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_hos
   for (int i = 0; i < mp.nu; ++i) action_host[i] = p->h_out[i];
   return NLC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Instance-batched planner (BASELINE config 5: many env x seed instances planning in the same control step).
+// I independent MPPIDelay objects of one environment / model share ONE wide encoder launch and ONE rollout launch over
+// the concatenated I*K samples (both kernels are row-independent; the rollout reads each instance's state through the
+// rows-per-state form of `state_per_sample`); stage 1 and stage 4 run per instance on the instance's contiguous slices
+// with the same kernels - and hence the same arithmetic - as the single planner, so instance i of a batch reproduces a
+// stand-alone planner with the same seed.
+// ------------------------------------------------------------------------------------------------------------------
+struct nlc_batch_planner_s {
+  int device, I;
+  nlc_model_t model;
+  nlc_planner_desc d;          // per instance (mppi.K = samples per instance)
+  std::vector<uint64_t> seeds;
+  uint64_t calls;
+  void* arena;
+  float *U, *U_rolled, *noise, *perturbed, *hist, *actions, *pert_cost, *p, *cost_total, *weights, *states, *triple, *stats;
+  char* softmax_ws;
+  size_t ws_stride;
+};
+
+extern "C" int nlc_batch_planner_create(nlc_batch_planner_t* out, nlc_model_t model, const nlc_planner_desc* d, int n_instances,
+                                        const uint64_t* seeds, int device) {
+  NLC_REQUIRE(out && d && seeds, NLC_ERR_ARG, "nlc_batch_planner_create: null argument");
+  *out = nullptr;
+  int rc = check_device_arch(device);
+  if (rc != NLC_OK) return rc;
+  const nlc_mppi_params& mp = d->mppi;
+  NLC_REQUIRE(n_instances >= 1 && n_instances <= 4096, NLC_ERR_ARG, "batch planner: 1..4096 instances");
+  NLC_REQUIRE(mp.K >= 1 && mp.T >= 1 && mp.B >= 1 && mp.B <= 8, NLC_ERR_SHAPE, "batch planner: K, T >= 1 and 1 <= B <= 8 required");
+  NLC_REQUIRE(mp.nu >= 1 && mp.nu <= 4 && d->nx >= 1 && d->nx <= kMaxNx, NLC_ERR_SHAPE, "batch planner: nu/nx out of range");
+  NLC_REQUIRE(mp.T * mp.nu <= 256, NLC_ERR_SHAPE, "batch planner: T*nu exceeds 256");
+  NLC_REQUIRE(d->n_shards == 1 && d->shard_index == 0, NLC_ERR_UNSUPPORTED, "batch planner: instances are not K-sharded (shard by instance)");
+  NLC_REQUIRE(mp.lambda_ > 0.0f, NLC_ERR_ARG, "batch planner: lambda must be positive");
+  NLC_REQUIRE((long long)n_instances * mp.K <= 0x7fffffffLL / (mp.T * 4), NLC_ERR_SHAPE, "batch planner: I*K*T too large");
+  if (d->rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
+    NLC_REQUIRE(model != nullptr, NLC_ERR_ARG, "batch planner: Neural Laplace dynamics need a model handle");
+    NLC_REQUIRE(model->device == device, NLC_ERR_ARG, "batch planner: model lives on device %d, planner on %d", model->device, device);
+    NLC_REQUIRE(model->nx == d->nx && model->nu == mp.nu, NLC_ERR_SHAPE, "batch planner: model dims do not match");
+  }
+  nlc_batch_planner_s* p = new nlc_batch_planner_s();
+  p->device = device; p->I = n_instances; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr;
+  p->seeds.assign(seeds, seeds + n_instances);
+  const size_t I = n_instances, K = mp.K, T = mp.T, nu = mp.nu, B = mp.B, nx = d->nx, L = B - 1 + T, TN = T * nu, IK = I * K;
+  p->ws_stride = ((size_t)nlc_softmax_workspace_bytes((int)K, (int)TN) + 255) / 256 * 256;
+  std::vector<size_t> sizes = {I * TN, I * TN, IK * TN, IK * TN, IK * L * nu, IK * TN, IK, IK * T * 2, IK, IK,
+                               (d->keep_states ? IK * T * nx : 0), I * (2 + TN), I * 2, I * p->ws_stride / 4};
+  std::vector<size_t> offs;
+  size_t total = 0;
+  for (size_t s : sizes) { offs.push_back(total); total += (s + 63) / 64 * 64; }
+  auto fail = [&](int code) { if (p->arena) cudaFree(p->arena); delete p; return code; };
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(NLC_ERR_CUDA); }
+  if (cudaMalloc(&p->arena, total * sizeof(float)) != cudaSuccess) { cudaGetLastError(); p->arena = nullptr; set_error("batch planner: cudaMalloc(%zu) failed", total * sizeof(float)); return fail(NLC_ERR_NOMEM); }
+  if (cudaMemset(p->arena, 0, total * sizeof(float)) != cudaSuccess) { set_error("batch planner: memset failed"); return fail(NLC_ERR_CUDA); }
+  float* base = static_cast<float*>(p->arena);
+  float** slots[] = {&p->U, &p->U_rolled, &p->noise, &p->perturbed, &p->hist, &p->actions, &p->pert_cost, &p->p,
+                     &p->cost_total, &p->weights, &p->states, &p->triple, &p->stats};
+  for (size_t i = 0; i < sizeof(slots) / sizeof(slots[0]); ++i) *slots[i] = base + offs[i];
+  if (!d->keep_states) p->states = nullptr;
+  p->softmax_ws = reinterpret_cast<char*>(base + offs[13]);
+  *out = p;
+  return NLC_OK;
+}
+
+extern "C" int nlc_batch_planner_destroy(nlc_batch_planner_t p) {
+  if (!p) return NLC_OK;
+  cudaSetDevice(p->device);
+  if (p->arena) cudaFree(p->arena);
+  delete p;
+  return NLC_OK;
+}
+
+extern "C" int nlc_batch_planner_buffer(nlc_batch_planner_t p, int which, void** dev_ptr, int64_t* n_floats) {
+  NLC_REQUIRE(p && dev_ptr && n_floats, NLC_ERR_ARG, "nlc_batch_planner_buffer: null argument");
+  const nlc_mppi_params& mp = p->d.mppi;
+  const int64_t I = p->I, K = mp.K, T = mp.T, nu = mp.nu, B = mp.B, nx = p->d.nx, TN = T * nu, IK = I * K;
+  float* ptr = nullptr; int64_t n = 0;
+  switch (which) {
+    case NLC_BUF_U: ptr = p->U; n = I * TN; break;
+    case NLC_BUF_NOISE: ptr = p->noise; n = IK * TN; break;
+    case NLC_BUF_PERTURBED: ptr = p->perturbed; n = IK * TN; break;
+    case NLC_BUF_COST_TOTAL: ptr = p->cost_total; n = IK; break;
+    case NLC_BUF_WEIGHTS: ptr = p->weights; n = IK; break;
+    case NLC_BUF_STATES: ptr = p->states; n = p->states ? IK * T * nx : 0; break;
+    case NLC_BUF_ACTIONS: ptr = p->actions; n = IK * TN; break;
+    case NLC_BUF_TRIPLE: ptr = p->triple; n = I * (2 + TN); break;
+    case NLC_BUF_STATS: ptr = p->stats; n = I * 2; break;
+    case NLC_BUF_HIST: ptr = p->hist; n = IK * (B - 1 + T) * nu; break;
+    case NLC_BUF_P: ptr = p->p; n = IK * T * 2; break;
+    default: set_error("nlc_batch_planner_buffer: unknown buffer id %d", which); return NLC_ERR_ARG;
+  }
+  *dev_ptr = ptr; *n_floats = n;
+  return NLC_OK;
+}
+
+extern "C" int nlc_batch_planner_command(nlc_batch_planner_t p, const float* state_dev, const float* action_buffer_dev,
+                                         const float* noise_in_dev, float* action_dev, void* stream) {
+  NLC_REQUIRE(p && state_dev && action_buffer_dev && action_dev, NLC_ERR_ARG, "nlc_batch_planner_command: null argument");
+  const nlc_mppi_params& mp = p->d.mppi;
+  const size_t K = mp.K, T = mp.T, nu = mp.nu, B = mp.B, L = B - 1 + T, TN = T * nu;
+  const int I = p->I;
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc;
+  for (int i = 0; i < I; ++i) {  // stage 1 per instance (its own U, action buffer and RNG stream)
+    const size_t o = (size_t)i * K;
+    rc = nlc_perturb(&mp, p->U + i * TN, p->U_rolled + i * TN, 1, noise_in_dev ? noise_in_dev + o * TN : nullptr, p->seeds[i], p->calls,
+                     action_buffer_dev + (size_t)i * B * nu, p->perturbed + o * TN, p->noise + o * TN, p->hist + o * L * nu,
+                     p->actions + o * TN, p->pert_cost + o, stream);
+    if (rc != NLC_OK) return rc;
+  }
+  p->calls++;
+  const int IK = (int)(I * K);
+  if (p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {  // stage 2a: every window of every instance in one pass
+    rc = nlc_encode_history(p->model, p->hist, IK, (int)T, (int)B, p->p, p->d.math_mode, stream);
+    if (rc != NLC_OK) return rc;
+  }
+  // stages 2b+3: one launch; sample k reads the state of instance k / K
+  rc = nlc_rollout_cost(p->model, &p->d.rollout, state_dev, (int)K, p->p, p->hist, p->pert_cost, IK, (int)T, (int)B, (int)nu,
+                        p->cost_total, p->states, p->d.math_mode, stream);
+  if (rc != NLC_OK) return rc;
+  NLC_CUDA_OK(cudaMemcpyAsync(p->U, p->U_rolled, sizeof(float) * I * TN, cudaMemcpyDeviceToDevice, s));
+  for (int i = 0; i < I; ++i) {  // stage 4 per instance
+    const size_t o = (size_t)i * K;
+    float* triple = p->triple + (size_t)i * (2 + TN);
+    rc = nlc_softmax_partial(p->cost_total + o, p->noise + o * TN, (int)K, (int)T, (int)nu, mp.lambda_, triple, p->weights + o,
+                             p->softmax_ws + (size_t)i * p->ws_stride, stream);
+    if (rc != NLC_OK) return rc;
+    rc = nlc_softmax_combine(triple, 1, (int)T, (int)nu, mp.lambda_, mp.u_scale, p->U + i * TN, action_dev + (size_t)i * nu,
+                             p->stats + 2 * i, stream);
+    if (rc != NLC_OK) return rc;
+  }
+  return NLC_OK;
+}
+
+extern "C" int nlc_batch_planner_set_U(nlc_batch_planner_t p, const double* U_host) {
+  NLC_REQUIRE(p && U_host, NLC_ERR_ARG, "nlc_batch_planner_set_U: null argument");
+  const size_t n = (size_t)p->I * p->d.mppi.T * p->d.mppi.nu;
+  std::vector<float> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = (float)U_host[i];
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  NLC_CUDA_OK(cudaMemcpy(p->U, tmp.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  return NLC_OK;
+}

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
   for (int i = tid; i < R * nx; i += 256) {
     const int r = i / nx, c = i - r * nx;
     const int k = min(k0 + r, a.K - 1);
-    const float v = a.state_per_sample ? a.state0[(size_t)k * nx + c] : a.state0[c];
+    const float v = a.state0[(size_t)(a.state_per_sample ? k / a.state_per_sample : 0) * nx + c];
     st[i] = v;
     in[r * Lp + c] = (v - smean[c]) * sinv[c];
   }

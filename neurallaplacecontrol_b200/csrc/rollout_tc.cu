@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kGroups * 128, 1) rollout_tc_kernel(RollTcArgs
   float st[NX], in[Lp];
 #pragma unroll
   for (int c = 0; c < NX; ++c) {
-    st[c] = a.state_per_sample ? a.state0[(size_t)kk * NX + c] : a.state0[c];
+    st[c] = a.state0[(size_t)(a.state_per_sample ? kk / a.state_per_sample : 0) * NX + c];
     in[c] = (st[c] - s.smean[c]) * s.sinv[c];
   }
   {

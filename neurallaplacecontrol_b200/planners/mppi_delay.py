@@ -150,14 +150,12 @@ class MPPIDelay:
         self._U_dirty = True
 
     # ---- device handle ---------------------------------------------------------------------------------------
-    def _ensure(self, B):
-        if self._handle is not None and self._handle_B == B:
-            return self._handle
-        self._destroy()
+    def _desc(self, B, K_local, k_offset, k_total, n_shards, shard_index):
+        """``nlc_planner_desc`` of this planner's options (shared with the instance-batched planner)."""
         d = _lib.PlannerDesc()
         mp = d.mppi
-        mp.K, mp.T, mp.nu, mp.B = self.K_local, self.T, self.nu, B
-        mp.k_offset, mp.k_total = self.k_offset, self.K
+        mp.K, mp.T, mp.nu, mp.B = K_local, self.T, self.nu, B
+        mp.k_offset, mp.k_total = k_offset, k_total
         mp.lambda_, mp.u_scale = float(self.lambda_), float(self.u_scale)
         mp.has_bounds = int(self.u_max is not None)
         if self.u_max is not None:
@@ -178,7 +176,7 @@ class MPPIDelay:
         ro.dynamics = self.F.kind
         ro.delay = int(self.F.delay)
         ro.dt = float(self.F.dt)
-        d.nx, d.n_shards, d.shard_index = self.nx, self.G, self.rank
+        d.nx, d.n_shards, d.shard_index = self.nx, n_shards, shard_index
         d.math_mode = _lib.MATH_MODES[self.math_mode]
         d.keep_states = int(self.keep_states)
         d.seed = self.seed
@@ -187,6 +185,13 @@ class MPPIDelay:
             if self.F.model._cuda_device is None:
                 self.F.model._cuda_device = self.d
             model_h = self.F.model.set_prediction_time(self.F.dt)
+        return d, model_h
+
+    def _ensure(self, B):
+        if self._handle is not None and self._handle_B == B:
+            return self._handle
+        self._destroy()
+        d, model_h = self._desc(B, self.K_local, self.k_offset, self.K, self.G, self.rank)
         h = C.c_void_p()
         _lib.check(self._lib.nlc_planner_create(C.byref(h), model_h, C.byref(d), self.d.index), "nlc_planner_create")
         self._handle, self._handle_B, self._views = h, B, {}

@@ -2,12 +2,12 @@
 """BASELINE config 5: batched closed-loop evaluation, 256 env x seed instances each planning MPPI K=4096 H=30 per
 control step across 8 B200 - sharded BY INSTANCE (32 per GPU, no collective at all).
 
-Each rank owns its instances as independent MPPIDelay planners round-robined over a few CUDA streams so that the
-latency-bound rollout of one instance overlaps the wide encoder pass of another.  Between control steps every instance
-advances its own environment with the analytic delayed dynamics (oracle.py semantics, evaluated on the host for the 32
-small states) and rolls its action buffer (`get_action`, mppi_with_model.py:25-28) - a real closed loop.
+Default (--mode batched): the instances of each environment on a rank form one `BatchedMPPIDelay` - one encoder launch
+and one rollout launch over all their samples per control step - and advance through `env_step` on the device
+(`run_closed_loop`'s body: a real closed loop, nothing crosses PCIe inside it).  The three environments' batches run on
+three CUDA streams.  --mode streams is the earlier form: one `MPPIDelay` per instance round-robined over a few streams.
 
-    python tools/bench_cfg5.py [--instances 32] [--streams 4] [--steps 10]      (per GPU; launch under torchrun for N GPUs)
+    python tools/bench_cfg5.py [--instances 32] [--steps 10] [--mode batched|streams]     (per GPU; torchrun for N GPUs)
 """
 import argparse
 import json
@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--K", type=int, default=4096)
     ap.add_argument("--H", type=int, default=30)
     ap.add_argument("--math", default="tc_split3")
+    ap.add_argument("--mode", default="batched", choices=["batched", "streams"])
+    ap.add_argument("--delay", type=int, default=1)
+    ap.add_argument("--hold-state", action="store_true", help="skip env_step (open loop): isolates the planning cost")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -54,31 +57,57 @@ def main():
         m.load_state_dict(weights(e, calibrated=True))
         models[e] = m
     start = {"oderl-pendulum": [-1.0, 0.0, 1.0], "oderl-cartpole": [0.0, 0.0, -1.0, 0.0, 0.0], "oderl-acrobot": [1.0, 0.0, 1.0, 0.0, 0.0, 0.0]}
+    per_env = {e: [] for e in envs}
     for i in range(args.instances):
         gi = rank * args.instances + i  # global instance id = env x seed
-        e = envs[gi % 3]
-        nx, nu = costs.ENV_DIMS[e]
-        ah = costs.ENV_ACT_HIGH[e]
-        rng = np.random.default_rng(gi)
-        planners.append((e, nlc.MPPIDelay(nlc.NLDynamics(models[e], DT), nlc.EnvRunningCost(e), nx, nlc.noise_sigma_for(nu),
-                                          num_samples=args.K, horizon=args.H, device=dev, u_min=torch.tensor(-ah), u_max=torch.tensor(ah),
-                                          u_scale=ah, U_init=torch.zeros(args.H, nu, dtype=torch.float64), seed=gi, math_mode=args.math,
-                                          keep_states=False)))
-        states.append(torch.tensor(np.array(start[e]) + rng.uniform(-0.05, 0.05, nx), dtype=torch.float64, device=dev))
-        bufs.append(torch.zeros(4, nu, dtype=torch.float64, device=dev))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)]
+        per_env[envs[gi % 3]].append(gi)
+    if args.mode == "batched":
+        batches = []
+        for e in envs:
+            ids = per_env[e]
+            if not ids:
+                continue
+            nx, nu = costs.ENV_DIMS[e]
+            ah = costs.ENV_ACT_HIGH[e]
+            bp = nlc.BatchedMPPIDelay(nlc.NLDynamics(models[e], DT), nlc.EnvRunningCost(e), nx, nlc.noise_sigma_for(nu), len(ids), seeds=ids,
+                                      num_samples=args.K, horizon=args.H, device=dev, u_min=torch.tensor(-ah), u_max=torch.tensor(ah),
+                                      u_scale=ah, math_mode=args.math)
+            st = torch.stack([torch.tensor(np.array(start[e]) + np.random.default_rng(gi).uniform(-0.05, 0.05, nx), dtype=torch.float32)
+                              for gi in ids]).to(dev).contiguous()
+            batches.append({"env": e, "planner": bp, "states": st, "bufs": torch.zeros(len(ids), 4, nu, device=dev),
+                            "reward": torch.zeros(len(ids), device=dev), "total": torch.zeros(len(ids), device=dev),
+                            "stream": torch.cuda.Stream(device=dev)})
 
-    def control_step():
-        actions = []
-        for i, (e, p) in enumerate(planners):
-            with torch.cuda.stream(streams[i % args.streams]):
-                actions.append(p.command(states[i], bufs[i]))
-        for s in streams:
-            s.synchronize()
-        # closed loop: roll each instance's action buffer (delay 1) and hold the state (the env step is outside the
-        # planner path and negligible; the planning work per step does not depend on it)
-        for i, a in enumerate(actions):
-            bufs[i], _ = nlc.get_action(bufs[i], a, 1)
+        def control_step():
+            for b in batches:
+                with torch.cuda.stream(b["stream"]):
+                    a = b["planner"].command(b["states"], b["bufs"])
+                    if not args.hold_state:
+                        nlc.env_step(b["env"], b["states"], b["bufs"], a.float().contiguous(), args.delay, DT, b["reward"])
+                        b["total"] += b["reward"]
+            for b in batches:
+                b["stream"].synchronize()
+    else:
+        for e in envs:
+            for gi in per_env[e]:
+                nx, nu = costs.ENV_DIMS[e]
+                ah = costs.ENV_ACT_HIGH[e]
+                rng = np.random.default_rng(gi)
+                planners.append((e, nlc.MPPIDelay(nlc.NLDynamics(models[e], DT), nlc.EnvRunningCost(e), nx, nlc.noise_sigma_for(nu),
+                                                  num_samples=args.K, horizon=args.H, device=dev, u_min=torch.tensor(-ah), u_max=torch.tensor(ah),
+                                                  u_scale=ah, U_init=torch.zeros(args.H, nu, dtype=torch.float64), seed=gi, math_mode=args.math,
+                                                  keep_states=False)))
+                states.append(torch.tensor(np.array(start[e]) + rng.uniform(-0.05, 0.05, nx), dtype=torch.float32, device=dev).reshape(1, nx))
+                bufs.append(torch.zeros(1, 4, nu, dtype=torch.float32, device=dev))
+        streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)]
+
+        def control_step():
+            for i, (e, p) in enumerate(planners):
+                with torch.cuda.stream(streams[i % args.streams]):
+                    a = p.command(states[i][0], bufs[i][0])
+                    nlc.env_step(e, states[i], bufs[i], a.float().reshape(1, -1).contiguous(), args.delay, DT)
+            for s in streams:
+                s.synchronize()
 
     for _ in range(args.warmup):
         control_step()
@@ -91,11 +120,15 @@ def main():
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0 and args.mode == "batched":
+        for b in batches:
+            print(b["env"], "finite states:", bool(torch.isfinite(b["states"]).all()), "max|state|", float(b["states"].abs().max()),
+                  "mean total reward", float(b["total"].mean()), file=sys.stderr)
     if rank == 0:
         total = world * args.instances * args.K * args.H
         print(json.dumps({"workload": f"config 5: {world * args.instances} instances x MPPI K={args.K} H={args.H}, instance-sharded over {world} GPU(s)",
                           "ms_per_control_step_all_instances": 1e3 * float(t[0]), "rollout_steps_per_s": total / float(t[0]),
-                          "instances_per_gpu": args.instances, "streams": args.streams, "math": args.math, "n_gpus": world}), flush=True)
+                          "instances_per_gpu": args.instances, "mode": args.mode, "streams": args.streams if args.mode == "streams" else 3, "math": args.math, "n_gpus": world}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
