@@ -131,3 +131,35 @@ def test_encode_obs_time_model_matches_reference(env):
                         costs.running_cost(env), noise_sigma=mppi.noise_sigma_for(nu), u_scale=ah, u_min=-ah, u_max=ah)
     for k in ("cost_total", "states", "U", "action"):
         assert relerr(g["plan_" + k], plan[k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("env", ["oderl-pendulum", "oderl-cartpole", "oderl-acrobot"])
+@pytest.mark.parametrize("delay", [0, 1, 3])
+def test_oracle_env_step_matches_reference_golden(env, delay):
+    """oracle/dynamics.py (restatement of the reference's oracle.py one-step dynamics + step_env) against the vectors
+    generated with the reference's own functions (oracle/gen_golden_envstep.py)."""
+    from oracle import dynamics
+
+    g = load("env_step_" + short(env))
+    s, b = torch.from_numpy(g[f"d{delay}_state0"]), torch.from_numpy(g[f"d{delay}_buf0"])
+    for it in range(g[f"d{delay}_actions"].shape[0]):
+        s, b, r = dynamics.env_step(env, s, b, torch.from_numpy(g[f"d{delay}_actions"][it]), delay, DT)
+        assert torch.equal(b, torch.from_numpy(g[f"d{delay}_bufs"][it]))
+        assert (s - torch.from_numpy(g[f"d{delay}_states"][it])).abs().max() < 1e-12
+        assert (r - torch.from_numpy(g[f"d{delay}_rewards"][it])).abs().max() < 1e-10
+
+
+@pytest.mark.parametrize("env", ["oderl-pendulum", "oderl-cartpole", "oderl-acrobot"])
+def test_oracle_analytic_dynamics_plan_matches_reference_golden(env):
+    """The oracle MPPI with the restated analytic dynamics reproduces the reference planner run with oracle.py (f1)."""
+    from oracle import costs, dynamics, mppi
+
+    g = load(f"plan_oracledyn_{short(env)}_d1")
+    nu = costs.ENV_DIMS[env][1]
+    ah = costs.ENV_ACT_HIGH[env]
+    out = mppi.command(torch.from_numpy(g["in_U"]), torch.from_numpy(np.asarray(g["in_state"])), torch.from_numpy(g["in_buffer"]),
+                       torch.from_numpy(g["in_noise"]), dynamics.make_analytic_dynamics(env, DT, 1), costs.running_cost(env),
+                       noise_sigma=mppi.noise_sigma_for(nu), u_scale=ah, u_min=-ah, u_max=ah)
+    for k in ("cost_total", "states", "U", "action"):
+        ref = torch.from_numpy(np.asarray(g[k]))
+        assert (out[k].reshape(ref.shape) - ref).abs().max() <= 1e-9 * max(1.0, float(ref.abs().max())), k
