@@ -67,6 +67,10 @@ struct ModelDev {
   // columns); and the matching fp32 constants (biases, layer-0 input weights, output layer), layout kE2* below
   void* enc2_w;
   float* enc2_c;
+  // input/bias blocks of the two GRU layers, [2 layers][256 accumulator columns][8 halves] =
+  // [W0_hi W0_hi W0_lo | W1_hi W1_hi W1_lo | b_hi b_lo]: all three split-3 terms of W_ih0 x + b in ONE K = 16 MMA against
+  // the operand block [x0_hi x0_lo x0_hi | x1_hi x1_lo x1_hi | 1 1 | 0 x 8]   (layer 1: biases only)
+  void* enc2_x;
   // rollout_tc2.cu: representation MLP with -2 log2(e) folded into every layer (all three feed tanh-like maps):
   // mlp2_w1 [2 (hi,lo)][128 x 16]  first layer on the tensor cores, K = [obs_n | p_action | 1 (folded bias) | 0..]
   //                                 (re-packed by nlc_model_set_prediction_time: the bias depends on the s-points);

@@ -46,13 +46,13 @@ constexpr int kRows = 128, kHg = 64, kG3 = 192, kThreads = 512;
 constexpr uint32_t kOpBytes = kRows * kHg * 2;  // one fp16 A-operand image (16 KB)
 constexpr uint32_t kWBytes = kG3 * kHg * 2;     // one fp16 weight image (24 KB)
 constexpr uint32_t kLbo = 128, kSbo = (kHg / 8) * 128;
-constexpr uint32_t kColD0 = 0, kColD1 = 192, kTmemCols = 512;
+constexpr uint32_t kColD0 = 0, kColD1 = 256, kTmemCols = 512;  // D0 = [r | z | hn | in], D1 = [in | r | z | hn]
 
 struct Args {
   const float* hist;
   float* p_out;
   int K, T, B, L, hist_ch;
-  int ablate;  // measurement only (NLC_ENC_ABLATE): 1 no MMA/waits, 2 no operand store, 4 no bias re-arm, 8 no gate math, 16 no TMEM loads
+  int ablate;  // measurement only (NLC_ENC_ABLATE): 1 no MMA issue, 8 no gate math
   long long rows;
   long long* trace;  // measurement only: clock64 timeline of CTA 0, [step][warp][8 events]
   ModelDev m;
@@ -133,7 +133,8 @@ __device__ __forceinline__ f2_t gru_pair(f2_t pr, f2_t pz, f2_t gi, f2_t gh, f2_
 
 // 8 hidden values of this thread's row -> one 16-byte slice of the fp16 hi (+ lo) A-operand image
 template <bool kSplit3>
-__device__ __forceinline__ void store_operand8(unsigned char* img_hi, unsigned char* img_lo, int row, int u0, const f2_t (&h)[4]) {
+__device__ __forceinline__ void store_operand8(unsigned char* img_hi, uint32_t sbo_hi, unsigned char* img_lo, uint32_t sbo_lo, int row, int u0,
+                                               const f2_t (&h)[4]) {
   uint32_t ph[4], pl[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -147,33 +148,49 @@ __device__ __forceinline__ void store_operand8(unsigned char* img_hi, unsigned c
       pl[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
   }
-  const uint32_t off = (uint32_t)(row >> 3) * kSbo + (uint32_t)(u0 >> 3) * kLbo + (uint32_t)(row & 7) * 16;
-  *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-  if (kSplit3) *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  const uint32_t in_group = (uint32_t)(u0 >> 3) * kLbo + (uint32_t)(row & 7) * 16;
+  *reinterpret_cast<uint4*>(img_hi + (uint32_t)(row >> 3) * sbo_hi + in_group) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  if (kSplit3) *reinterpret_cast<uint4*>(img_lo + (uint32_t)(row >> 3) * sbo_lo + in_group) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
-// D[128 x 192] += A[128 x 64] * B[192 x 64]^T : 4 (x3) MMA instructions
+// D[128 x 192] += A[128 x 64] * B[192 x 64]^T : 4 (x3) MMA instructions.  The hi and lo images of A may have different
+// 8-row-group strides (the layer-0 state image carries an extra K block, see Smem)
 template <bool kSplit3>
-__device__ __forceinline__ void issue_gemm192(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+__device__ __forceinline__ void issue_gemm192(uint32_t d_tmem, uint32_t a_hi, uint32_t a_hi_sbo, uint32_t a_lo, uint32_t a_lo_sbo,
+                                              uint32_t b_hi, uint32_t b_lo) {
   const uint32_t idesc = idesc_f16_f32(kRows, kG3);
 #pragma unroll
   for (int ks = 0; ks < kHg / 16; ++ks) {
     const uint32_t off = ks * 2 * kLbo;  // 16 K-elements = two core matrices
-    mma_f16_ss(d_tmem, smem_desc(a_hi + off, kLbo, kSbo), smem_desc(b_hi + off, kLbo, kSbo), idesc, 1u);
+    mma_f16_ss(d_tmem, smem_desc(a_hi + off, kLbo, a_hi_sbo), smem_desc(b_hi + off, kLbo, kSbo), idesc, 1u);
     if (kSplit3) {
-      mma_f16_ss(d_tmem, smem_desc(a_lo + off, kLbo, kSbo), smem_desc(b_hi + off, kLbo, kSbo), idesc, 1u);
-      mma_f16_ss(d_tmem, smem_desc(a_hi + off, kLbo, kSbo), smem_desc(b_lo + off, kLbo, kSbo), idesc, 1u);
+      mma_f16_ss(d_tmem, smem_desc(a_lo + off, kLbo, a_lo_sbo), smem_desc(b_hi + off, kLbo, kSbo), idesc, 1u);
+      mma_f16_ss(d_tmem, smem_desc(a_hi + off, kLbo, a_hi_sbo), smem_desc(b_lo + off, kLbo, kSbo), idesc, 1u);
     }
   }
 }
 
-constexpr int kThreadsAll = kThreads + 32;  // 16 epilogue warps + the MMA warp
+constexpr int kThreadsAll = kThreads + 32;        // 16 epilogue warps + the MMA warp
+// Layer 0's input projection and biases ride on the tensor cores as one extra K block of the layer-0 state operand:
+//   A block (per window)  [x0_hi x0_lo x0_hi | x1_hi x1_lo x1_hi | 1 1 | 0 ...]      (16 halves)
+//   B block (per column)  [W0_hi W0_hi W0_lo | W1_hi W1_hi W1_lo | b_hi b_lo | 0 ...]
+// so one K = 16 MMA with accumulate = 0 writes  W_ih0 x + b  (all three split terms at once) into D0 = [r | z | hn | in]
+// and the hidden products accumulate on top: no input FMAs, no bias loads, no accumulator re-arm in the layer-0 epilogue.
+constexpr int kKx = kHg + 16;
+constexpr uint32_t kSboX = (kKx / 8) * 128;       // 8-row-group stride of the K = 80 image
+constexpr uint32_t kH0HiBytes = kRows * kKx * 2;  // 20 KB
+// The B side of that block stores only its first 8 K-elements ([256][8] halves, 4 KB): the A side's second 8 are zeros
+// for ever, so the descriptor lets the second core matrix alias the next row group's (finite) data - 0 x finite = 0.
+constexpr uint32_t kWxBytes = 256 * 8 * 2;
+constexpr int kC2Wout = 0, kC2Bout = 128, kC2Count = 136;  // shared-memory constants: the output layer
 
 struct Smem {
-  alignas(128) unsigned char w[3][2][kWBytes];
-  alignas(128) unsigned char h0[2][kOpBytes];
+  alignas(128) unsigned char w[3][2][kWBytes];   // [W_hh0, W_ih1 (n|r|z), W_hh1][hi, lo]
+  alignas(128) unsigned char wx[2][kWxBytes + 128];  // input/bias blocks: layer 0 rows in D0 order, layer 1 in D1 order; + zero pad
+  alignas(128) unsigned char h0_hi[kH0HiBytes];  // layer-0 state, K = 64 + the [x | 1] block
+  alignas(128) unsigned char h0_lo[kOpBytes];
   alignas(128) unsigned char h1[2][kOpBytes];
-  alignas(16) float c[kE2Count];
+  alignas(16) float c[kC2Count];
   alignas(16) float pout[3][kRows * 2];
   alignas(8) uint64_t bar_a, bar_b, h0_ready, h1_ready;
   uint32_t tmem_base;
@@ -198,7 +215,15 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     const uint4* src = reinterpret_cast<const uint4*>(a.m.enc2_w);
     uint4* dst = reinterpret_cast<uint4*>(&s.w[0][0][0]);
     for (int i = tid; i < (int)(3 * 2 * kWBytes / 16); i += kThreadsAll) dst[i] = __ldg(src + i);
-    for (int i = tid; i < kE2Count; i += kThreadsAll) s.c[i] = a.m.enc2_c[i];
+    const uint4* sx = reinterpret_cast<const uint4*>(a.m.enc2_x);
+    for (int i = tid; i < (int)(2 * (kWxBytes + 128) / 16); i += kThreadsAll) {
+      const int l = i / (int)((kWxBytes + 128) / 16), j = i - l * (int)((kWxBytes + 128) / 16);
+      reinterpret_cast<uint4*>(s.wx[l])[j] = j < (int)(kWxBytes / 16) ? __ldg(sx + l * (int)(kWxBytes / 16) + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint4* dz = reinterpret_cast<uint4*>(s.h0_hi);  // the second half of the [x | 1] block stays zero for ever
+    for (int i = tid; i < (int)(kH0HiBytes / 16); i += kThreadsAll) dz[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 128; i += kThreadsAll) s.c[kC2Wout + i] = a.m.enc2_c[kE2Wout + i];
+    if (tid < 2) s.c[kC2Bout + tid] = a.m.enc2_c[kE2Bout + tid];
     if (tid == 0) {
       mbar_init(&s.bar_a, 1); mbar_init(&s.bar_b, 1);
       mbar_init(&s.h0_ready, kThreads / 32); mbar_init(&s.h1_ready, kThreads / 32);  // one arrival per epilogue warp
@@ -214,38 +239,26 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
   const float* cst = s.c;
 
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {  // accumulator columns start out holding the biases
-    if (warp >= 16) break;
-    const int u0 = ubase + 8 * c;
-    bias_to_tmem8(tlane + kColD0 + u0, cst + kE2Brz0 + u0);
-    bias_to_tmem8(tlane + kColD0 + 64 + u0, cst + kE2Brz0 + 64 + u0);
-    bias_to_tmem8(tlane + kColD0 + 128 + u0, cst + kE2Bhn0 + u0);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) bias_to_tmem8(tlane + kColD1 + 64 * g + u0, cst + kE2B1 + 64 * g + u0);
-  }
-  tmem_st_wait();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-
-  const uint32_t a_h0_hi = smem_u32(s.h0[0]), a_h0_lo = smem_u32(s.h0[1]);
+  const uint32_t a_h0_hi = smem_u32(s.h0_hi), a_h0_lo = smem_u32(s.h0_lo);
   const uint32_t a_h1_hi = smem_u32(s.h1[0]), a_h1_lo = smem_u32(s.h1[1]);
   const uint32_t w_hh0_hi = smem_u32(s.w[0][0]), w_hh0_lo = smem_u32(s.w[0][1]);
   const uint32_t w_ih1_hi = smem_u32(s.w[1][0]), w_ih1_lo = smem_u32(s.w[1][1]);
   const uint32_t w_hh1_hi = smem_u32(s.w[2][0]), w_hh1_lo = smem_u32(s.w[2][1]);
+  const uint32_t w_x0 = smem_u32(s.wx[0]), w_x1 = smem_u32(s.wx[1]);
   const long long n_tiles = (a.rows + kRows - 1) / kRows;
-
 
   if (warp == 16) {
     // =====================================  MMA warp  =====================================
-    // mirrors the epilogue warps' publication order: h0 (-> layer-0 product of the next cell), then h1 / D1 re-armed
-    // (-> layer-1 product of the next cell: input part from h0, hidden part from h1)
+    // mirrors the epilogue warps' publication order: h0 + the next cell's [x | 1] block (-> layer-0 product of the next
+    // cell), then h1 / D1 re-armed (-> layer-1 product of the next cell: input part from h0, hidden part from h1)
     uint32_t n_h0 = 0, n_h1 = 0;
-    auto issue_a = [&]() {
+    auto issue_a = [&](bool with_hidden) {
       if (lane == 0) {
         fence_after_sync();
-        if (!(abl & 1)) issue_gemm192<kSplit3>(tmem + kColD0, a_h0_hi, a_h0_lo, w_hh0_hi, w_hh0_lo);
+        if (!(abl & 1)) {
+          mma_f16_ss(tmem + kColD0, smem_desc(a_h0_hi + 8 * kLbo, kLbo, kSboX), smem_desc(w_x0, kLbo, 128), idesc_f16_f32(kRows, 256), 0u);
+          if (with_hidden) issue_gemm192<kSplit3>(tmem + kColD0, a_h0_hi, kSboX, a_h0_lo, kSbo, w_hh0_hi, w_hh0_lo);
+        }
         mma_commit(&s.bar_a);
       }
       __syncwarp();
@@ -254,16 +267,20 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       if (lane == 0) {
         fence_after_sync();
         if (!(abl & 1)) {
-          issue_gemm192<kSplit3>(tmem + kColD1, a_h0_hi, a_h0_lo, w_ih1_hi, w_ih1_lo);
-          if (with_h1) issue_gemm192<kSplit3>(tmem + kColD1 + 64, a_h1_hi, a_h1_lo, w_hh1_hi, w_hh1_lo);
+          // biases first (accumulate = 0 over all of D1 = [in | r | z | hn]): the 1-columns of the [x | 1] block
+          mma_f16_ss(tmem + kColD1, smem_desc(a_h0_hi + 8 * kLbo, kLbo, kSboX), smem_desc(w_x1, kLbo, 128), idesc_f16_f32(kRows, 256), 0u);
+          issue_gemm192<kSplit3>(tmem + kColD1, a_h0_hi, kSboX, a_h0_lo, kSbo, w_ih1_hi, w_ih1_lo);
+          if (with_h1) issue_gemm192<kSplit3>(tmem + kColD1 + 64, a_h1_hi, kSbo, a_h1_lo, kSbo, w_hh1_hi, w_hh1_lo);
         }
         mma_commit(&s.bar_b);
       }
       __syncwarp();
     };
     if ((long long)blockIdx.x < n_tiles) {
-      mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;
-      issue_a();
+      mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;  // [x(0) | 1]
+      issue_a(false);
+      mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;  // h0(0), [x(1) | 1]
+      issue_a(true);
       mbar_wait_sleep(&s.h1_ready, n_h1 & 1); ++n_h1;
       issue_b(false);
     }
@@ -272,7 +289,8 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       for (int st = 0; st < B; ++st) {
         if (st + 1 < B || has_next) {
           mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;
-          if (st + 2 < B || (st + 1 == B && has_next)) issue_a();
+          if (st + 2 < B || st + 1 == B) issue_a(true);   // next cell of this tile, or cell 1 of the next tile
+          else if (has_next) issue_a(false);              // st + 2 == B: cell 0 of the next tile (zero state)
         }
         mbar_wait_sleep(&s.h1_ready, n_h1 & 1); ++n_h1;
         if (st + 1 < B) issue_b(true);
@@ -280,15 +298,15 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       }
     }
   } else {
+  // =====================================  epilogue warps  =====================================
   float amean[GIN], ainv[GIN];
 #pragma unroll
   for (int v = 0; v < GIN; ++v) { amean[v] = a.m.act_mean[v]; ainv[v] = a.m.act_inv_std[v]; }
 
   uint32_t n_a = 0, n_b = 0;    // waits completed on bar_a / bar_b
   f2_t h0r[8], h1r[8];
-  f2_t xx[GIN] = {};            // the window entry of the NEXT layer-0 cell (normalised, both halves equal), prefetched
+  float xn[GIN] = {};           // normalised window entry of the FOLLOWING layer-0 cell (threads with grp == 0 feed the operand)
 
-  // window entry j of this thread's row in tile `tile_`: reversed order, cell st consumes entry B-1-st (w_nl.py:27)
   // hist offset of this thread's window in a tile (one integer division per tile, not per cell)
   auto window_base = [&](long long tile_) -> size_t {
     long long grow = tile_ * kRows + row;
@@ -299,106 +317,95 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     return ((size_t)k * a.L + t) * a.hist_ch;
   };
   size_t base_cur = 0, base_next = 0;
-  auto fetch_x = [&](bool next_tile_, int st_) {
-    if (abl & 64) return;
-    const int j = B - 1 - st_;
+  // window entry of layer-0 cell `cell_`: reversed order, cell c consumes entry B-1-c (w_nl.py:27)
+  auto fetch_x = [&](bool next_tile_, int cell_) {
+    if (grp != 0) return;
+    const int j = B - 1 - cell_;
     const float* src = a.hist + (next_tile_ ? base_next : base_cur) + (size_t)j * a.hist_ch;
 #pragma unroll
     for (int v = 0; v < GIN; ++v) {
       // channels beyond hist_ch: the time channel of encode_obs_time (mppi_with_model.py:110-119)
       const float x = v < a.hist_ch ? __ldg(src + v) : (float)(B - 1 - j);
-      const float xn_ = (x - amean[v]) * ainv[v];  // w_nl.py:121
-      xx[v] = pk2(xn_, xn_);
+      xn[v] = (x - amean[v]) * ainv[v];  // w_nl.py:121
     }
   };
-  // layer-0 cell: gates from D0 (or from the biases alone when the state is zero) + the input products
-  auto cell_a = [&](bool from_zero) {
-    f2_t xc[GIN];
+  // [x_hi x_lo x_hi | ... | 1 1] -> the extra K block of this window's row in the layer-0 state image
+  auto write_x = [&]() {
+    if (grp != 0) return;
+    __half hv[8];
 #pragma unroll
-    for (int v = 0; v < GIN; ++v) xc[v] = xx[v];
+    for (int i = 0; i < 8; ++i) hv[i] = __float2half_rn(0.0f);
+#pragma unroll
+    for (int v = 0; v < GIN; ++v) {
+      const __half hi = __float2half_rn(xn[v]);
+      const __half lo = __float2half_rn(xn[v] - __half2float(hi));
+      hv[3 * v] = hi; hv[3 * v + 1] = lo; hv[3 * v + 2] = hi;
+    }
+    hv[6] = __float2half_rn(1.0f); hv[7] = __float2half_rn(1.0f);
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const __half2 p2 = __halves2half2(hv[2 * i], hv[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&p2); }
+    *reinterpret_cast<uint4*>(s.h0_hi + (uint32_t)(row >> 3) * kSboX + 8 * kLbo + (uint32_t)(row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  // layer-0 cell: complete pre-activations come out of D0 = [r | z | hn | in]
+  auto cell_a = [&](bool from_zero) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int u0 = ubase + 8 * c;
       f2_t gr[4], gz[4], gh[4], gn[4];
-      if (!from_zero && !(abl & 16)) {
-        ldtm8p(tlane + kColD0 + u0, gr);
-        ldtm8p(tlane + kColD0 + 64 + u0, gz);
-        ldtm8p(tlane + kColD0 + 128 + u0, gh);
-      } else {
-        lds8p(cst + kE2Brz0 + u0, gr);
-        lds8p(cst + kE2Brz0 + 64 + u0, gz);
-        lds8p(cst + kE2Bhn0 + u0, gh);
-      }
-      lds8p(cst + kE2Bin0 + u0, gn);
-      if (!from_zero) tmem_ld_wait();
-#pragma unroll
-      for (int v = 0; v < GIN; ++v) {
-        if (abl & 32) break;
-        f2_t w[4];
-        lds8p(cst + kE2Wih0 + (0 * kMaxNu + v) * kHg + u0, w);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gr[i] = fma2(w[i], xc[v], gr[i]);
-        lds8p(cst + kE2Wih0 + (1 * kMaxNu + v) * kHg + u0, w);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gz[i] = fma2(w[i], xc[v], gz[i]);
-        lds8p(cst + kE2Wih0 + (2 * kMaxNu + v) * kHg + u0, w);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gn[i] = fma2(w[i], xc[v], gn[i]);
-      }
+      ldtm8p(tlane + kColD0 + u0, gr);
+      ldtm8p(tlane + kColD0 + 64 + u0, gz);
+      ldtm8p(tlane + kColD0 + 128 + u0, gh);
+      ldtm8p(tlane + kColD0 + 192 + u0, gn);
+      tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (abl & 8) h0r[4 * c + i] = add2(add2(gr[i], gz[i]), add2(gn[i], gh[i]));
         else h0r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], from_zero ? 0ull : h0r[4 * c + i]);
       }
-      if (!from_zero && !(abl & 4)) {
-        bias_to_tmem8(tlane + kColD0 + u0, cst + kE2Brz0 + u0);
-        bias_to_tmem8(tlane + kColD0 + 64 + u0, cst + kE2Brz0 + 64 + u0);
-        bias_to_tmem8(tlane + kColD0 + 128 + u0, cst + kE2Bhn0 + u0);
-      }
     }
   };
-  // publish h0r as the A operand; the elected thread then issues `issue_a` (layer-0 product of the next cell)
-  auto publish_h0 = [&](bool issue_a) {
+  // publish h0r as the A operand (and, for grp 0, the following cell's [x | 1] block); the MMA warp takes it from there
+  auto publish_h0 = [&](bool with_h0, bool with_x) {
+    if (with_h0) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      if (abl & 2) break;
-      const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h0r[4 * c]);
-      store_operand8<kSplit3>(s.h0[0], s.h0[1], row, ubase + 8 * c, hc);
+      for (int c = 0; c < 2; ++c) {
+        const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h0r[4 * c]);
+        store_operand8<kSplit3>(s.h0_hi, kSboX, s.h0_lo, kSbo, row, ubase + 8 * c, hc);
+      }
     }
+    if (with_x) write_x();
     fence_proxy_async_smem();
-    tmem_st_wait();
     fence_before_sync();
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.h0_ready);
-    (void)issue_a;
   };
-  // after the layer-1 epilogue: everyone re-armed D1 (and stored h1 when `with_h1`); the elected thread issues the
-  // next layer-1 product: input part from the h0 image (published earlier in program order), hidden part from h1
-  auto publish_h1_and_issue_b = [&](bool with_h1, bool issue) {
-    if (with_h1 && !(abl & 2)) {
+  // after the layer-1 epilogue: D1 read (and h1 stored when `with_h1`)
+  auto publish_h1 = [&](bool with_h1) {
+    if (with_h1) {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h1r[4 * c]);
-        store_operand8<kSplit3>(s.h1[0], s.h1[1], row, ubase + 8 * c, hc);
+        store_operand8<kSplit3>(s.h1[0], kSbo, s.h1[1], kSbo, row, ubase + 8 * c, hc);
       }
       fence_proxy_async_smem();
     }
-    tmem_st_wait();
     fence_before_sync();
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.h1_ready);
-    (void)issue;
   };
 
-  // ---- head of the first tile: layer-0 cell 0 from the zero state, then A(1) and the input part of B(0) ----
+  // ---- head of the first tile: layer-0 cell 0 (zero state: the [x | 1] product alone), then A(1) and the input part of B(0) ----
   if ((long long)blockIdx.x < n_tiles) {
     base_cur = window_base(blockIdx.x);
     fetch_x(false, 0);
-    cell_a(true);
+    publish_h0(false, true);
     fetch_x(false, 1);
-    publish_h0(true);
-    // nothing of layer 1 exists yet: arm the "D1 free / h1 published" phase so that B(0) can be issued uniformly
-    publish_h1_and_issue_b(false, true);
+    mbar_wait_sleep(&s.bar_a, n_a & 1); ++n_a;
+    fence_after_sync();
+    cell_a(true);
+    publish_h0(true, true);
+    publish_h1(false);  // nothing of layer 1 exists yet: the input part of B(0) can go
   }
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * kRows;
@@ -406,53 +413,46 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     const bool has_next = next_tile < n_tiles;
     if (has_next) base_next = window_base(next_tile);
     for (int st = 0; st < B; ++st) {
-      // ================= layer-0 epilogue A(st+1) (or the next tile's cell 0)  ||  MMA B(st) =================
-      if (st + 1 < B) {
+      // ======== layer-0 epilogue: cell st+1 of this tile, or cell 0 of the next one  ||  MMA B(st) ========
+      const bool a_slot = st + 1 < B || has_next;
+      // the cell after that one: its window entry is fetched now and joins the operand at the publication below
+      const bool following = st + 2 < B || st + 1 == B || (st + 2 == B && has_next);
+      if (a_slot) {
+        if (st + 2 < B) fetch_x(false, st + 2);
+        else if (st + 1 == B) fetch_x(true, 1);
+        else if (has_next) fetch_x(true, 0);
         mark(0);
         mbar_wait_sleep(&s.bar_a, n_a & 1); ++n_a;
         fence_after_sync();
         mark(1);
-        cell_a(false);
-        if (st + 2 < B) fetch_x(false, st + 2); else if (has_next) fetch_x(true, 0);
-      } else if (has_next) {
-        cell_a(true);
-        fetch_x(true, 1);
+        cell_a(st + 1 == B);
       }
       // MMA B(st) reads the h0 image: wait for its commit before overwriting (it also gates the epilogue below)
       mark(2);
       mbar_wait_sleep(&s.bar_b, n_b & 1); ++n_b;
       fence_after_sync();
       mark(3);
-      if (st + 1 < B) publish_h0(st + 2 < B);
-      else if (has_next) publish_h0(true);
+      if (a_slot) publish_h0(true, following);
       mark(4);
-      // ================= layer-1 epilogue B(st)  ||  MMA A(st+2) =================
+      // ======== layer-1 epilogue B(st)  ||  MMA A ========
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int u0 = ubase + 8 * c;
         f2_t gn[4], gr[4], gz[4], gh[4];
-        if (!(abl & 16)) {
-          ldtm8p(tlane + kColD1 + u0, gn);
-          ldtm8p(tlane + kColD1 + 64 + u0, gr);
-          ldtm8p(tlane + kColD1 + 128 + u0, gz);
-          ldtm8p(tlane + kColD1 + 192 + u0, gh);
-          tmem_ld_wait();
-        } else {
-          lds8p(cst + kE2B1 + u0, gn); lds8p(cst + kE2B1 + 64 + u0, gr); lds8p(cst + kE2B1 + 128 + u0, gz); lds8p(cst + kE2B1 + 192 + u0, gh);
-        }
+        ldtm8p(tlane + kColD1 + u0, gn);
+        ldtm8p(tlane + kColD1 + 64 + u0, gr);
+        ldtm8p(tlane + kColD1 + 128 + u0, gz);
+        ldtm8p(tlane + kColD1 + 192 + u0, gh);
+        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (abl & 8) h1r[4 * c + i] = add2(add2(gr[i], gz[i]), add2(gn[i], gh[i]));
           else h1r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], st > 0 ? h1r[4 * c + i] : 0ull);
         }
-        if (!(abl & 4)) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) bias_to_tmem8(tlane + kColD1 + 64 * g + u0, cst + kE2B1 + 64 * g + u0);
-        }
       }
       mark(5);
       if (st + 1 < B) {
-        publish_h1_and_issue_b(true, true);
+        publish_h1(true);
         mark(6);
         ++tstep;
       } else {
@@ -462,8 +462,8 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
         for (int i = 0; i < 8; ++i) {
           float x0, x1;
           upk2(h1r[i], x0, x1);
-          const float2 wa = *reinterpret_cast<const float2*>(cst + kE2Wout + ubase + 2 * i);
-          const float2 wb = *reinterpret_cast<const float2*>(cst + kE2Wout + kHg + ubase + 2 * i);
+          const float2 wa = *reinterpret_cast<const float2*>(cst + kC2Wout + ubase + 2 * i);
+          const float2 wb = *reinterpret_cast<const float2*>(cst + kC2Wout + kHg + ubase + 2 * i);
           o0 = fmaf(wa.y, x1, fmaf(wa.x, x0, o0));
           o1 = fmaf(wb.y, x1, fmaf(wb.x, x0, o1));
         }
@@ -477,10 +477,10 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
           const float2 p2 = *reinterpret_cast<const float2*>(&s.pout[2][row * 2]);
           if (row0 + row < a.rows)
             *reinterpret_cast<float2*>(a.p_out + (row0 + row) * 2) =
-                make_float2(((o0 + p0.x) + p1.x) + p2.x + cst[kE2Bout], ((o1 + p0.y) + p1.y) + p2.y + cst[kE2Bout + 1]);
+                make_float2(((o0 + p0.x) + p1.x) + p2.x + cst[kC2Bout], ((o1 + p0.y) + p1.y) + p2.y + cst[kC2Bout + 1]);
         }
-        // D1 is re-armed: the input part of the next tile's B(0) can go (its h0 image was published above)
-        publish_h1_and_issue_b(false, has_next);
+        // D1 is read: the input part of the next tile's B(0) can go (its h0 image was published above)
+        publish_h1(false);
         mark(6);
         ++tstep;
       }

@@ -171,7 +171,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   // tensor-core operand image of the three recurrent GRU matrices: fp16 hi/lo, UMMA canonical layout
   const size_t tc_halves = (size_t)3 * 2 * G3 * Hg;
   size_t o_tc = A.add(tc_halves / 2);
-  size_t o_enc2w = A.add(tc_halves / 2), o_enc2c = A.add(nlc::kE2Count);
+  size_t o_enc2w = A.add(tc_halves / 2), o_enc2c = A.add(nlc::kE2Count), o_enc2x = A.add(2 * 256 * 8 / 2);
   size_t o_m2w1 = A.add((size_t)2 * Hm * 16 / 2), o_m2w2 = A.add((size_t)2 * Hm * Hm / 2), o_m2w3 = A.add((size_t)2 * N3t * Hm / 2);
   size_t o_m2c = A.add(128 + 256);
   size_t o_tc_w2 = A.add((size_t)2 * Hm * Hm / 2), o_tc_w3 = A.add((size_t)2 * N3t * Hm / 2), o_b3tc = A.add(N3t);
@@ -254,6 +254,41 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
       for (int v = 0; v < gin; ++v)
         for (int u = 0; u < Hg; ++u)
           put(o_enc2c, nlc::kE2Wih0 + (size_t)(g * nlc::kMaxNu + v) * Hg + u, (g < 2 ? cR : cN) * d->gru_w_ih_l0[(size_t)(g * Hg + u) * gin + v]);
+    if (gin <= 2) {  // the [x | 1] blocks of the tensor-core encoder (encode_tc2.cu): [layer][256 rows][8 halves]
+      uint16_t* wx = reinterpret_cast<uint16_t*>(A.data.data() + o_enc2x);
+      auto split = [](double v, uint16_t& hi, uint16_t& lo) {
+        __half h = __float2half_rn((float)v);
+        __half l = __float2half_rn((float)(v - (double)__half2float(h)));
+        hi = *reinterpret_cast<uint16_t*>(&h); lo = *reinterpret_cast<uint16_t*>(&l);
+      };
+      for (int row = 0; row < 256; ++row) {
+        const int blk = row / Hg, u = row % Hg;
+        uint16_t* r0 = wx + (size_t)row * 8;          // layer 0, accumulator order [r | z | hn | in]
+        uint16_t* r1 = wx + (size_t)(256 + row) * 8;  // layer 1, accumulator order [in | r | z | hn]: biases only
+        for (int k = 0; k < 8; ++k) r0[k] = r1[k] = 0;
+        {
+          // r, z: W_ih0 x + b_ih + b_hh;  hn: b_hh[n] only;  in: W_ih0[n] x + b_ih[n]
+          const int src_row = blk == 0 ? u : blk == 1 ? Hg + u : 2 * Hg + u;
+          const double sc = blk < 2 ? cR : cN;
+          const double bias = blk < 2 ? d->gru_b_ih_l0[src_row] + d->gru_b_hh_l0[src_row]
+                                      : (blk == 2 ? d->gru_b_hh_l0[src_row] : d->gru_b_ih_l0[src_row]);
+          if (blk != 2)
+            for (int v = 0; v < gin; ++v) {
+              uint16_t hi, lo;
+              split(sc * d->gru_w_ih_l0[(size_t)src_row * gin + v], hi, lo);
+              r0[3 * v] = hi; r0[3 * v + 1] = hi; r0[3 * v + 2] = lo;
+            }
+          split(sc * bias, r0[6], r0[7]);
+        }
+        {
+          const double bias = blk == 0 ? cN * d->gru_b_ih_l1[2 * Hg + u]
+                            : blk == 1 ? cR * (d->gru_b_ih_l1[u] + d->gru_b_hh_l1[u])
+                            : blk == 2 ? cR * (d->gru_b_ih_l1[Hg + u] + d->gru_b_hh_l1[Hg + u])
+                                       : cN * d->gru_b_hh_l1[2 * Hg + u];
+          split(bias, r1[6], r1[7]);
+        }
+      }
+    }
     for (int i = 0; i < 2 * Hg; ++i) put(o_enc2c, nlc::kE2Wout + i, d->enc_out_w[i]);
     for (int i = 0; i < 2; ++i) put(o_enc2c, nlc::kE2Bout + i, d->enc_out_b[i]);
   }
@@ -311,7 +346,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   m->d.w_hh0_t = base + o_hh0; m->d.w_ih1_t = base + o_ih1; m->d.w_hh1_t = base + o_hh1;
   m->d.b_ih1 = base + o_b_ih1; m->d.b_hh1 = base + o_b_hh1; m->d.w_out = base + o_wout; m->d.b_out = base + o_bout;
   m->d.enc_tc_w = base + o_tc; m->d.mlp_tc_w2 = base + o_tc_w2; m->d.mlp_tc_w3 = base + o_tc_w3; m->d.b3_tc = base + o_b3tc;
-  m->d.enc2_w = base + o_enc2w; m->d.enc2_c = base + o_enc2c;
+  m->d.enc2_w = base + o_enc2w; m->d.enc2_c = base + o_enc2c; m->d.enc2_x = base + o_enc2x;
   m->d.mlp2_w1 = base + o_m2w1; m->d.mlp2_w2 = base + o_m2w2; m->d.mlp2_w3 = base + o_m2w3; m->d.mlp2_c = base + o_m2c;
   m->d.w1_full_t = base + o_w1full; m->d.b1_raw = base + o_b1raw; m->d.w1x_t = base + o_w1x; m->d.b1_fold = base + o_b1f;
   m->d.w2_t = base + o_w2; m->d.b2 = base + o_b2; m->d.w3_t = base + o_w3; m->d.b3 = base + o_b3;
