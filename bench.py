@@ -300,9 +300,14 @@ def run_gpu(args, env, K, H, desc):
         kernels = {"encoder": {"name": "encode_gru_kernel" if args.math == "fp32" else "encode_tc2_kernel", "ms": ms_enc, "flop": enc_flop},
                    "rollout": {"name": roll_name, "ms": ms_roll, "flop": roll_flop}}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        # MMA FLOPs the tensor pipe actually executes per algorithmic FLOP: 3 fp16 products per fp32-class product in
+        # tc_split3 (A_hi B_hi + A_lo B_hi + A_hi B_lo), 1 in tc_fp16, none on the FFMA path
+        issue_mult = {"tc_split3": 3.0, "tc_fp16": 1.0, "fp32": 0.0}[args.math]
         for kv in kernels.values():
             kv["tflops"] = kv["flop"] / (kv["ms"] * 1e-3) / 1e12
             kv["frac"] = kv["tflops"] / peaks["bf16_tflops_sustained"]
+            kv["issued_tflops"] = issue_mult * kv["tflops"]
+            kv["issued_frac"] = kv["issued_tflops"] / peaks["bf16_tflops_sustained"]
         achieved = kernels[dom]["tflops"]
         # secondary roofline: transcendental (MUFU / XU pipe) throughput.  Counts per rollout-step from the kernels' code:
         # encoder 8 GRU cells x 64 units x (3 ex2 + 1 rcp; the (r,z) reciprocal is a Newton iteration on the FMA pipe) =
@@ -335,11 +340,12 @@ def run_gpu(args, env, K, H, desc):
             "gpu_launches": launches * world,
             "roofline": {"bound": "tensor", "kernel": kernels[dom]["name"],
                          "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"],
+                         "frac": achieved / peaks["bf16_tflops_sustained"], "issued_frac": kernels[dom]["issued_frac"],
+                         "traffic": traffic, "peak_source": peaks["source"],
                          "kernel_ms": kernels[dom]["ms"], "flop_per_launch": kernels[dom]["flop"], "kernels": kernels,
-                         "note": "algorithmic (hoisted) FLOPs per launch / CUDA-event time; peak = measured sustained bf16 "
-                                 "tensor TFLOP/s.  tc_split3 issues 3 fp16 MMAs per algorithmic product (fp32-class result), "
-                                 "so frac <= 1/3 by construction; both kernels are bound by their CUDA-core gate / sphere-map "
+                         "note": "frac = algorithmic (hoisted) FLOPs per launch / CUDA-event time / measured sustained bf16 tensor "
+                                 "TFLOP/s.  tc_split3 issues 3 fp16 MMAs per algorithmic product (fp32-class result), so frac <= 1/3 "
+                                 "by construction; issued_frac counts the MMA FLOPs the tensor pipe executes against the same peak; both kernels are bound by their CUDA-core gate / sphere-map "
                                  "epilogues (MUFU + issue), not by the MMAs (see profiles/ and DESIGN.md 3).",
                          "whole_step_achieved": HOISTED_FLOP[env] * steps_per_plan / (ms_dev * 1e-3) / 1e12},
         }
