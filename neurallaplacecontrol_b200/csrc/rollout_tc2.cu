@@ -84,13 +84,13 @@ __device__ __forceinline__ float mufu_tanh(float x) { float y; asm("tanh.approx.
 __device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // tanh of two pre-activations that carry the folded scale x' = -2 log2(e) x
-template <bool kAccurate>
+template <bool kAccurate, int kRcp>
 __device__ __forceinline__ f2_t tanh2_scaled(f2_t xs) {
   float a, b;
   if (kAccurate) {
     upk2(xs, a, b);
     const f2_t d = add2(pk2(mufu_ex2(fminf(a, 120.0f)), mufu_ex2(fminf(b, 120.0f))), pk2(1.0f, 1.0f));
-    return fma2(pk2(2.0f, 2.0f), rcp2<3>(d), pk2(-1.0f, -1.0f));
+    return fma2(pk2(2.0f, 2.0f), rcp2<kRcp>(d), pk2(-1.0f, -1.0f));
   }
   upk2(mul2(xs, pk2(-0.34657359027997264f, -0.34657359027997264f)), a, b);
   return pk2(mufu_tanh(a), mufu_tanh(b));
@@ -141,9 +141,9 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, 
 // Two (channel, term) pairs of the L3 epilogue.  v = (theta', phi') pre-activations (bias added, scale folded):
 //   y = tanh(theta_pre) -> theta = pi y (w_nl.py:59);   radius = tan((pi/2) sigmoid(2 phi_pre)) (w_nl.py:60-62 + sphere map,
 //   written through s = sigmoid(-2|phi_pre|) in (0, 1/2] so both tails keep relative accuracy, common.cuh:sphere_radius);
-//   term = weight_k radius cos(pi (y + k t/T)).      MUFU: 2 ex2 + 1 cos + 1 rcp per pair; the two sigmoids' reciprocals
+//   term = weight_k radius cos(pi y + k pi t/T).      MUFU: 2 ex2 + 1 cos + 1 rcp per pair; the two sigmoids' reciprocals
 //   come from ONE Newton reciprocal of the product of their denominators.
-template <bool kAccurate>
+template <bool kAccurate, int kRcp>
 __device__ __forceinline__ void l3_two_pairs(f2_t th, f2_t ph, float phase0, float phase1, float w0, float w1, float& t0, float& t1) {
   float a0, a1, b0, b1;
   upk2(th, a0, a1);
@@ -154,9 +154,14 @@ __device__ __forceinline__ void l3_two_pairs(f2_t th, f2_t ph, float phase0, flo
   if (kAccurate) {
     const f2_t d1 = add2(pk2(mufu_ex2(fminf(a0, 60.0f)), mufu_ex2(fminf(a1, 60.0f))), one);
     const f2_t d2 = add2(e2, one);
-    const f2_t inv = rcp2<3>(mul2(d1, d2));
-    y = fma2(pk2(2.0f, 2.0f), mul2(d2, inv), pk2(-1.0f, -1.0f));
-    sg = mul2(e2, mul2(d1, inv));
+    if (kRcp == 0) {  // two independent MUFU reciprocals: shortest dependency chain
+      y = fma2(pk2(2.0f, 2.0f), rcp2<0>(d1), pk2(-1.0f, -1.0f));
+      sg = mul2(e2, rcp2<0>(d2));
+    } else {          // one Newton reciprocal of the product on the FMA pipe: fewest MUFU operations
+      const f2_t inv = rcp2<kRcp>(mul2(d1, d2));
+      y = fma2(pk2(2.0f, 2.0f), mul2(d2, inv), pk2(-1.0f, -1.0f));
+      sg = mul2(e2, mul2(d1, inv));
+    }
   } else {
     float c0, c1;
     upk2(mul2(th, pk2(-0.34657359027997264f, -0.34657359027997264f)), c0, c1);
@@ -182,19 +187,17 @@ __device__ __forceinline__ void l3_two_pairs(f2_t th, f2_t ph, float phase0, flo
   const bool neg0 = b0 >= 0.0f, neg1 = b1 >= 0.0f;
   const float rad0 = (neg0 ? sn0 : cs0) * mufu_rcp(neg0 ? cs0 : sn0);
   const float rad1 = (neg1 ? sn1 : cs1) * mufu_rcp(neg1 ? cs1 : sn1);
-  // cos(pi (y + phase)), phase in half-turns: exact reduction to [-1, 1], then cos.approx
+  // cos(pi y + a_k), a_k = pi k t/T reduced to (-pi, pi]: the argument stays inside (-2 pi, 2 pi), where cos.approx is
+  // good to 5.2e-7 absolute without any further range reduction (tools/cos_err.cu; 3.4e-7 with an exact reduction)
   float y0, y1;
   upk2(y, y0, y1);
-  float z0 = y0 + phase0, z1 = y1 + phase1;
-  z0 = fmaf(-2.0f, rintf(0.5f * z0), z0);
-  z1 = fmaf(-2.0f, rintf(0.5f * z1), z1);
-  t0 = (w0 * rad0) * mufu_cos(3.14159265358979f * z0);
-  t1 = (w1 * rad1) * mufu_cos(3.14159265358979f * z1);
+  t0 = (w0 * rad0) * mufu_cos(fmaf(3.14159265358979f, y0, phase0));
+  t1 = (w1 * rad1) * mufu_cos(fmaf(3.14159265358979f, y1, phase1));
 }
 
 // L3 epilogue of one 16-column chunk (8 pairs); kChunk = chunk index in the full N3t column space, kCol0 = first chunk
 // of the half that currently sits in the D region
-template <int NX, int S, int kChunk, int kCol0, bool kAccurate>
+template <int NX, int S, int kChunk, int kCol0, bool kAccurate, int kRcp>
 __device__ __forceinline__ void l3_chunk(uint32_t tD, const float* __restrict__ b3, const float* __restrict__ phase,
                                          const float* __restrict__ weight, float (&delta)[NX]) {
   f2_t v[8];
@@ -220,24 +223,24 @@ __device__ __forceinline__ void l3_chunk(uint32_t tD, const float* __restrict__ 
       const int ch0 = p0 / S, k0 = p0 - ch0 * S;
       const int ch1 = (p1 < NX * S) ? p1 / S : ch0, k1 = (p1 < NX * S) ? p1 - ch1 * S : k0;
       float t0, t1;
-      l3_two_pairs<kAccurate>(pk2(th0, th1), pk2(ph0, ph1), phase[k0], phase[k1], weight[k0], weight[k1], t0, t1);
+      l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phase[k0], phase[k1], weight[k0], weight[k1], t0, t1);
       delta[ch0] += t0;
       if (p1 < NX * S) delta[ch1] += t1;
     }
   }
 }
 // chunks kChunk, kChunk+2, ... < kEnd (the two column halves of a sample take alternating chunks)
-template <int NX, int S, int kChunk, int kEnd, int kCol0, bool kAccurate>
+template <int NX, int S, int kChunk, int kEnd, int kCol0, bool kAccurate, int kRcp>
 struct L3Loop {
   static __device__ __forceinline__ void run(uint32_t tD, const float* b3, const float* phase, const float* weight, float (&delta)[NX]) {
     if constexpr (kChunk < kEnd) {
-      l3_chunk<NX, S, kChunk, kCol0, kAccurate>(tD, b3, phase, weight, delta);
-      L3Loop<NX, S, kChunk + 2, kEnd, kCol0, kAccurate>::run(tD, b3, phase, weight, delta);
+      l3_chunk<NX, S, kChunk, kCol0, kAccurate, kRcp>(tD, b3, phase, weight, delta);
+      L3Loop<NX, S, kChunk + 2, kEnd, kCol0, kAccurate, kRcp>::run(tD, b3, phase, weight, delta);
     }
   }
 };
 
-template <int NX, int S, bool kSplit3>
+template <int NX, int S, bool kSplit3, int kRcp>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int Lp = NX + 2;
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
     for (int i = tid; i < 2 * N3t * kH * 2 / 16; i += kThreads) d3[i] = __ldg(s3 + i);
     for (int i = tid; i < kH; i += kThreads) s.b2[i] = a.m.mlp2_c[i];
     for (int i = tid; i < 256; i += kThreads) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
-    for (int i = tid; i < S; i += kThreads) { s.phase[i] = a.m.ilt_phase[i] * 0.318309886183791f; s.weight[i] = a.m.ilt_weight[i]; }
+    for (int i = tid; i < S; i += kThreads) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
     if (tid < NX) { s.smean[tid] = a.m.state_mean[tid]; s.sinv[tid] = a.m.state_inv_std[tid]; }
     if (tid == 0) {
       for (int g = 0; g < 2; ++g) mbar_init(&s.done[g], 1);
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
             ldtm16p(tD + n0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = tanh2_scaled<kSplit3>(v[i]);
+            for (int i = 0; i < 8; ++i) v[i] = tanh2_scaled<kSplit3, kRcp>(v[i]);
             uint32_t ph[8], pl[8];
             pack16<kSplit3>(v, ph, pl);
             tmem_st8(tA + n0 / 2, ph);
@@ -394,8 +397,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 b = *reinterpret_cast<const float4*>(s.b2 + n0 + 4 * i);
-              v[2 * i] = tanh2_scaled<kSplit3>(add2(v[2 * i], pk2(b.x, b.y)));
-              v[2 * i + 1] = tanh2_scaled<kSplit3>(add2(v[2 * i + 1], pk2(b.z, b.w)));
+              v[2 * i] = tanh2_scaled<kSplit3, kRcp>(add2(v[2 * i], pk2(b.x, b.y)));
+              v[2 * i + 1] = tanh2_scaled<kSplit3, kRcp>(add2(v[2 * i + 1], pk2(b.z, b.w)));
             }
             uint32_t ph[8], pl[8];
             pack16<kSplit3>(v, ph, pl);
@@ -415,8 +418,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         wait_mma();
         mark(5);
         if (active) {
-          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3>::run(tD, s.b3, s.phase, s.weight, delta);
-          else L3Loop<NX, S, 1, kChunksA, 0, kSplit3>::run(tD, s.b3, s.phase, s.weight, delta);
+          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
+          else L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
         }
         if (N3b > 0) {
           mark(6);
@@ -426,8 +429,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
           if (active) {
             constexpr int kFirstB0 = kChunksA + (kChunksA & 1);        // first chunk >= kChunksA with even index
             constexpr int kFirstB1 = kChunksA + 1 - (kChunksA & 1);    // ... with odd index
-            if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3>::run(tD, s.b3, s.phase, s.weight, delta);
-            else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3>::run(tD, s.b3, s.phase, s.weight, delta);
+            if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
+            else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
           }
         }
 #pragma unroll
@@ -459,12 +462,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
-template <int NX, int S, bool kSplit3>
+template <int NX, int S, bool kSplit3, int kRcp>
 static int launch_one(const Args& a, cudaStream_t stream) {
   constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
   const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3t * kH * 2 + sizeof(SmemTail) + 128;
   NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
-  auto kern = rollout_tc2_kernel<NX, S, kSplit3>;
+  auto kern = rollout_tc2_kernel<NX, S, kSplit3, kRcp>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // one group per 32..128 samples: enough CTAs to give every group at least one warp of samples, at most one per SM
   int grid = (a.K + 63) / 64;
@@ -487,8 +490,14 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
   a.trace = g_roll_trace;
-#define NLC_RT2_CASE(NX_, S_) \
-  if (m->nx == NX_ && m->S == S_) return split3 ? rt2::launch_one<NX_, S_, true>(a, stream) : rt2::launch_one<NX_, S_, false>(a, stream);
+  // reciprocal flavour of the fp32-class epilogues: 3 = Newton on the FMA pipe (default: 1.71 ms at config 4),
+  // 0 = MUFU.RCP (1.85 ms: shorter chains, but the MUFU pipe is the scarcer one).  NLC_ROLLOUT_RCP is a measurement knob.
+  static const int rcp = [] { const char* e = getenv("NLC_ROLLOUT_RCP"); return (e && e[0] == '0') ? 0 : 3; }();
+#define NLC_RT2_CASE(NX_, S_)                                                                                   \
+  if (m->nx == NX_ && m->S == S_) {                                                                             \
+    if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, stream);                                          \
+    return rcp == 3 ? rt2::launch_one<NX_, S_, true, 3>(a, stream) : rt2::launch_one<NX_, S_, true, 0>(a, stream); \
+  }
   NLC_RT2_CASE(3, 17)
   NLC_RT2_CASE(5, 17)
   NLC_RT2_CASE(6, 17)
