@@ -9,7 +9,7 @@
 //           per-block partials, the last block to finish adds them in block order (deterministic).
 //   combine softmax_combine_kernel : beta = min beta_g, rescale by exp(-(beta_g-beta)/lambda),
 //                                U += W/eta, action = U[0]*u_scale.
-// HBM-bound streaming kernels: rows of noise are read as contiguous T*nu-float rows, 8 rows per block pass.
+// HBM-bound streaming kernels: rows of noise are read as contiguous T*nu-float rows, 32 rows per warp pass.
 #include "common.cuh"
 
 namespace nlc {
@@ -52,41 +52,74 @@ __global__ void __launch_bounds__(256) softmax_min_kernel(const float* __restric
   }
 }
 
-// block = 256 threads laid out as (ry, j): j < TNp columns (TNp = T*nu rounded up to 32), ry rows per pass.
+// One block = 8 warps over a contiguous range of samples.  A warp takes 32 samples at a time: lane r computes the weight of
+// sample r (one exp per sample, not per element), then the 32 noise rows stream through with the weight broadcast by
+// shuffle; lane l owns columns l, l+32, ... of W (<= 8 accumulators), so every load is a contiguous 128-byte line and
+// 16 loads per lane are in flight (rows unrolled by four).  Partial sums: warps in warp order through shared memory,
+// blocks in block order by the last block to finish - run-to-run identical.
 __global__ void __launch_bounds__(256) softmax_sum_kernel(const float* __restrict__ cost, const float* __restrict__ noise,
-                                                          int K, int TN, int TNp, float inv_lambda, SoftWs* ws,
+                                                          int K, int TN, float inv_lambda, SoftWs* ws,
                                                           float* partials /*[grid][1+TN]*/, float* triple,
                                                           float* weights, int rows_per_block) {
-  extern __shared__ float red[];  // [RY][TNp] + [RY]
-  const int RY = 256 / TNp;
-  const int j = threadIdx.x % TNp, ry = threadIdx.x / TNp;
+  __shared__ float red[8][257];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float beta = ord2f(ws->min_ord);
   const int kb = blockIdx.x * rows_per_block;
   const int ke = min(K, kb + rows_per_block);
-  float acc = 0.0f, eta = 0.0f;
-  if (ry < RY) {
-    for (int k = kb + ry; k < ke; k += RY) {
-      const float w = exp_acc(-inv_lambda * (__ldg(cost + k) - beta));  // _ensure_non_zero, mppi_delay.py:12-13
-      if (j < TN) acc = fmaf(w, __ldg(noise + (size_t)k * TN + j), acc);
-      if (j == 0) {
-        eta += w;
-        if (weights) weights[k] = w;
+  const int nci = (TN + 31) >> 5;  // column chunks of 32 (<= 8)
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  float eta = 0.0f;
+  for (int k0 = kb + 32 * warp; k0 < ke; k0 += 32 * 8) {
+    const int k = k0 + lane;
+    float w = 0.0f;
+    if (k < ke) {
+      w = exp_acc(-inv_lambda * (__ldg(cost + k) - beta));  // _ensure_non_zero, mppi_delay.py:12-13
+      if (weights) weights[k] = w;
+    }
+    eta += w;
+    const int nr = min(32, ke - k0);
+    const float* base = noise + (size_t)k0 * TN + lane;
+    int r = 0;
+    for (; r + 4 <= nr; r += 4) {
+      float v[4][8];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          v[rr][i] = (i < nci && lane + 32 * i < TN) ? __ldg(base + (size_t)(r + rr) * TN + 32 * i) : 0.0f;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float wr = __shfl_sync(0xffffffffu, w, r + rr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wr, v[rr][i], acc[i]);
       }
     }
-    red[ry * TNp + j] = acc;
-    if (j == 0) red[RY * TNp + ry] = eta;
+    for (; r < nr; ++r) {
+      const float wr = __shfl_sync(0xffffffffu, w, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nci && lane + 32 * i < TN) acc[i] = fmaf(wr, __ldg(base + (size_t)r * TN + 32 * i), acc[i]);
+    }
   }
+  eta = warp_sum(eta);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane + 32 * i] = acc[i];
+  if (lane == 0) red[warp][256] = eta;
   __syncthreads();
   float* my = partials + (size_t)blockIdx.x * (1 + TN);
   if (threadIdx.x < TN) {
-    float s = 0.0f;
-    for (int r = 0; r < RY; ++r) s += red[r * TNp + threadIdx.x];
-    my[1 + threadIdx.x] = s;
+    float sacc = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sacc += red[wv][threadIdx.x];
+    my[1 + threadIdx.x] = sacc;
   }
   if (threadIdx.x == 0) {
-    float s = 0.0f;
-    for (int r = 0; r < RY; ++r) s += red[RY * TNp + r];
-    my[0] = s;
+    float sacc = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sacc += red[wv][256];
+    my[0] = sacc;
   }
   __threadfence();
   __shared__ bool last;
@@ -96,9 +129,9 @@ __global__ void __launch_bounds__(256) softmax_sum_kernel(const float* __restric
   if (last) {  // fixed block order => run-to-run identical sums
     __threadfence();
     for (int c = threadIdx.x; c < 1 + TN; c += blockDim.x) {
-      float s = 0.0f;
-      for (unsigned b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * (1 + TN) + c];
-      triple[1 + c] = s;
+      float sacc = 0.0f;
+      for (unsigned bb = 0; bb < gridDim.x; ++bb) sacc += partials[(size_t)bb * (1 + TN) + c];
+      triple[1 + c] = sacc;
     }
     if (threadIdx.x == 0) triple[0] = beta;
   }
@@ -156,11 +189,8 @@ extern "C" int nlc_softmax_partial(const float* cost_dev, const float* noise_dev
   NLC_LAUNCH_OK("softmax_min_kernel");
   const int grid = sum_grid(K);
   const int rows_per_block = (K + grid - 1) / grid;
-  const int TNp = (TN + 31) / 32 * 32;
-  const int RY = 256 / TNp;
-  const size_t smem = (size_t)(RY * TNp + RY) * sizeof(float);
-  softmax_sum_kernel<<<grid, 256, smem, s>>>(cost_dev, noise_dev, K, TN, TNp, 1.0f / lambda_, ws, partials, triple_dev,
-                                             weights_dev, rows_per_block);
+  softmax_sum_kernel<<<grid, 256, 0, s>>>(cost_dev, noise_dev, K, TN, 1.0f / lambda_, ws, partials, triple_dev, weights_dev,
+                                          rows_per_block);
   NLC_LAUNCH_OK("softmax_sum_kernel");
   return NLC_OK;
 }
