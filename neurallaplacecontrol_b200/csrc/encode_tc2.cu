@@ -3,32 +3,35 @@
 // self-tests; encode_gru.cu is the fp32 CUDA-core anchor.)
 //
 // Dataflow as in encode_gru.cu: all K*T windows of a plan in one wide pass, M = 128 windows per tile, persistent CTAs,
-// zero-state products skipped; the ten 64x192 recurrent products of a window are tcgen05.mma (kind::f16) with fp32
-// accumulators in TMEM, the gate nonlinearities run on the CUDA cores.  What this form does differently, each item
-// from a measurement (profiles/r1_encoder_*.md):
+// zero-state products skipped; the recurrent products of a window are tcgen05.mma (kind::f16) with fp32 accumulators in
+// TMEM, the gate nonlinearities run on the CUDA cores.  What this form does differently, each item from a measurement
+// (profiles/r1_encoder_*.md, r1_mma_rate.md):
 //   * a dedicated MMA warp.  tcgen05.mma issue is back-pressured by MMA execution (~95 clk per instruction measured
 //     with tools/trace_encoder.py), so an epilogue thread that also issues loses the whole MMA time every cell and the
 //     other warps end up waiting for it: a third of every step went into those waits.  16 epilogue warps + 1 MMA warp,
 //     coupled only by mbarriers (one arrival per warp); no CTA-wide barrier in the steady state;
-//   * -log2(e) / -2 log2(e) folded into the weight images, biases and layer-0 input weights on the host (model.cu):
-//     pre-activations feed ex2 directly;
+//   * the epilogue does gates and nothing else.  Layer 0's input projection W_ih0 x and the biases of BOTH layers ride
+//     on the tensor cores as one extra K block of the layer-0 state operand, [x_hi x_lo x_hi .. | 1 1] against
+//     [W_hi W_hi W_lo .. | b_hi b_lo]: one K = 16 MMA with accumulate = 0 initialises an accumulator tile with all three
+//     split-3 terms of W x + b, the hidden products accumulate on top.  No input FMAs, no bias loads, no re-arming of
+//     accumulators, no special case for the zero-state cell (3.06 -> 2.35 ms at config 4);
+//   * -log2(e) / -2 log2(e) folded into every operand image on the host (model.cu): pre-activations feed ex2 directly;
 //   * gate arithmetic in packed fp32x2 (FFMA2/FADD2/FMUL2: half the issue slots, f32x2.cuh);
 //   * the (r, z) reciprocal is a Newton iteration on the FMA pipe instead of a MUFU.RCP: 4 MUFU per hidden unit
 //     instead of 5 (tools/pipe_bench.cu: 34 vs 41.5 clk per warp-unit on the bare gate);
-//   * W_ih1 rows ordered [n | r | z] and accumulator columns [in | r | z | hn]: a layer-1 cell is two N=192 products
-//     (24 MMA instructions instead of 48);
-//   * every thread prefetches its own window entry for the next cell straight from global memory (no staging barrier).
+//   * W_ih1 rows ordered [n | r | z] and accumulator columns [in | r | z | hn]: a layer-1 cell is two N=192 products;
+//   * the threads that feed the [x | 1] block prefetch their window entry one cell ahead straight from global memory.
 //
 //   operands   fp16 hi (+ lo) images, K-major no-swizzle canonical layout; NLC_MATH_TC_SPLIT3: A_hi B_hi + A_lo B_hi +
 //              A_hi B_lo, fp32 accumulate (fp32-class);  NLC_MATH_TC_FP16: A_hi B_hi only.
-//   TMEM       D0[192] = [r | z | hn] of layer 0;  D1[256] = [in | r | z | hn] of layer 1.  Accumulators hold the
-//              biases between cells (re-written after every read), so MMAs always accumulate.
+//   TMEM       D0[256] = [r | z | hn | in] of layer 0;  D1[256] = [in | r | z | hn] of layer 1: all 512 columns.
 //   schedule   layer 0 runs one cell ahead of layer 1, so every MMA burst runs under the other layer's gate epilogue:
 //                 epi A(s+1) || MMA B(s)   ->   epi B(s) || MMA A(s+2)   ->   ...        (tiles software-pipelined)
 //   barriers   bar_a / bar_b: MMA A / B complete (tcgen05.commit);  h0_ready / h1_ready: all 16 epilogue warps stored
-//              their operand slice and re-armed their accumulator columns.
+//              their operand slice and finished reading their accumulator columns.
 //   threads    epilogue warp w < 16: TMEM lanes 32 (w & 3).. (its 32 windows), hidden units 16 (w >> 2).. +15 of both
-//              layers; warp 16: MMA issue.  544 threads -> 96 registers per thread.
+//              layers; warp 16: MMA issue.  544 threads -> 96 registers per thread (the register file is allocated in
+//              units of 4 warps: 104 would not launch).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -62,16 +65,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
-  const float4 t0 = *reinterpret_cast<const float4*>(p), t1 = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-}
-__device__ __forceinline__ void lds8p(const float* p, f2_t (&v)[4]) {
-  float t[8];
-  lds8(p, t);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = pk2(t[2 * i], t[2 * i + 1]);
-}
 __device__ __forceinline__ void ldtm8p(uint32_t taddr, f2_t (&v)[4]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -81,16 +74,6 @@ __device__ __forceinline__ void ldtm8p(uint32_t taddr, f2_t (&v)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = pk2u(r[2 * i], r[2 * i + 1]);
 }
-// re-arm 8 accumulator columns of this thread's TMEM lane with a bias vector
-__device__ __forceinline__ void bias_to_tmem8(uint32_t taddr, const float* b8) {
-  float v[8];
-  lds8(b8, v);
-  uint32_t r[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
-  tmem_st8(taddr, r);
-}
-
 // GRU cell update of two hidden units from pre-activations that already carry the exponent scales:
 //   pr, pz = -log2e (W_r. + b_r), -log2e (W_z. + b_z);   gi, gh = -2 log2e (W_in x + b_in), -2 log2e (W_hn h + b_hn)
 //   r = 1/(1 + 2^pr), z = 1/(1 + 2^pz) through ONE reciprocal of the product;  n = 2/(1 + 2^(gi + r gh)) - 1;

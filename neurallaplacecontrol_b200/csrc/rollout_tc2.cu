@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
             ldtm16p(tD + n0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = tanh2_scaled<kSplit3, kRcp>(v[i]);
+            for (int i = 0; i < 8; ++i) v[i] = tanh2_scaled<kSplit3, kRcp / 10>(v[i]);
             uint32_t ph[8], pl[8];
             pack16<kSplit3>(v, ph, pl);
             tmem_st8(tA + n0 / 2, ph);
@@ -397,8 +397,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 b = *reinterpret_cast<const float4*>(s.b2 + n0 + 4 * i);
-              v[2 * i] = tanh2_scaled<kSplit3, kRcp>(add2(v[2 * i], pk2(b.x, b.y)));
-              v[2 * i + 1] = tanh2_scaled<kSplit3, kRcp>(add2(v[2 * i + 1], pk2(b.z, b.w)));
+              v[2 * i] = tanh2_scaled<kSplit3, kRcp / 10>(add2(v[2 * i], pk2(b.x, b.y)));
+              v[2 * i + 1] = tanh2_scaled<kSplit3, kRcp / 10>(add2(v[2 * i + 1], pk2(b.z, b.w)));
             }
             uint32_t ph[8], pl[8];
             pack16<kSplit3>(v, ph, pl);
@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         wait_mma();
         mark(5);
         if (active) {
-          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
-          else L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
+          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+          else L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
         }
         if (N3b > 0) {
           mark(6);
@@ -429,8 +429,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
           if (active) {
             constexpr int kFirstB0 = kChunksA + (kChunksA & 1);        // first chunk >= kChunksA with even index
             constexpr int kFirstB1 = kChunksA + 1 - (kChunksA & 1);    // ... with odd index
-            if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
-            else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3, kRcp>::run(tD, s.b3, s.phase, s.weight, delta);
+            if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+            else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
           }
         }
 #pragma unroll
@@ -492,11 +492,14 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   a.trace = g_roll_trace;
   // reciprocal flavour of the fp32-class epilogues: 3 = Newton on the FMA pipe (default: 1.71 ms at config 4),
   // 0 = MUFU.RCP (1.85 ms: shorter chains, but the MUFU pipe is the scarcer one).  NLC_ROLLOUT_RCP is a measurement knob.
-  static const int rcp = [] { const char* e = getenv("NLC_ROLLOUT_RCP"); return (e && e[0] == '0') ? 0 : 3; }();
+  static const int rcp = [] { const char* e = getenv("NLC_ROLLOUT_RCP"); return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 33; }();
 #define NLC_RT2_CASE(NX_, S_)                                                                                   \
   if (m->nx == NX_ && m->S == S_) {                                                                             \
-    if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, stream);                                          \
-    return rcp == 3 ? rt2::launch_one<NX_, S_, true, 3>(a, stream) : rt2::launch_one<NX_, S_, true, 0>(a, stream); \
+    if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, stream);  /* digits: (MLP tanh, L3 pair) reciprocal flavour */                                          \
+    if (rcp == 0) return rt2::launch_one<NX_, S_, true, 0>(a, stream);                                          \
+    if (rcp == 3) return rt2::launch_one<NX_, S_, true, 3>(a, stream);                                          \
+    if (rcp == 30) return rt2::launch_one<NX_, S_, true, 30>(a, stream);                                        \
+    return rt2::launch_one<NX_, S_, true, 33>(a, stream);                                                       \
   }
   NLC_RT2_CASE(3, 17)
   NLC_RT2_CASE(5, 17)
