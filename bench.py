@@ -295,8 +295,8 @@ def run_gpu(args, env, K, H, desc):
         e2e = steps_per_plan / (ms_e2e * 1e-3)
         enc_flop = ENCODER_FLOP * Kl * H
         roll_flop = (HOISTED_FLOP[env] - ENCODER_FLOP) * Kl * H
-        two_tiles = (Kl + 127) // 128 > 148 and os.environ.get("NLC_ROLLOUT_FORM", "") != "1"  # the library's own choice
-        roll_name = "rollout_nl_kernel" if args.math == "fp32" else ("rollout_tc2_kernel" if two_tiles else "rollout_tc_kernel")
+        two_tiles = (Kl + 127) // 128 > 148  # the library's own choice: two 128-sample tiles per CTA beyond one wave
+        roll_name = "rollout_nl_kernel" if args.math == "fp32" else "rollout_tc2_kernel"
         kernels = {"encoder": {"name": "encode_gru_kernel" if args.math == "fp32" else "encode_tc2_kernel", "ms": ms_enc, "flop": enc_flop},
                    "rollout": {"name": roll_name, "ms": ms_roll, "flop": roll_flop}}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
@@ -312,13 +312,13 @@ def run_gpu(args, env, K, H, desc):
         # secondary roofline: transcendental (MUFU / XU pipe) throughput.  Counts per rollout-step from the kernels' code:
         # encoder 8 GRU cells x 64 units x (3 ex2 + 1 rcp; the (r,z) reciprocal is a Newton iteration on the FMA pipe) =
         # 2048 (3 tanh.approx in tc_fp16); two-tile rollout 2 x 128 tanh (1 ex2 each) + nx*S pairs x (2 ex2 + cos + rcp);
-        # one-tile rollout 2 x 128 x 2 + nx*S x 6.  Peak: 16 /clk/SM measured by tools/mufu_bench.cu (15.9) x 148 SMs x the
+        # Peak: 16 /clk/SM measured by tools/mufu_bench.cu (15.9) x 148 SMs x the
         # SM clock seen during the run.
         if args.math != "fp32":
             sm_hz = 1e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
             mufu_peak = 15.9 * 148 * sm_hz
             per_step = {"encoder": 8 * 64 * (4 if args.math == "tc_split3" else 3),
-                        "rollout": (2 * 128 + nx * inp["S"] * 4) if two_tiles else (4 * 128 + nx * inp["S"] * 6)}
+                        "rollout": 2 * 128 + nx * inp["S"] * 4}
             for name, kv in kernels.items():
                 kv["mufu_per_s"] = per_step[name] * Kl * H / (kv["ms"] * 1e-3)
                 kv["mufu_frac"] = kv["mufu_per_s"] / mufu_peak
@@ -332,7 +332,7 @@ def run_gpu(args, env, K, H, desc):
             "ms_per_step": ms_dev, "plan_latency_ms": ms_dev, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "env": env, "K": K, "H": H, "S": inp["S"], "hidden": 128, "history_window": B,
-                       "parallelism": f"K-sharded x{world}", "K_per_gpu": K // world, "math": args.math, "noise": "on-device Philox4x32-10",
+                       "parallelism": f"K-sharded x{world}", "K_per_gpu": K // world, "rollout_tiles_per_cta": 2 if two_tiles else 1, "math": args.math, "noise": "on-device Philox4x32-10",
                        "l2": "flushed between timed steps (256 MiB fill)", "keep_states": True},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 4 * (nx + B * nu),

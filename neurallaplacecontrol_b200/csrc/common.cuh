@@ -59,10 +59,8 @@ struct ModelDev {
   float* b_hh1;   // [3Hg]
   float* w_out;   // [2][Hg]
   float* b_out;   // [2]
-  // fp16 hi/lo splits of the three recurrent matrices in the tcgen05 canonical layout (see
-  // encode_tc.cu); [3 matrices][2 (hi,lo)][3Hg * Hg] halves
-  void* enc_tc_w;
-  // encode_tc2.cu: the same three matrices with -log2(e) (r, z rows) and -2 log2(e) (n rows) folded in so that the gate
+  // encode_tc2.cu: the three recurrent matrices as fp16 hi/lo tcgen05 operand images [3][2 (hi,lo)][3Hg * Hg] (K-major
+  // canonical layout, tc_pack.cuh) with -log2(e) (r, z rows) and -2 log2(e) (n rows) folded in so that the gate
   // epilogue feeds ex2 directly, W_ih1 with its rows ordered [n | r | z] (one N=192 product into adjacent accumulator
   // columns); and the matching fp32 constants (biases, layer-0 input weights, output layer), layout kE2* below
   void* enc2_w;
@@ -79,11 +77,6 @@ struct ModelDev {
   void* mlp2_w2;
   void* mlp2_w3;
   float* mlp2_c;
-  // fp16 hi/lo operand images of the representation MLP for the tcgen05 rollout (rollout_tc.cu):
-  // mlp_tc_w2 [2 (hi,lo)][128 x 128], mlp_tc_w3 [2][N3t x 128] with the pair-permuted rows of w3_t, zero padded
-  void* mlp_tc_w2;
-  void* mlp_tc_w3;
-  float* b3_tc;     // [N3t] pair-permuted, zero padded
   // ---- representation MLP (w_nl.py:32-63) --------------------------------------------------
   float* w1_full_t; // [2S+nx+2][Hm]  unfolded first layer (per-sample-time forward)
   float* b1_raw;    // [Hm]

@@ -3,7 +3,7 @@
 // of a plan are encoded up front in one wide, non-recurrent-in-t pass and the sequential rollout only
 // carries the representation MLP.
 //
-// This file is the fp32 CUDA-core (FFMA) form: the 1e-4 parity anchor.  encode_tc.cu is the tcgen05 form.
+// This file is the fp32 CUDA-core (FFMA) form: the 1e-4 parity anchor.  encode_tc2.cu is the tcgen05 form.
 //
 // One CTA = 256 threads = a tile of 64 windows.  The three recurrent matrices (k-major, 3 x 48 KB) stay
 // in shared memory for the CTA's whole persistent loop.  Thread (ug, rg) owns hidden units 4ug..4ug+3 of
@@ -210,7 +210,6 @@ int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, in
   return NLC_OK;
 }
 
-int launch_encode_tc(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream);
 int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream);
 
 // hist_ch: channels stored per history entry (model gin for nlc_model_forward, whose caller supplies the time channel
@@ -227,12 +226,7 @@ int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K
     case NLC_MATH_TC_FP16:
       // shapes without a tensor-core instantiation run on the fp32 kernel
       if (B < 2 || B * m->gin > 8 || m->gin > 2) return launch_encode_fp32(m, hist_dev, hist_ch, K, T, B, p_dev, s);
-      {
-        // NLC_ENCODER_V1=1 selects the first (lock-step) tcgen05 form for A/B measurements; default is the two-chain form
-        static const bool v1 = [] { const char* e = getenv("NLC_ENCODER_V1"); return e && e[0] == '1'; }();
-        if (v1) return launch_encode_tc(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
-        return launch_encode_tc2(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
-      }
+      return launch_encode_tc2(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
     default: set_error("nlc_encode_history: unknown math_mode %d", math_mode); return NLC_ERR_ARG;
   }
 }

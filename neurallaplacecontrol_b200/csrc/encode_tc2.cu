@@ -1,6 +1,5 @@
 // Delayed-history encoder (ReverseGRUEncoder.forward, w_nl.py:25-29) on the 5th-generation tensor cores: the default
-// form.  (encode_tc.cu is the first, lock-step form, kept for A/B measurements behind NLC_ENCODER_V1=1 and for the UMMA
-// self-tests; encode_gru.cu is the fp32 CUDA-core anchor.)
+// form (encode_gru.cu is the fp32 CUDA-core anchor; umma_selftest.cu checks the operand layouts in isolation).
 //
 // Dataflow as in encode_gru.cu: all K*T windows of a plan in one wide pass, M = 128 windows per tile, persistent CTAs,
 // zero-state products skipped; the recurrent products of a window are tcgen05.mma (kind::f16) with fp32 accumulators in

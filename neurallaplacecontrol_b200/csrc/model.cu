@@ -170,11 +170,9 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   size_t o_smean = A.add(nx), o_sinv = A.add(nx), o_amean = A.add(gin), o_ainv = A.add(gin);
   // tensor-core operand image of the three recurrent GRU matrices: fp16 hi/lo, UMMA canonical layout
   const size_t tc_halves = (size_t)3 * 2 * G3 * Hg;
-  size_t o_tc = A.add(tc_halves / 2);
   size_t o_enc2w = A.add(tc_halves / 2), o_enc2c = A.add(nlc::kE2Count), o_enc2x = A.add(2 * 256 * 8 / 2);
   size_t o_m2w1 = A.add((size_t)2 * Hm * 16 / 2), o_m2w2 = A.add((size_t)2 * Hm * Hm / 2), o_m2w3 = A.add((size_t)2 * N3t * Hm / 2);
   size_t o_m2c = A.add(128 + 256);
-  size_t o_tc_w2 = A.add((size_t)2 * Hm * Hm / 2), o_tc_w3 = A.add((size_t)2 * N3t * Hm / 2), o_b3tc = A.add(N3t);
 
   for (int i = 0; i < G3 * gin; ++i) put(o_w_ih0, i, d->gru_w_ih_l0[i]);
   for (int i = 0; i < G3; ++i) {
@@ -219,12 +217,6 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
     }
     put(o_amean, i, mean);
     put(o_ainv, i, 1.0 / stdv);
-  }
-  {
-    uint16_t* tc = reinterpret_cast<uint16_t*>(A.data.data() + o_tc);
-    const double* mats[3] = {d->gru_w_hh_l0, d->gru_w_ih_l1, d->gru_w_hh_l1};
-    for (int w = 0; w < 3; ++w)
-      nlc::tc_pack_weight_split(mats[w], G3, Hg, tc + (size_t)w * 2 * G3 * Hg, tc + (size_t)w * 2 * G3 * Hg + (size_t)G3 * Hg);
   }
   {
     // encode_tc2.cu operands: exponent scales folded (sigmoid(x) = 1/(1 + 2^(-log2e x)), tanh(x) = 2/(1 + 2^(-2 log2e x)) - 1)
@@ -293,21 +285,6 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
     for (int i = 0; i < 2; ++i) put(o_enc2c, nlc::kE2Bout + i, d->enc_out_b[i]);
   }
 
-  {
-    uint16_t* w2i = reinterpret_cast<uint16_t*>(A.data.data() + o_tc_w2);
-    nlc::tc_pack_weight_split(d->mlp_w2, Hm, Hm, w2i, w2i + (size_t)Hm * Hm);
-    std::vector<double> w3p((size_t)N3t * Hm, 0.0);
-    for (int c = 0; c < nx; ++c)
-      for (int k = 0; k < S; ++k)
-        for (int part = 0; part < 2; ++part) {
-          const int src = (part * nx + c) * S + k, dst = 2 * (c * S + k) + part;
-          for (int h = 0; h < Hm; ++h) w3p[(size_t)dst * Hm + h] = d->mlp_w4[(size_t)src * Hm + h];
-          put(o_b3tc, dst, d->mlp_b4[src]);
-        }
-    uint16_t* w3i = reinterpret_cast<uint16_t*>(A.data.data() + o_tc_w3);
-    nlc::tc_pack_weight_split(w3p.data(), N3t, Hm, w3i, w3i + (size_t)N3t * Hm);
-  }
-
   if (N3t <= 256) {  // rollout_tc2.cu operands: -2 log2(e) folded
     const double cN = -2.0 * 1.4426950408889634;
     std::vector<double> w2s((size_t)Hm * Hm);
@@ -345,7 +322,6 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   m->d.w_ih0 = base + o_w_ih0; m->d.b_ih0 = base + o_b_ih0; m->d.b_hh0 = base + o_b_hh0;
   m->d.w_hh0_t = base + o_hh0; m->d.w_ih1_t = base + o_ih1; m->d.w_hh1_t = base + o_hh1;
   m->d.b_ih1 = base + o_b_ih1; m->d.b_hh1 = base + o_b_hh1; m->d.w_out = base + o_wout; m->d.b_out = base + o_bout;
-  m->d.enc_tc_w = base + o_tc; m->d.mlp_tc_w2 = base + o_tc_w2; m->d.mlp_tc_w3 = base + o_tc_w3; m->d.b3_tc = base + o_b3tc;
   m->d.enc2_w = base + o_enc2w; m->d.enc2_c = base + o_enc2c; m->d.enc2_x = base + o_enc2x;
   m->d.mlp2_w1 = base + o_m2w1; m->d.mlp2_w2 = base + o_m2w2; m->d.mlp2_w3 = base + o_m2w3; m->d.mlp2_c = base + o_m2c;
   m->d.w1_full_t = base + o_w1full; m->d.b1_raw = base + o_b1raw; m->d.w1x_t = base + o_w1x; m->d.b1_fold = base + o_b1f;

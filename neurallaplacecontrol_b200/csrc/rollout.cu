@@ -260,32 +260,22 @@ int launch_rollout_fp32(nlc_model_s* m, const nlc_rollout_opts* o, const float* 
 
 int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K, int T, int B, float* p_dev, int math_mode,
                         cudaStream_t s);
-int launch_rollout_tc(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
-                      const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
-                      float* delta_out, int split3, int groups, cudaStream_t stream);
-
 int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                        const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
-                       float* delta_out, int split3, cudaStream_t stream);
+                       float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream);
 
 // math_mode dispatch: the tensor-core kernel when it has an instantiation for (nx, S), else the FFMA kernel
 static int launch_rollout(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                           const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
                           float* delta_out, int math_mode, cudaStream_t stream) {
   if (math_mode != NLC_MATH_FP32 && 2 * m->nx * m->S <= 256) {
-    // Two tiles per CTA (rollout_tc2.cu) pay off once the plan is more than one wave of 128-sample tiles; below that the
-    // first form's four column groups per tile give the shorter step (tools/bench_rollout.py sweep).
-    // NLC_ROLLOUT_FORM=1|2 forces a form (read at every call: the parity tests run both).
-    const char* f = getenv("NLC_ROLLOUT_FORM");
-    const int form = (f && (f[0] == '1' || f[0] == '2')) ? f[0] - '0' : ((K + 127) / 128 > 148 ? 2 : 1);
-    if (form == 2) {
-      int rc2 = launch_rollout_tc2(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out,
-                                   math_mode == NLC_MATH_TC_SPLIT3, stream);
-      if (rc2 != NLC_ERR_UNSUPPORTED) return rc2;
-    }
-    const char* g = getenv("NLC_ROLLOUT_GROUPS");
-    int rc = launch_rollout_tc(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out,
-                               math_mode == NLC_MATH_TC_SPLIT3, (g && atoi(g) == 2) ? 2 : 4, stream);
+    // rollout_tc2.cu: two tiles per CTA once the plan is more than one wave of 128-sample tiles, one tile on all 16 warps
+    // below that (the step latency is then all that matters).  NLC_ROLLOUT_TILES=1|2 forces a form (read at every call:
+    // the parity tests run both).
+    const char* f = getenv("NLC_ROLLOUT_TILES");
+    const int tiles = (f && (f[0] == '1' || f[0] == '2')) ? f[0] - '0' : ((K + 127) / 128 > 148 ? 2 : 1);
+    int rc = launch_rollout_tc2(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out,
+                                math_mode == NLC_MATH_TC_SPLIT3, tiles, stream);
     if (rc != NLC_ERR_UNSUPPORTED) return rc;
   }
   return launch_rollout_fp32(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out, stream);

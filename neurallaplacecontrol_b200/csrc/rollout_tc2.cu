@@ -1,6 +1,5 @@
-// Stages 2+3 for the Neural Laplace dynamics, representation MLP on the 5th-generation tensor cores: the default form.
-// (rollout_tc.cu is the first form - one tile per CTA, phases strictly alternating - kept for A/B measurements behind
-// NLC_ROLLOUT_FORM=1; rollout.cu is the fp32 CUDA-core anchor.)
+// Stages 2+3 for the Neural Laplace dynamics, representation MLP on the 5th-generation tensor cores
+// (rollout.cu is the fp32 CUDA-core anchor).
 //
 // Same recurrence as rollout.cu: state <- state + ILT(MLP([s | obs_n | p_action])), cost += running_cost, whole horizon in
 // one launch, state in registers.  The recurrence is a strict chain per sample (L1 -> L2 -> L3 -> ILT -> next step), so
@@ -72,7 +71,7 @@ struct SmemTail {  // after the weight images
   alignas(16) float b3[256];
   float phase[kMaxS], weight[kMaxS];
   float smean[kMaxNx], sinv[kMaxNx];
-  alignas(16) float exch[2][2][kRows * kMaxNx];  // [group][column half] partial ILT sums
+  alignas(16) float exch[4][kRows * kMaxNx];     // [tile * column groups + column group] partial ILT sums
   alignas(8) uint64_t done[2];
   uint32_t tmem_base;
 };
@@ -229,26 +228,32 @@ __device__ __forceinline__ void l3_chunk(uint32_t tD, const float* __restrict__ 
     }
   }
 }
-// chunks kChunk, kChunk+2, ... < kEnd (the two column halves of a sample take alternating chunks)
-template <int NX, int S, int kChunk, int kEnd, int kCol0, bool kAccurate, int kRcp>
+// chunks kChunk, kChunk + kStride, ... < kEnd (the column groups of a sample take chunks round-robin)
+template <int NX, int S, int kChunk, int kEnd, int kCol0, bool kAccurate, int kRcp, int kStride>
 struct L3Loop {
   static __device__ __forceinline__ void run(uint32_t tD, const float* b3, const float* phase, const float* weight, float (&delta)[NX]) {
     if constexpr (kChunk < kEnd) {
       l3_chunk<NX, S, kChunk, kCol0, kAccurate, kRcp>(tD, b3, phase, weight, delta);
-      L3Loop<NX, S, kChunk + 2, kEnd, kCol0, kAccurate, kRcp>::run(tD, b3, phase, weight, delta);
+      L3Loop<NX, S, kChunk + kStride, kEnd, kCol0, kAccurate, kRcp, kStride>::run(tD, b3, phase, weight, delta);
     }
   }
 };
 
-template <int NX, int S, bool kSplit3, int kRcp>
+template <int NX, int S, bool kSplit3, int kRcp, int kTiles>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int Lp = NX + 2;
   constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
   constexpr int kChunks = N3t / 16;
-  constexpr int kChunksA = N3t <= 128 ? kChunks : (kChunks + 1) / 2;  // chunks in the first column half
+  // kTiles == 2: two 128-sample tiles per CTA, 8 warps and 256 TMEM columns each, two column groups per tile, L3 in two
+  // column halves.  kTiles == 1 (plans of at most one wave of tiles, where the step latency is all that matters): one
+  // tile, all 16 warps on it in four column groups, L3 in one piece (A 128 + D up to 256 columns).
+  constexpr int kCG = 4 / kTiles;                                   // column groups per tile
+  constexpr int kGroupWarps = 4 * kCG, kGroupT = 32 * kGroupWarps;  // warps / threads per tile
+  constexpr int kColsPerThread = kH / kCG, kC16 = kColsPerThread / 16;
+  constexpr int kChunksA = (kTiles == 1 || N3t <= 128) ? kChunks : (kChunks + 1) / 2;  // chunks in the first column half
   constexpr int N3a = 16 * kChunksA, N3b = N3t - N3a;
-  static_assert(N3a <= 128 && N3b <= 128 && Lp + 1 <= 16, "tile shape");
+  static_assert((kTiles == 1 || (N3a <= 128 && N3b <= 128)) && N3t <= 256 && Lp + 1 <= 16, "tile shape");
   unsigned char* w1_img = smem_raw;                                   // [hi | lo] 128 x 16 halves = 4 KB each
   unsigned char* w2_img = w1_img + 2 * kH * 16 * 2;                   // [hi | lo] 32 KB each
   unsigned char* w3_img = w2_img + 2 * kH * kH * 2;                   // [hi | lo] N3t * 256 B each
@@ -282,8 +287,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   const uint32_t tmem = s.tmem_base;
 
   // samples of this group: a contiguous range, a multiple of 32 rows long (except at the very end of the plan)
-  const int g = warp >> 3;
-  const int n_slots = 2 * gridDim.x, slot = 2 * blockIdx.x + g;
+  const int g = warp / kGroupWarps;
+  const int n_slots = kTiles * gridDim.x, slot = kTiles * blockIdx.x + g;
   const int per_slot = ((a.K + n_slots - 1) / n_slots + 31) / 32 * 32;
   const long long r_begin_ll = (long long)slot * per_slot;
   const int r_begin = (int)(r_begin_ll < a.K ? r_begin_ll : a.K);
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
 
   {
     // =====================================  epilogue warps of group g  =====================================
-    const int wl = warp & 7, q = wl & 3, cg = wl >> 2;
+    const int wl = warp % kGroupWarps, q = wl & 3, cg = wl >> 2;
     const int row = 32 * q + lane;
     const uint32_t tlane = tg + ((uint32_t)(32 * q) << 16);
     const uint32_t tA = tlane + kColA, tD = tlane + kColD;
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
     auto issue = [&](int ev) {
       tmem_st_wait();
       fence_before_sync();
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGroupT) : "memory");
       if (wl == 0 && lane == 0) {
         fence_after_sync();
         if (ev == 0) issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w1_hi, w1_lo, kH, 1, kSbo16);
@@ -369,8 +374,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         mark(1);
         if (active) {
 #pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16) {
-            const int n0 = 64 * cg + 16 * c16;
+          for (int c16 = 0; c16 < kC16; ++c16) {
+            const int n0 = kColsPerThread * cg + 16 * c16;
             f2_t v[8];
             ldtm16p(tD + n0, v);
             tmem_ld_wait();
@@ -389,8 +394,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         mark(3);
         if (active) {
 #pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16) {
-            const int n0 = 64 * cg + 16 * c16;
+          for (int c16 = 0; c16 < kC16; ++c16) {
+            const int n0 = kColsPerThread * cg + 16 * c16;
             f2_t v[8];
             ldtm16p(tD + n0, v);
             tmem_ld_wait();
@@ -418,8 +423,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         wait_mma();
         mark(5);
         if (active) {
-          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
-          else L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
+          else if (cg == 1) L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
+          else if (kCG == 4 && cg == 2) L3Loop<NX, S, 2, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
+          else if (kCG == 4) L3Loop<NX, S, 3, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
         }
         if (N3b > 0) {
           mark(6);
@@ -429,20 +436,22 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
           if (active) {
             constexpr int kFirstB0 = kChunksA + (kChunksA & 1);        // first chunk >= kChunksA with even index
             constexpr int kFirstB1 = kChunksA + 1 - (kChunksA & 1);    // ... with odd index
-            if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
-            else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+            if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3, kRcp % 10, 2>::run(tD, s.b3, s.phase, s.weight, delta);
+            else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3, kRcp % 10, 2>::run(tD, s.b3, s.phase, s.weight, delta);
           }
         }
 #pragma unroll
-        for (int c = 0; c < NX; ++c) s.exch[g][cg][row * NX + c] = delta[c];
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-        // both threads of a sample add the partials in the same order: the replicated state stays bit-identical
+        for (int c = 0; c < NX; ++c) s.exch[g * kCG + cg][row * NX + c] = delta[c];
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGroupT) : "memory");
+        // every thread of a sample adds the partials in the same order: the replicated state stays bit-identical
 #pragma unroll
         for (int c = 0; c < NX; ++c) {
-          const float d = s.exch[g][0][row * NX + c] + s.exch[g][1][row * NX + c];
+          float d = s.exch[g * kCG][row * NX + c];
+#pragma unroll
+          for (int j = 1; j < kCG; ++j) d += s.exch[g * kCG + j][row * NX + c];
           st[c] += d;                                             // mppi_with_model.py:121
           in[c] = (st[c] - s.smean[c]) * s.sinv[c];
-          if (cg == 1 && live) {
+          if (cg == kCG - 1 && live) {
             if (a.states) a.states[((size_t)kk * a.T + t) * NX + c] = st[c];
             if (a.delta_out) a.delta_out[(size_t)kk * NX + c] = d;
           }
@@ -462,19 +471,25 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
-template <int NX, int S, bool kSplit3, int kRcp>
-static int launch_one(const Args& a, cudaStream_t stream) {
+template <int NX, int S, bool kSplit3, int kRcp, int kTiles>
+static int launch_one_t(const Args& a, cudaStream_t stream) {
   constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
   const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3t * kH * 2 + sizeof(SmemTail) + 128;
   NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
-  auto kern = rollout_tc2_kernel<NX, S, kSplit3, kRcp>;
+  auto kern = rollout_tc2_kernel<NX, S, kSplit3, kRcp, kTiles>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // one group per 32..128 samples: enough CTAs to give every group at least one warp of samples, at most one per SM
-  int grid = (a.K + 63) / 64;
+  // one tile slot per 32..128 samples: enough CTAs to give every slot at least one warp of samples, at most one per SM
+  int grid = (a.K + 32 * kTiles - 1) / (32 * kTiles);
   if (grid > 148) grid = 148;
   kern<<<grid, kThreads, smem, stream>>>(a);
   NLC_LAUNCH_OK("rollout_tc2_kernel");
   return NLC_OK;
+}
+
+// two tiles per CTA once the plan is more than one wave of 128-sample tiles, else one tile on all 16 warps
+template <int NX, int S, bool kSplit3, int kRcp>
+static int launch_one(const Args& a, int tiles, cudaStream_t stream) {
+  return tiles == 1 ? launch_one_t<NX, S, kSplit3, kRcp, 1>(a, stream) : launch_one_t<NX, S, kSplit3, kRcp, 2>(a, stream);
 }
 
 }  // namespace rt2
@@ -485,7 +500,7 @@ void set_rollout_trace(long long* p) { g_roll_trace = p; }
 
 int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                        const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
-                       float* delta_out, int split3, cudaStream_t stream) {
+                       float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream) {
   rt2::Args a;
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
@@ -495,11 +510,11 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   static const int rcp = [] { const char* e = getenv("NLC_ROLLOUT_RCP"); return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 33; }();
 #define NLC_RT2_CASE(NX_, S_)                                                                                   \
   if (m->nx == NX_ && m->S == S_) {                                                                             \
-    if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, stream);  /* digits: (MLP tanh, L3 pair) reciprocal flavour */                                          \
-    if (rcp == 0) return rt2::launch_one<NX_, S_, true, 0>(a, stream);                                          \
-    if (rcp == 3) return rt2::launch_one<NX_, S_, true, 3>(a, stream);                                          \
-    if (rcp == 30) return rt2::launch_one<NX_, S_, true, 30>(a, stream);                                        \
-    return rt2::launch_one<NX_, S_, true, 33>(a, stream);                                                       \
+    if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, tiles_per_cta, stream);  /* digits: (MLP tanh, L3 pair) reciprocal flavour */                                          \
+    if (rcp == 0) return rt2::launch_one<NX_, S_, true, 0>(a, tiles_per_cta, stream);                                          \
+    if (rcp == 3) return rt2::launch_one<NX_, S_, true, 3>(a, tiles_per_cta, stream);                                          \
+    if (rcp == 30) return rt2::launch_one<NX_, S_, true, 30>(a, tiles_per_cta, stream);                                        \
+    return rt2::launch_one<NX_, S_, true, 33>(a, tiles_per_cta, stream);                                                       \
   }
   NLC_RT2_CASE(3, 17)
   NLC_RT2_CASE(5, 17)

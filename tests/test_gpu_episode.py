@@ -63,7 +63,7 @@ def _make(env, mode, **kw):
 def test_batched_planner_reproduces_standalone_planners(env, mode, monkeypatch):
     """Instance i of a batch == MPPIDelay(seed=seeds[i]) on the same state / buffer / U: bit-identical samples, costs
     and actions over two consecutive control steps (same kernels, row-independent arithmetic)."""
-    monkeypatch.setenv("NLC_ROLLOUT_FORM", "1")  # both sides on the same rollout form regardless of I*K
+    monkeypatch.setenv("NLC_ROLLOUT_TILES", "1")  # both sides on the same rollout form regardless of I*K
     I, K, T, B = 3, 200, 6, 4
     nlc, m, nx, nu, ah, common = _make(env, mode, K=K, T=T)
     gen = torch.Generator().manual_seed(5)
@@ -119,7 +119,7 @@ def test_batched_planner_with_injected_noise_matches_reference_plan():
 def test_closed_loop_batch_equals_single_instance_loops(dynamics, monkeypatch):
     """run_closed_loop over I instances == I single-instance loops (MPPIDelay.command + env_step with I = 1), and with
     the analytic dynamics the pendulum swings towards upright (reward improves over a random policy)."""
-    monkeypatch.setenv("NLC_ROLLOUT_FORM", "1")
+    monkeypatch.setenv("NLC_ROLLOUT_TILES", "1")
     env, delay, I, K, T, n_steps = "oderl-pendulum", 1, 4, 256, 10, 8
     nlc, m, nx, nu, ah, common = _make(env, "fp32", K=K, T=T)
     dyn = nlc.AnalyticDelayDynamics(env, delay, DT) if dynamics == "analytic" else nlc.NLDynamics(m, DT)

@@ -270,12 +270,12 @@ def test_tc_encoder_matches_reference(env, mode, tol):
     assert relerr(outs["fp32"], outs[mode]) < tol, relerr(outs["fp32"], outs[mode])
 
 
-@pytest.mark.parametrize("form", ["1", "2"])
+@pytest.mark.parametrize("tiles", ["1", "2"])
 @pytest.mark.parametrize("mode,tol", [("tc_split3", 1e-4), ("tc_fp16", 2e-2)])
-def test_tc_plan_cfg1(mode, tol, form, monkeypatch):
+def test_tc_plan_cfg1(mode, tol, tiles, monkeypatch):
     """BASELINE config 1 end to end with the tensor-core encoder and either form of the tensor-core rollout.  tc_split3
     holds the fp32 bound (1e-4); the single-pass fp16 mode is the stated looser bound."""
-    monkeypatch.setenv("NLC_ROLLOUT_FORM", form)
+    monkeypatch.setenv("NLC_ROLLOUT_TILES", tiles)
     from oracle.gen_golden import START_STATE, injected_noise
     from test_gpu_parity import _run_plan
     from _util import action_relerr, load
@@ -295,7 +295,8 @@ def test_tc_plan_cfg1(mode, tol, form, monkeypatch):
 @pytest.mark.parametrize("env,K,T", [("oderl-acrobot", 20011, 6), ("oderl-cartpole", 19000, 5), ("oderl-pendulum", 40000, 4)])
 def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
     """Plans larger than one wave of 128-sample tiles take the two-tiles-per-CTA rollout (partially filled and ragged
-    last tiles, K not a multiple of 32): same costs and states as the one-tile form and as the fp32 anchor kernel."""
+    last tiles, K not a multiple of 32): same costs and states as the one-tile form (which then walks several tiles per
+    CTA) and as the fp32 anchor kernel."""
     import ctypes as C
 
     from oracle import costs
@@ -315,11 +316,11 @@ def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
     ro = L.RolloutOpts()
     ro.env, ro.state_constraint, ro.goal_x, ro.dynamics, ro.delay, ro.dt = L.ENV_IDS[env], 0, 0.0, 0, 0, DT
     outs = {}
-    for name, mode, form in (("fp32", "fp32", "1"), ("one_tile", "tc_split3", "1"), ("two_tiles", "tc_split3", "2"), ("auto", "tc_split3", "")):
-        if form:
-            monkeypatch.setenv("NLC_ROLLOUT_FORM", form)
+    for name, mode, tiles in (("fp32", "fp32", "1"), ("two_tiles", "tc_split3", "2"), ("one_tile", "tc_split3", "1"), ("auto", "tc_split3", "")):
+        if tiles:
+            monkeypatch.setenv("NLC_ROLLOUT_TILES", tiles)
         else:
-            monkeypatch.delenv("NLC_ROLLOUT_FORM", raising=False)
+            monkeypatch.delenv("NLC_ROLLOUT_TILES", raising=False)
         cost = torch.full((K,), float("nan"), device="cuda")
         states = torch.full((K, T, nx), float("nan"), device="cuda")
         L.check(lib.nlc_rollout_cost(h, C.byref(ro), state.data_ptr(), 1, p.data_ptr(), hist.data_ptr(), None, K, T, B, nu,

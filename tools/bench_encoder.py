@@ -5,7 +5,7 @@ CUDA events for each kernel form / measurement ablation given on the command lin
     python tools/bench_encoder.py [--env oderl-acrobot] [--K 65536] [--H 50] [--math tc_split3] VARIANT ...
 
 A VARIANT is a comma-separated list of NAME=VALUE environment settings read by the launcher at every call
-(NLC_ENC_ABLATE; NLC_ENC_FORM / NLC_ENC_RCP / NLC_ENCODER_V1 are latched at first use, so one form per process), e.g.
+(NLC_ENC_ABLATE; NLC_ENC_RCP is latched at first use, so one reciprocal flavour per process), e.g.
     python tools/bench_encoder.py NLC_ENC_ABLATE=0 NLC_ENC_ABLATE=1 NLC_ENC_ABLATE=9
 """
 import argparse

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Rollout microbenchmark (representation MLP + Fourier ILT + cost over the horizon, encoder output given), timed alone
 with CUDA events over a sweep of K.     python tools/bench_rollout.py [--env oderl-acrobot] [--H 50] [--math tc_split3] K ...
-NLC_ROLLOUT_FORM=1|2 in the environment forces a kernel form (default: by plan size)."""
+NLC_ROLLOUT_TILES=1|2 in the environment forces the tiles-per-CTA form (default: by plan size)."""
 import argparse
 import ctypes as C
 import json
@@ -64,7 +64,7 @@ def main():
             s.record(); run(); e.record(); e.synchronize()
             ms.append(s.elapsed_time(e))
         m = sorted(ms)[len(ms) // 2]
-        print(json.dumps({"K": K, "H": H, "env": args.env, "math": args.math, "form": os.environ.get("NLC_ROLLOUT_FORM", "auto"), "ms": m,
+        print(json.dumps({"K": K, "H": H, "env": args.env, "math": args.math, "tiles": os.environ.get("NLC_ROLLOUT_TILES", "auto"), "ms": m,
                           "rollout_steps_per_s": K * H / (m * 1e-3), "cost_checksum": float(cost.double().sum())}), flush=True)
 
 

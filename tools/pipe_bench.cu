@@ -1,5 +1,5 @@
 // Microbenchmark of the CUDA-core pipes the GRU / MLP gate epilogues live on (sm_100a): packed fp32x2 FMA issue rate,
-// MUFU f16x2 forms, and complete GRU gate updates in the variants considered for encode_tc.cu:
+// MUFU f16x2 forms, and complete GRU gate updates in the variants considered for encode_tc2.cu:
 //   v0  5 MUFU per unit (2 ex2 + shared rcp for r,z; ex2 + rcp for n), scalar fp32           (round-1 kernel)
 //   v1  same with log2(e) folded into the pre-activations and packed f32x2 arithmetic
 //   v2  3 MUFU per unit: the two reciprocals as Newton iterations on the FMA pipe (packed)
