@@ -229,9 +229,16 @@ int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int state_per_s
  * triple is used directly) and update U; the action lands in NLC_BUF_ACTION.                       */
 int nlc_planner_finish(nlc_planner_t p, void* stream);
 
+/* Both phases in one call for the single-shard planner, on the planner's own input buffers (NLC_BUF_STATE [nx],
+ * NLC_BUF_ACTION_BUFFER [B][nu], filled by the caller) with the on-device sampler.  The fixed launch sequence is captured
+ * once into a CUDA graph and replayed with one launch per control step (the sampler's call index lives in device memory);
+ * NLC_NO_GRAPH=1 in the environment keeps direct launches.                                          */
+int nlc_planner_step(nlc_planner_t p, void* stream);
+
 /* MPPIDelay.command (mppi_delay.py:193-224) end to end with HOST buffers, single shard: copies the
  * state [nx] and action_buffer [B][nu] (fp64, as the reference's callers hold them) to the device,
- * runs both phases, copies the action [nu] back and synchronises the stream.                      */
+ * runs both phases, copies the action [nu] back and synchronises the stream.  Without injected noise the whole step,
+ * copies included, is one CUDA-graph launch.                                                        */
 int nlc_planner_command_host(nlc_planner_t p, const double* state_host, const double* action_buffer_host,
                              const float* noise_in_dev, double* action_host, void* stream);
 

@@ -1,6 +1,7 @@
 // Planner handle: the device-resident state of one MPPIDelay object (planners/mppi_delay.py:64-230) and
 // the control step as a fixed sequence of kernel launches on one stream:
 //   perturb -> encode_history -> rollout_cost -> softmax (init, min, sum) -> [exchange triples] -> combine
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -19,9 +20,22 @@ struct nlc_planner_s {
   float *triple, *all_triples, *action, *stats, *state_in, *abuf_in;
   void* softmax_ws;
   // pinned host staging for the host-buffer entry point
-  float* h_in;   // [K*nx max? no: nx + B*nu]
+  float* h_in;   // [nx + B*nu]
   float* h_out;  // [nu]
+  // sampler call index in device memory (read by the perturb kernel, bumped right after it) so that a whole control step
+  // is a fixed sequence of launches with fixed arguments: captured once into CUDA graphs, replayed with one launch
+  unsigned long long* call_ctr;
+  cudaStream_t cap_stream;
+  cudaGraphExec_t graph_core, graph_host;  // [perturb .. combine] on the planner's own input buffers; same + H2D / D2H copies
+  bool graph_core_tried, graph_host_tried;
 };
+
+namespace nlc {
+int perturb_launch(const nlc_mppi_params* p, const float* U_prev_dev, float* U_dev, int roll, const float* noise_in_dev,
+                   uint64_t seed, uint64_t call_index, const unsigned long long* call_index_dev, const float* action_buffer_dev,
+                   float* perturbed_dev, float* noise_dev, float* hist_dev, float* actions_dev, float* pert_cost_dev, void* stream);
+int launch_bump_counter(unsigned long long* ctr, cudaStream_t stream);
+}  // namespace nlc
 
 using namespace nlc;
 
@@ -43,6 +57,8 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   }
   nlc_planner_s* p = new nlc_planner_s();
   p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;
+  p->call_ctr = nullptr; p->cap_stream = nullptr; p->graph_core = nullptr; p->graph_host = nullptr;
+  p->graph_core_tried = p->graph_host_tried = false;
   const size_t K = mp.K, T = mp.T, nu = mp.nu, B = mp.B, nx = d->nx, L = B - 1 + T, TN = T * nu;
   std::vector<size_t> sizes = {
       TN, TN, K * TN, K * TN, K * L * nu, K * TN, K, K * T * 2, K, K, (d->keep_states ? K * T * nx : 0),
@@ -53,6 +69,7 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->arena_bytes = total * sizeof(float);
   auto fail = [&](int code) {
     if (p->arena) cudaFree(p->arena);
+    if (p->call_ctr) cudaFree(p->call_ctr);
     if (p->h_in) cudaFreeHost(p->h_in);
     if (p->h_out) cudaFreeHost(p->h_out);
     delete p;
@@ -61,6 +78,9 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(NLC_ERR_CUDA); }
   if (cudaMalloc(&p->arena, p->arena_bytes) != cudaSuccess) { cudaGetLastError(); p->arena = nullptr; set_error("planner: cudaMalloc(%zu) failed", p->arena_bytes); return fail(NLC_ERR_NOMEM); }
   if (cudaMemset(p->arena, 0, p->arena_bytes) != cudaSuccess) { set_error("planner: memset failed"); return fail(NLC_ERR_CUDA); }
+  if (cudaMalloc(&p->call_ctr, sizeof(unsigned long long)) != cudaSuccess || cudaMemset(p->call_ctr, 0, sizeof(unsigned long long)) != cudaSuccess) {
+    cudaGetLastError(); set_error("planner: counter allocation failed"); return fail(NLC_ERR_NOMEM);
+  }
   float* base = static_cast<float*>(p->arena);
   float** slots[] = {&p->U, &p->U_rolled, &p->noise, &p->perturbed, &p->hist, &p->actions, &p->pert_cost, &p->p,
                      &p->cost_total, &p->weights, &p->states, &p->triple, &p->all_triples, &p->action, &p->stats,
@@ -78,6 +98,10 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
 extern "C" int nlc_planner_destroy(nlc_planner_t p) {
   if (!p) return NLC_OK;
   cudaSetDevice(p->device);
+  if (p->graph_core) cudaGraphExecDestroy(p->graph_core);
+  if (p->graph_host) cudaGraphExecDestroy(p->graph_host);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  if (p->call_ctr) cudaFree(p->call_ctr);
   if (p->arena) cudaFree(p->arena);
   if (p->h_in) cudaFreeHost(p->h_in);
   if (p->h_out) cudaFreeHost(p->h_out);
@@ -137,8 +161,10 @@ extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int 
   NLC_REQUIRE(p && state_dev && action_buffer_dev, NLC_ERR_ARG, "nlc_planner_rollout: null argument");
   const nlc_mppi_params& mp = p->d.mppi;
   NLC_CUDA_OK(cudaSetDevice(p->device));
-  int rc = nlc_perturb(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, p->calls, action_buffer_dev, p->perturbed,
-                       p->noise, p->hist, p->actions, p->pert_cost, stream);
+  int rc = perturb_launch(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, 0, p->call_ctr, action_buffer_dev, p->perturbed,
+                          p->noise, p->hist, p->actions, p->pert_cost, stream);
+  if (rc != NLC_OK) return rc;
+  rc = launch_bump_counter(p->call_ctr, static_cast<cudaStream_t>(stream));  // the next control step draws fresh samples
   if (rc != NLC_OK) return rc;
   p->calls++;
   if (p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
@@ -162,6 +188,81 @@ extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {
   return nlc_softmax_combine(triples, p->d.n_shards, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats, stream);
 }
 
+// One whole control step on the planner's own input buffers (state_in [nx], abuf_in [B][nu]), on-device sampler.
+static int planner_core_direct(nlc_planner_t p, void* stream) {
+  int rc = nlc_planner_rollout(p, p->state_in, 0, p->abuf_in, nullptr, stream);
+  if (rc != NLC_OK) return rc;
+  return nlc_planner_finish(p, stream);
+}
+
+// Capture that sequence (optionally bracketed by the pinned-host copies of the host entry point) once into a CUDA graph.
+// Capture runs on a private stream (the caller's may be the legacy default stream, which cannot capture); the executable
+// graph is then launched on the caller's stream.  Any failure leaves the planner on direct launches.
+static cudaGraphExec_t planner_capture(nlc_planner_t p, bool with_host_copies) {
+  static const bool disabled = [] { const char* e = getenv("NLC_NO_GRAPH"); return e && e[0] == '1'; }();
+  if (disabled || p->d.n_shards != 1) return nullptr;
+  if (!p->cap_stream && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  // first use of every kernel outside capture: one-time function attributes and lazy module loading must not be captured
+  const uint64_t calls0 = p->calls;
+  if (planner_core_direct(p, p->cap_stream) != NLC_OK || cudaStreamSynchronize(p->cap_stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  // undo the warm-up's side effects on the control sequence and the sampler: U <- U before the roll is not recoverable
+  // from U_rolled alone, so the warm-up ran on a scratch copy (see caller); the counter is rewound here
+  if (cudaMemsetAsync(p->call_ctr, 0, sizeof(unsigned long long), p->cap_stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  unsigned long long c0 = calls0;
+  if (cudaMemcpyAsync(p->call_ctr, &c0, sizeof(c0), cudaMemcpyHostToDevice, p->cap_stream) != cudaSuccess ||
+      cudaStreamSynchronize(p->cap_stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  p->calls = calls0;
+  const nlc_mppi_params& mp = p->d.mppi;
+  const int nx = p->d.nx, nb = mp.B * mp.nu;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  bool ok = true;
+  if (with_host_copies) {
+    ok = ok && cudaMemcpyAsync(p->state_in, p->h_in, sizeof(float) * nx, cudaMemcpyHostToDevice, p->cap_stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(p->abuf_in, p->h_in + nx, sizeof(float) * nb, cudaMemcpyHostToDevice, p->cap_stream) == cudaSuccess;
+  }
+  ok = ok && planner_core_direct(p, p->cap_stream) == NLC_OK;
+  if (with_host_copies) ok = ok && cudaMemcpyAsync(p->h_out, p->action, sizeof(float) * mp.nu, cudaMemcpyDeviceToHost, p->cap_stream) == cudaSuccess;
+  const cudaError_t ee = cudaStreamEndCapture(p->cap_stream, &graph);
+  p->calls = calls0;  // launches recorded during capture did not run
+  if (!ok || ee != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return nullptr; }
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGetLastError(); exec = nullptr; }
+  cudaGraphDestroy(graph);
+  return exec;
+}
+
+// The warm-up inside planner_capture runs a real control step; it must not change the planner's state.  U is saved and
+// restored around it (T*nu floats).
+static cudaGraphExec_t planner_capture_preserving_state(nlc_planner_t p, bool with_host_copies) {
+  const size_t n = sizeof(float) * p->d.mppi.T * p->d.mppi.nu;
+  std::vector<float> U(p->d.mppi.T * p->d.mppi.nu), st(p->d.nx), ab(p->d.mppi.B * p->d.mppi.nu);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(U.data(), p->U, n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(st.data(), p->state_in, sizeof(float) * st.size(), cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(ab.data(), p->abuf_in, sizeof(float) * ab.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  cudaGraphExec_t exec = planner_capture(p, with_host_copies);
+  cudaDeviceSynchronize();
+  cudaMemcpy(p->U, U.data(), n, cudaMemcpyHostToDevice);
+  cudaMemcpy(p->state_in, st.data(), sizeof(float) * st.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(p->abuf_in, ab.data(), sizeof(float) * ab.size(), cudaMemcpyHostToDevice);
+  cudaGetLastError();
+  return exec;
+}
+
+extern "C" int nlc_planner_step(nlc_planner_t p, void* stream) {
+  NLC_REQUIRE(p, NLC_ERR_ARG, "nlc_planner_step: null planner");
+  NLC_REQUIRE(p->d.n_shards == 1, NLC_ERR_UNSUPPORTED, "nlc_planner_step is the single-shard entry point");
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  if (!p->graph_core_tried) { p->graph_core_tried = true; p->graph_core = planner_capture_preserving_state(p, false); }
+  if (p->graph_core) {
+    NLC_CUDA_OK(cudaGraphLaunch(p->graph_core, static_cast<cudaStream_t>(stream)));
+    p->calls++;
+    count_launch(8);
+    return NLC_OK;
+  }
+  return planner_core_direct(p, stream);
+}
+
 extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_host, const double* action_buffer_host,
                                         const float* noise_in_dev, double* action_host, void* stream) {
   NLC_REQUIRE(p && state_host && action_buffer_host && action_host, NLC_ERR_ARG, "nlc_planner_command_host: null argument");
@@ -170,15 +271,22 @@ extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_hos
   const int nx = p->d.nx, nb = mp.B * mp.nu;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   NLC_CUDA_OK(cudaSetDevice(p->device));
+  if (!noise_in_dev && !p->graph_host_tried) { p->graph_host_tried = true; p->graph_host = planner_capture_preserving_state(p, true); }
   for (int i = 0; i < nx; ++i) p->h_in[i] = (float)state_host[i];
   for (int i = 0; i < nb; ++i) p->h_in[nx + i] = (float)action_buffer_host[i];
-  NLC_CUDA_OK(cudaMemcpyAsync(p->state_in, p->h_in, sizeof(float) * nx, cudaMemcpyHostToDevice, s));
-  NLC_CUDA_OK(cudaMemcpyAsync(p->abuf_in, p->h_in + nx, sizeof(float) * nb, cudaMemcpyHostToDevice, s));
-  int rc = nlc_planner_rollout(p, p->state_in, 0, p->abuf_in, noise_in_dev, stream);
-  if (rc != NLC_OK) return rc;
-  rc = nlc_planner_finish(p, stream);
-  if (rc != NLC_OK) return rc;
-  NLC_CUDA_OK(cudaMemcpyAsync(p->h_out, p->action, sizeof(float) * mp.nu, cudaMemcpyDeviceToHost, s));
+  if (!noise_in_dev && p->graph_host) {  // the whole step, copies included, as one graph launch
+    NLC_CUDA_OK(cudaGraphLaunch(p->graph_host, s));
+    p->calls++;
+    count_launch(8);
+  } else {
+    NLC_CUDA_OK(cudaMemcpyAsync(p->state_in, p->h_in, sizeof(float) * nx, cudaMemcpyHostToDevice, s));
+    NLC_CUDA_OK(cudaMemcpyAsync(p->abuf_in, p->h_in + nx, sizeof(float) * nb, cudaMemcpyHostToDevice, s));
+    int rc = nlc_planner_rollout(p, p->state_in, 0, p->abuf_in, noise_in_dev, stream);
+    if (rc != NLC_OK) return rc;
+    rc = nlc_planner_finish(p, stream);
+    if (rc != NLC_OK) return rc;
+    NLC_CUDA_OK(cudaMemcpyAsync(p->h_out, p->action, sizeof(float) * mp.nu, cudaMemcpyDeviceToHost, s));
+  }
   NLC_CUDA_OK(cudaStreamSynchronize(s));
   for (int i = 0; i < mp.nu; ++i) action_host[i] = p->h_out[i];
   return NLC_OK;

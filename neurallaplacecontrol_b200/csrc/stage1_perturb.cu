@@ -12,6 +12,7 @@ struct PerturbArgs {
   nlc_mppi_params p;
   const float* U_prev; float* U_cur; int roll;
   const float* noise_in; uint32_t seed_lo, seed_hi, call_lo, call_hi;
+  const unsigned long long* call_ptr;  // when set, the call index is read from device memory (graph-captured planner steps)
   const float* action_buffer;
   float* perturbed; float* noise; float* hist; float* actions; float* pert_cost;
 };
@@ -19,8 +20,8 @@ struct PerturbArgs {
 // Standard normals for (global sample, t): Philox4x32-10, counter = (idx_lo, idx_hi, call_lo, call_hi)
 // with idx = global_k*T + t, key = seed; Box-Muller on (x0,x1) and (x2,x3).  oracle/philox.py is the
 // numpy statement of the same generator.
-__device__ __forceinline__ void philox_normals(uint64_t idx, const PerturbArgs& a, float z[4]) {
-  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), a.call_lo, a.call_hi};
+__device__ __forceinline__ void philox_normals(uint64_t idx, const PerturbArgs& a, uint32_t call_lo, uint32_t call_hi, float z[4]) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), call_lo, call_hi};
   philox4x32_10(c, a.seed_lo, a.seed_hi);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -41,6 +42,11 @@ __global__ void __launch_bounds__(256) perturb_kernel(PerturbArgs a) {
   const int warp_in_grid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   const float u_scale = a.p.u_scale;
+  uint32_t call_lo = a.call_lo, call_hi = a.call_hi;
+  if (a.call_ptr) {
+    const unsigned long long cv = *a.call_ptr;
+    call_lo = (uint32_t)cv; call_hi = (uint32_t)(cv >> 32);
+  }
 
   if (a.roll >= 0 && blockIdx.x == 0) {  // publish the rolled U for stage 4 (mppi_delay.py:199-200)
     for (int i = threadIdx.x; i < T * NU; i += blockDim.x) {
@@ -63,7 +69,7 @@ __global__ void __launch_bounds__(256) perturb_kernel(PerturbArgs a) {
         for (int u = 0; u < NU; ++u) nz[u] = a.noise_in[e + u];
       } else {
         float z[4];
-        philox_normals((uint64_t)gk * (uint64_t)T + (uint64_t)t, a, z);
+        philox_normals((uint64_t)gk * (uint64_t)T + (uint64_t)t, a, call_lo, call_hi, z);
 #pragma unroll
         for (int u = 0; u < NU; ++u) {
           float acc = a.p.noise_mu[u];
@@ -105,6 +111,19 @@ __global__ void __launch_bounds__(256) perturb_kernel(PerturbArgs a) {
   }
 }
 
+__global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1ull; }
+
+int launch_bump_counter(unsigned long long* ctr, cudaStream_t stream) {
+  bump_counter_kernel<<<1, 1, 0, stream>>>(ctr);
+  NLC_LAUNCH_OK("bump_counter_kernel");
+  return NLC_OK;
+}
+
+// nlc_perturb with the call index optionally taken from device memory (call_index_dev != nullptr)
+int perturb_launch(const nlc_mppi_params* p, const float* U_prev_dev, float* U_dev, int roll, const float* noise_in_dev,
+                   uint64_t seed, uint64_t call_index, const unsigned long long* call_index_dev, const float* action_buffer_dev,
+                   float* perturbed_dev, float* noise_dev, float* hist_dev, float* actions_dev, float* pert_cost_dev, void* stream);
+
 }  // namespace nlc
 
 using namespace nlc;
@@ -113,6 +132,14 @@ extern "C" int nlc_perturb(const nlc_mppi_params* p, const float* U_prev_dev, fl
                            const float* noise_in_dev, uint64_t seed, uint64_t call_index,
                            const float* action_buffer_dev, float* perturbed_dev, float* noise_dev, float* hist_dev,
                            float* actions_dev, float* pert_cost_dev, void* stream) {
+  return perturb_launch(p, U_prev_dev, U_dev, roll, noise_in_dev, seed, call_index, nullptr, action_buffer_dev, perturbed_dev,
+                        noise_dev, hist_dev, actions_dev, pert_cost_dev, stream);
+}
+
+int nlc::perturb_launch(const nlc_mppi_params* p, const float* U_prev_dev, float* U_dev, int roll, const float* noise_in_dev,
+                        uint64_t seed, uint64_t call_index, const unsigned long long* call_index_dev,
+                        const float* action_buffer_dev, float* perturbed_dev, float* noise_dev, float* hist_dev,
+                        float* actions_dev, float* pert_cost_dev, void* stream) {
   NLC_REQUIRE(p && U_prev_dev && action_buffer_dev && perturbed_dev && noise_dev && hist_dev && pert_cost_dev,
               NLC_ERR_ARG, "nlc_perturb: null pointer");
   NLC_REQUIRE(p->K >= 1 && p->T >= 1 && p->B >= 1, NLC_ERR_ARG, "nlc_perturb: K, T, B must be positive");
@@ -124,6 +151,7 @@ extern "C" int nlc_perturb(const nlc_mppi_params* p, const float* U_prev_dev, fl
   a.noise_in = noise_in_dev;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.call_lo = (uint32_t)call_index; a.call_hi = (uint32_t)(call_index >> 32);
+  a.call_ptr = call_index_dev;
   a.action_buffer = action_buffer_dev;
   a.perturbed = perturbed_dev; a.noise = noise_dev; a.hist = hist_dev; a.actions = actions_dev; a.pert_cost = pert_cost_dev;
   const int warps_per_block = 8;

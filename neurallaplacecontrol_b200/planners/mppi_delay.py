@@ -321,6 +321,11 @@ class MPPIDelay:
                 st[0].copy_(state.reshape(-1).to(device=self.d, dtype=torch.float32))
             ab = self._buf(_lib.BUF_ACTION_BUFFER, (B, self.nu))
             ab.copy_(action_buffer.reshape(B, self.nu).to(device=self.d, dtype=torch.float32))
+            if self.G == 1 and noise is None and not per_sample:
+                # fixed launch sequence on the planner's own buffers: one CUDA-graph launch (nlc_planner_step)
+                _lib.check(self._lib.nlc_planner_step(h, stream), "nlc_planner_step")
+                self._calls += 1
+                return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
             _lib.check(self._lib.nlc_planner_rollout(h, st.data_ptr(), int(per_sample), ab.data_ptr(), _lib.ptr(noise), stream),
                        "nlc_planner_rollout")
             if self.G > 1:
