@@ -270,6 +270,34 @@ def test_tc_encoder_matches_reference(env, mode, tol):
     assert relerr(outs["fp32"], outs[mode]) < tol, relerr(outs["fp32"], outs[mode])
 
 
+@pytest.mark.parametrize("env,B", [("oderl-pendulum", 2), ("oderl-pendulum", 3), ("oderl-pendulum", 8), ("oderl-cartpole", 5),
+                                   ("oderl-acrobot", 2), ("oderl-acrobot", 3), ("oderl-acrobot", 4)])
+@pytest.mark.parametrize("K,T", [(1, 1), (3, 7), (130, 1), (77, 40), (700, 13)])
+def test_tc_encoder_window_lengths_and_ragged_tiles(env, B, K, T):
+    """The tensor-core encoder's cell pipeline depends on the window length B (2 <= B, B * nu <= 8) and on how the K*T windows
+    fall into 128-window tiles (single partial tile, exactly one tile + 2, many tiles per CTA, one window): same output as
+    the fp32 CUDA-core encoder for every combination."""
+    from oracle import costs
+    from test_gpu_parity import make_model
+
+    L = _lib()
+    lib = L.load()
+    nx, nu = costs.ENV_DIMS[env]
+    m = make_model(env, calibrated=False, math_mode="tc_split3")
+    h = m.set_prediction_time(DT)
+    gen = torch.Generator().manual_seed(1000 * B + K + T)
+    hist = ((torch.rand(K, B - 1 + T, nu, generator=gen) * 2 - 1) * costs.ENV_ACT_HIGH[env]).cuda().contiguous()
+    outs = {}
+    for name in ("fp32", "tc_split3", "tc_fp16"):
+        p = torch.full((K, T, 2), float("nan"), device="cuda")
+        L.check(lib.nlc_encode_history(h, hist.data_ptr(), K, T, B, p.data_ptr(), L.MATH_MODES[name], L.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.isfinite(p).all(), name
+        outs[name] = p
+    assert relerr(outs["fp32"], outs["tc_split3"]) < 2e-5, relerr(outs["fp32"], outs["tc_split3"])
+    assert relerr(outs["fp32"], outs["tc_fp16"]) < 5e-3, relerr(outs["fp32"], outs["tc_fp16"])
+
+
 @pytest.mark.parametrize("tiles", ["1", "2"])
 @pytest.mark.parametrize("mode,tol", [("tc_split3", 1e-4), ("tc_fp16", 2e-2)])
 def test_tc_plan_cfg1(mode, tol, tiles, monkeypatch):
@@ -329,6 +357,51 @@ def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
         assert torch.isfinite(cost).all() and torch.isfinite(states).all(), name
         outs[name] = (cost, states)
     assert torch.equal(outs["auto"][0], outs["two_tiles"][0])  # the library picks the two-tile form for this size
+    for name in ("one_tile", "two_tiles"):
+        assert relerr(outs["fp32"][0], outs[name][0]) < 1e-4, (name, relerr(outs["fp32"][0], outs[name][0]))
+        assert relerr(outs["fp32"][1], outs[name][1]) < 1e-4, (name, relerr(outs["fp32"][1], outs[name][1]))
+
+
+@pytest.mark.parametrize("S", [17, 33])
+@pytest.mark.parametrize("K,T", [(1, 1), (33, 3), (300, 9)])
+def test_rollout_s_terms_and_tiny_plans(S, K, T, monkeypatch):
+    """Randomly initialised pendulum models with 17 and 33 Fourier terms (both have tensor-core instantiations; S = 33 takes
+    the two-halves L3 path when two tiles share a CTA), plans down to a single sample and a single step: the tensor-core
+    rollout in both tile forms against the fp32 CUDA-core kernel."""
+    import ctypes as C
+
+    import neurallaplacecontrol_b200 as nlc
+
+    L = _lib()
+    lib = L.load()
+    env, nx, nu, B = "oderl-pendulum", 3, 1, 4
+    torch.manual_seed(S)
+    m = nlc.NeuralLaplaceModel(nx, nu, nx, hidden_units=128, s_recon_terms=S, state_mean=np.zeros(nx), state_std=np.ones(nx),
+                               action_mean=np.array([0.0]), action_std=np.array([1.0]), normalize=True, normalize_time=True, dt=DT,
+                               device="cuda:0").double()
+    with torch.no_grad():  # keep the Fourier sum in the operating range of a trained model (cf. oracle/gen_golden.py calibrate_)
+        last = m.laplace_rep_func.linear_tanh_stack[4]
+        last.weight.mul_(0.05)
+        last.bias.mul_(0.05)
+        last.bias[nx * S:].sub_(3.0)
+    h = m.set_prediction_time(DT)
+    gen = torch.Generator().manual_seed(K * 100 + T)
+    hist = ((torch.rand(K, B - 1 + T, nu, generator=gen) * 2 - 1) * 2.0).cuda().contiguous()
+    state = (torch.tensor([-1.0, 0.0, 1.0]) + 0.05 * torch.randn(K, nx, generator=gen)).cuda().contiguous()
+    p = torch.empty(K, T, 2, device="cuda")
+    L.check(lib.nlc_encode_history(h, hist.data_ptr(), K, T, B, p.data_ptr(), L.MATH_MODES["fp32"], L.current_stream_ptr()))
+    ro = L.RolloutOpts()
+    ro.env, ro.state_constraint, ro.goal_x, ro.dynamics, ro.delay, ro.dt = L.ENV_IDS[env], 0, 0.0, 0, 0, DT
+    outs = {}
+    for name, mode, tiles in (("fp32", "fp32", "1"), ("one_tile", "tc_split3", "1"), ("two_tiles", "tc_split3", "2")):
+        monkeypatch.setenv("NLC_ROLLOUT_TILES", tiles)
+        cost = torch.full((K,), float("nan"), device="cuda")
+        states = torch.full((K, T, nx), float("nan"), device="cuda")
+        L.check(lib.nlc_rollout_cost(h, C.byref(ro), state.data_ptr(), 1, p.data_ptr(), hist.data_ptr(), None, K, T, B, nu,
+                                     cost.data_ptr(), states.data_ptr(), L.MATH_MODES[mode], L.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.isfinite(cost).all() and torch.isfinite(states).all(), name
+        outs[name] = (cost, states)
     for name in ("one_tile", "two_tiles"):
         assert relerr(outs["fp32"][0], outs[name][0]) < 1e-4, (name, relerr(outs["fp32"][0], outs[name][0]))
         assert relerr(outs["fp32"][1], outs[name][1]) < 1e-4, (name, relerr(outs["fp32"][1], outs[name][1]))
