@@ -273,7 +273,7 @@ static int launch_rollout(nlc_model_s* m, const nlc_rollout_opts* o, const float
     // below that (the step latency is then all that matters).  NLC_ROLLOUT_TILES=1|2 forces a form (read at every call:
     // the parity tests run both).
     const char* f = getenv("NLC_ROLLOUT_TILES");
-    const int tiles = (f && (f[0] == '1' || f[0] == '2')) ? f[0] - '0' : ((K + 127) / 128 > 148 ? 2 : 1);
+    const int tiles = (f && (f[0] == '1' || f[0] == '2' || f[0] == '3')) ? f[0] - '0' : ((K + 127) / 128 > 148 ? 2 : 1);
     int rc = launch_rollout_tc2(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out,
                                 math_mode == NLC_MATH_TC_SPLIT3, tiles, stream);
     if (rc != NLC_ERR_UNSUPPORTED) return rc;

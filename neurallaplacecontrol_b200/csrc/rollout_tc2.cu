@@ -35,6 +35,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "env_cost.cuh"
 #include "f32x2.cuh"
@@ -137,6 +139,37 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, 
   }
 }
 
+// The same product for a warp that lives on 32 registers (the ping-pong form's MMA warp after setmaxnreg.dec).  Not
+// inlined, so that the compiler cannot hoist the descriptors of every product of the step loop into registers (inlined,
+// that spilled 246 words under the small budget); inside, fully unrolled with the descriptors advanced by immediates
+// (a rolled loop that rebuilt them issued one MMA per ~130 clocks: the MMAs, not the epilogues, then set the step time).
+// Called by the whole (converged) warp; ONE thread chosen by elect.sync issues and commits.  With elect.sync ptxas knows
+// the region is single-threaded and moves the operands to uniform registers once; under `if (lane == 0)` it wraps every
+// UTCHMMA in a generic divergence loop (ELECT + 6 R2UR + branch): ~100-170 clocks per MMA next to busy epilogue warps.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
+template <int kSteps, bool kSplit3>
+__device__ __noinline__ void issue_gemm_ts_fn(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi_desc, uint64_t b_lo_desc, uint32_t idesc,
+                                              uint64_t* done) {
+  if (elect_one()) {
+    fence_after_sync();
+#pragma unroll
+    for (int ks = 0; ks < kSteps; ++ks) {
+      const uint64_t off = (uint64_t)(ks * 2 * kLbo >> 4);  // the start-address field counts 16-byte units
+      mma_f16_ts(d_tmem, a_tmem + 8 * ks, b_hi_desc + off, idesc, ks > 0 ? 1u : 0u);
+      if (kSplit3) {
+        mma_f16_ts(d_tmem, a_tmem + 64 + 8 * ks, b_hi_desc + off, idesc, 1u);
+        mma_f16_ts(d_tmem, a_tmem + 8 * ks, b_lo_desc + off, idesc, 1u);
+      }
+    }
+    mma_commit(done);
+  }
+  __syncwarp();
+}
+
 // Two (channel, term) pairs of the L3 epilogue.  v = (theta', phi') pre-activations (bias added, scale folded):
 //   y = tanh(theta_pre) -> theta = pi y (w_nl.py:59);   radius = tan((pi/2) sigmoid(2 phi_pre)) (w_nl.py:60-62 + sphere map,
 //   written through s = sigmoid(-2|phi_pre|) in (0, 1/2] so both tails keep relative accuracy, common.cuh:sphere_radius);
@@ -235,6 +268,75 @@ struct L3Loop {
     if constexpr (kChunk < kEnd) {
       l3_chunk<NX, S, kChunk, kCol0, kAccurate, kRcp>(tD, b3, phase, weight, delta);
       L3Loop<NX, S, kChunk + kStride, kEnd, kCol0, kAccurate, kRcp, kStride>::run(tD, b3, phase, weight, delta);
+    }
+  }
+};
+
+// Ping-pong form: the (theta, phi) columns are dealt in UNITS of 8 columns (4 pairs) - 13 chunks over 4 column groups leave
+// one group with 4 chunks and three with 3, 26 units give 7, 7, 6, 6 - and all of a thread's units of a phase are loaded
+// before the first is used (one TMEM round trip per phase instead of one per chunk).  Unit u = columns 8u .. 8u+7 of the
+// full column space, pairs 4u .. 4u+3; kBase = first unit of the half that currently sits in the D region.
+__device__ __forceinline__ void ldtm8q(uint32_t taddr, f2_t (&v)[4]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = pk2u(r[2 * i], r[2 * i + 1]);
+}
+template <int NX, int S, int kUnit, bool kAccurate, int kRcp>
+__device__ __forceinline__ void l3_unit(const f2_t (&v)[4], const float* __restrict__ b3, const float* __restrict__ phase,
+                                        const float* __restrict__ weight, float (&delta)[NX]) {
+  f2_t bb[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(b3 + 8 * kUnit + 4 * i);
+    bb[2 * i] = pk2(t.x, t.y);
+    bb[2 * i + 1] = pk2(t.z, t.w);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i += 2) {
+    const int p0 = 4 * kUnit + i, p1 = p0 + 1;
+    if (p0 < NX * S) {
+      const f2_t s0 = add2(v[i], bb[i]), s1 = add2(v[i + 1], bb[i + 1]);
+      float th0, ph0, th1, ph1;
+      upk2(s0, th0, ph0);
+      upk2(s1, th1, ph1);
+      const int ch0 = p0 / S, k0 = p0 - ch0 * S;
+      const int ch1 = (p1 < NX * S) ? p1 / S : ch0, k1 = (p1 < NX * S) ? p1 - ch1 * S : k0;
+      float t0, t1;
+      l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phase[k0], phase[k1], weight[k0], weight[k1], t0, t1);
+      delta[ch0] += t0;
+      if (p1 < NX * S) delta[ch1] += t1;
+    }
+  }
+}
+// units kFirst, kFirst + 4, ... < kEnd of one column group: at most kMaxUnits of them
+template <int NX, int S, int kFirst, int kEnd, int kBase, bool kAccurate, int kRcp>
+struct L3Units {
+  static constexpr int kCount = kFirst < kEnd ? (kEnd - kFirst + 3) / 4 : 0;
+  template <int I>
+  static __device__ __forceinline__ void load(uint32_t tD, f2_t (&v)[kCount > 0 ? kCount : 1][4]) {
+    if constexpr (I < kCount) {
+      ldtm8q(tD + 8 * (kFirst + 4 * I - kBase), v[I]);
+      load<I + 1>(tD, v);
+    }
+  }
+  template <int I>
+  static __device__ __forceinline__ void compute(const f2_t (&v)[kCount > 0 ? kCount : 1][4], const float* b3, const float* phase,
+                                                 const float* weight, float (&delta)[NX]) {
+    if constexpr (I < kCount) {
+      l3_unit<NX, S, kFirst + 4 * I, kAccurate, kRcp>(v[I], b3, phase, weight, delta);
+      compute<I + 1>(v, b3, phase, weight, delta);
+    }
+  }
+  static __device__ __forceinline__ void run(uint32_t tD, const float* b3, const float* phase, const float* weight, float (&delta)[NX]) {
+    if constexpr (kCount > 0) {
+      f2_t v[kCount][4];
+      load<0>(tD, v);
+      tmem_ld_wait();
+      compute<0>(v, b3, phase, weight, delta);
     }
   }
 };
@@ -471,6 +573,374 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
+
+// ======================================  ping-pong form  ======================================
+// Two 128-sample tiles per CTA again, but ALL 16 warps work on ONE tile's epilogue at a time and alternate between the
+// tiles phase by phase:
+//     E1x E1y  E2x E2y  E3ax E3ay  E3bx E3by  Ux Uy        (x, y = the two tiles;  U = state update + next A1)
+// Every product (M2, M3a, M3b, M1 of the next step) is issued at the end of its tile's phase and has the whole following
+// phase of the OTHER tile to complete, so the CUDA cores never wait for the tensor pipe and every SM sub-partition always
+// has its four warps in the same instruction mix.  The free-running two-group form above leaves each tile with two warps
+// per sub-partition (latency-bound epilogues: 33.5 k clocks per step of a tile pair at config 4, issue slots 40 % busy).
+//   hand-off   a dedicated MMA warp (warp 16), coupled to the 16 epilogue warps only by mbarriers: an epilogue warp
+//              arrives on ready[tile] after its TMEM stores and moves on to the other tile's phase; the MMA warp waits for the
+//              16 arrivals, issues the product and commits it to done[tile].  (tcgen05.mma issue is back-pressured by MMA
+//              execution: with one of the epilogue warps issuing - even a different one every time - that warp falls
+//              behind by the whole product and the next hand-off waits for it: 43.9 k clocks per step, nothing
+//              overlapped.)  The register file cannot hold 17 warps at 128 registers, so the CTA is launched with 20 warps at
+//              96 and re-balanced with setmaxnreg: 112 for the epilogue warps, 24 for the MMA warp's group.
+//   threads    warp w: TMEM lanes 32 (w & 3).. (its 32 samples of BOTH tiles), column group w >> 2 (32 of the 128 hidden
+//              units; chunks c = cg (mod 4) of the (theta, phi) columns).  The state of a sample is replicated in its four
+//              threads; partial ILT sums are exchanged through shared memory among the four warps of a row quarter.
+//   L3         first half N3a = min(N3t, 128) columns, second half the rest (<= 128): A 128 + D 128 columns per tile.
+template <int NX>
+struct SmemTailPP {
+  alignas(16) float b2[kH];
+  alignas(16) float b3[256];
+  float phase[kMaxS], weight[kMaxS];
+  float smean[kMaxNx], sinv[kMaxNx];
+  alignas(16) float exch[2][4][NX * kRows];  // [tile][column group][channel][row] partial ILT sums
+  alignas(8) float stage_p[2][kRows][2];     // cp.async landing slots: p_action of the next step ...
+  alignas(8) float stage_u[2][kRows][2];     // ... and the action this step applies (running cost), per tile and sample
+  alignas(8) uint64_t done[2], ready[2];
+  uint32_t tmem_base;
+};
+constexpr int kThreadsPP = kThreads + 128;    // 16 epilogue warps + the MMA warp's group (setmaxnreg works on groups of 4 warps)
+
+template <int NX, int S, bool kSplit3, int kRcp>
+__global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int Lp = NX + 2;
+  constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
+  constexpr int kChunks = N3t / 16;
+  constexpr int kChunksA = kChunks < 8 ? kChunks : 8;
+  constexpr int N3a = 16 * kChunksA, N3b = N3t - N3a;
+  static_assert(N3b <= 128 && N3t <= 256 && Lp + 1 <= 16, "tile shape");
+  unsigned char* w1_img = smem_raw;                                   // [hi | lo] 128 x 16 halves = 4 KB each
+  unsigned char* w2_img = w1_img + 2 * kH * 16 * 2;                   // [hi | lo] 32 KB each
+  unsigned char* w3_img = w2_img + 2 * kH * kH * 2;                   // [hi | lo] N3t * 256 B each
+  SmemTailPP<NX>& s = *reinterpret_cast<SmemTailPP<NX>*>(w3_img + 2 * (size_t)N3t * kH * 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.trace && blockIdx.x == 0 && lane == 0 && warp < 16) a.trace[(51 * 16 + warp) * 16 + 0] = clock64();
+  const long long cta_t0 = clock64();
+  unsigned long long cta_g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0));
+
+  {
+    const uint4* s1 = reinterpret_cast<const uint4*>(a.m.mlp2_w1);
+    uint4* d1 = reinterpret_cast<uint4*>(w1_img);
+    for (int i = tid; i < 2 * kH * 16 * 2 / 16; i += kThreadsPP) d1[i] = __ldg(s1 + i);
+    const uint4* s2 = reinterpret_cast<const uint4*>(a.m.mlp2_w2);
+    uint4* d2 = reinterpret_cast<uint4*>(w2_img);
+    for (int i = tid; i < 2 * kH * kH * 2 / 16; i += kThreadsPP) d2[i] = __ldg(s2 + i);
+    const uint4* s3 = reinterpret_cast<const uint4*>(a.m.mlp2_w3);
+    uint4* d3 = reinterpret_cast<uint4*>(w3_img);
+    for (int i = tid; i < 2 * N3t * kH * 2 / 16; i += kThreadsPP) d3[i] = __ldg(s3 + i);
+    for (int i = tid; i < kH; i += kThreadsPP) s.b2[i] = a.m.mlp2_c[i];
+    for (int i = tid; i < 256; i += kThreadsPP) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
+    for (int i = tid; i < S; i += kThreadsPP) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
+    if (tid < NX) { s.smean[tid] = a.m.state_mean[tid]; s.sinv[tid] = a.m.state_inv_std[tid]; }
+    for (int i = tid; i < 2 * kRows * 2; i += kThreadsPP) (&s.stage_u[0][0][0])[i] = 0.0f;
+    if (tid == 0) {
+      for (int g = 0; g < 2; ++g) { mbar_init(&s.done[g], 1); mbar_init(&s.ready[g], kThreads / 32); }
+      mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&s.tmem_base, kTmemCols);
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+
+  const int q = warp & 3, cg = warp >> 2;
+  const int row = 32 * q + lane;
+  const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t w1_hi = smem_u32(w1_img), w1_lo = w1_hi + kH * 16 * 2;
+  const uint32_t w2_hi = smem_u32(w2_img), w2_lo = w2_hi + kH * kH * 2;
+  const uint32_t w3_hi = smem_u32(w3_img), w3_lo = w3_hi + (uint32_t)N3t * kH * 2;
+  const uint32_t w3b_off = (uint32_t)(N3a / 8) * kSbo;
+
+  // samples of the two tile slots of this CTA: contiguous ranges, multiples of 32 rows long (except at the end of the plan)
+  const int n_slots = 2 * gridDim.x;
+  const int per_slot = ((a.K + n_slots - 1) / n_slots + 31) / 32 * 32;
+  const int n_iter = (per_slot + kRows - 1) / kRows;
+  int r_begin[2], r_end[2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    const long long b = (long long)(2 * blockIdx.x + x) * per_slot;
+    r_begin[x] = (int)(b < a.K ? b : a.K);
+    r_end[x] = (r_begin[x] + per_slot < a.K) ? r_begin[x] + per_slot : a.K;
+  }
+
+  if (warp >= 16) {
+    // =====================================  MMA warp (and the rest of its register group)  =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 16) {
+      // products in the epilogue warps' hand-off order, the two tiles strictly alternating: (M1x M1y) then per step
+      // (M2x M2y M3ax M3ay [M3bx M3by] M1x' M1y').  ONE issuing warp on purpose: with a warp per tile the two M2 products
+      // interleave on the tensor pipe and the one needed first completes last.
+      uint32_t gcount = 0;  // products so far: tile = gcount & 1, parity of its ready barrier = (gcount >> 1) & 1
+      int mstep = 0, mprod = 0;  // measurement only: the MMA warp's own timeline, second half of the trace buffer
+      auto product = [&](int x, int ev) {
+        mbar_wait_sleep(&s.ready[x], (gcount >> 1) & 1u);
+        ++gcount;
+        if (lane == 0 && a.trace && blockIdx.x == 0 && mstep < 51 && mprod < 8) a.trace[52 * 256 + mstep * 256 + 2 * mprod] = clock64();
+        __syncwarp();
+        const uint32_t tg = tmem + kGroupCols * x;
+        uint64_t* done = &s.done[x];
+        if (ev == 0) issue_gemm_ts_fn<1, kSplit3>(tg + kColD, tg + kColA, smem_desc(w1_hi, kLbo, kSbo16), smem_desc(w1_lo, kLbo, kSbo16), idesc_f16_f32(kRows, kH), done);
+        else if (ev == 1) issue_gemm_ts_fn<kH / 16, kSplit3>(tg + kColD, tg + kColA, smem_desc(w2_hi, kLbo, kSbo), smem_desc(w2_lo, kLbo, kSbo), idesc_f16_f32(kRows, kH), done);
+        else if (ev == 2) issue_gemm_ts_fn<kH / 16, kSplit3>(tg + kColD, tg + kColA, smem_desc(w3_hi, kLbo, kSbo), smem_desc(w3_lo, kLbo, kSbo), idesc_f16_f32(kRows, N3a), done);
+        else issue_gemm_ts_fn<kH / 16, kSplit3>(tg + kColD, tg + kColA, smem_desc(w3_hi + w3b_off, kLbo, kSbo), smem_desc(w3_lo + w3b_off, kLbo, kSbo),
+                                                idesc_f16_f32(kRows, N3b > 0 ? N3b : 16), done);
+        if (lane == 0 && a.trace && blockIdx.x == 0 && mstep < 51 && mprod < 8) a.trace[52 * 256 + mstep * 256 + 2 * mprod + 1] = clock64();
+        ++mprod;
+      };
+      constexpr int kPerStep = N3b > 0 ? 8 : 6;
+#pragma unroll 1
+      for (int it = 0; it < n_iter; ++it) {
+        const int n_products = kPerStep * a.T;   // 2 + kPerStep T - 2: no M1 pair after the last step
+#pragma unroll 1
+        for (int i = 0; i < n_products; ++i) {
+          const int j = i < 2 ? i : (i - 2) % kPerStep;  // position inside the prologue / the step
+          const int ev = i < 2 ? 0 : ((j >> 1) + 1 == kPerStep / 2 ? 0 : (j >> 1) + 1);
+          if (i >= 2 && j == 0) { ++mstep; mprod = 0; }
+          product(i & 1, ev);
+        }
+      }
+    }
+  } else {
+  // =====================================  epilogue warps  =====================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+  // The tile loops below are NOT unrolled (`x` is a run-time value; per-tile register state is reached through selects):
+  // unrolled, the step loop was 166 KB of instructions, more than the SM's instruction cache holds - CTAs then ran
+  // 14-20 % slower the further their TPC sits from the GPC's instruction path (tools/trace_rollout_pp.py, per-CTA spans).
+  int tstep = 0;
+  // measurement only (tools/trace_rollout_pp.py): clock64 timeline of CTA 0, [step < 51][warp][16 events]
+  auto mark = [&](int ev) {
+    if (a.trace && blockIdx.x == 0 && lane == 0 && tstep < 51) a.trace[(tstep * 16 + warp) * 16 + ev] = clock64();
+  };
+  if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[(51 * 16 + warp) * 16 + 1] = clock64();
+  uint32_t nphase = 0;  // products of each tile waited for so far (the two tiles wait once each per phase)
+  // this warp's TMEM stores / loads of the phase are done: the MMA warp issues tile x's next product after all 16 arrivals
+  auto handoff = [&](int x) {
+    tmem_st_wait();
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.ready[x]);
+  };
+  auto wait_mma = [&](int x) {
+    mbar_wait_sleep(&s.done[x], nphase & 1u);
+    fence_after_sync();
+  };
+
+  for (int it = 0; it < n_iter; ++it) {
+    // per-tile state: sample index, liveness bits (bit x), state and cost accumulator of both tiles
+    int kk0, kk1, amask = 0, lmask = 0;
+    float st0[NX], st1[NX], cost0 = 0.0f, cost1 = 0.0f;
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int tile0 = r_begin[x] + it * kRows;
+      int nr = r_end[x] - tile0;
+      nr = nr < 0 ? 0 : (nr > kRows ? kRows : nr);
+      if (32 * q < nr) amask |= 1 << x;     // warp-uniform: this warp has at least one live sample of tile x
+      if (row < nr) lmask |= 1 << x;
+      const int k = row < nr ? tile0 + row : r_end[x] - 1;
+      const float* sp = a.state0 + (size_t)(a.state_per_sample ? k / a.state_per_sample : 0) * NX;
+#pragma unroll
+      for (int c = 0; c < NX; ++c) { if (x == 0) st0[c] = sp[c]; else st1[c] = sp[c]; }
+      if (x == 0) kk0 = k; else kk1 = k;
+      if (cg == 2) *reinterpret_cast<float2*>(&s.stage_p[x][row][0]) = *reinterpret_cast<const float2*>(a.p + ((size_t)k * a.T) * 2);
+    }
+    // A1 = [obs_n | p_action | 1 | 0..] as the K = 16 operand of the first layer (one thread per sample: column group 2);
+    // p_action comes from this thread's own stage_p slot
+    auto write_a1 = [&](int x, const float (&stx)[NX]) {
+      if (cg == 2 && ((amask >> x) & 1)) {
+        float in[Lp];
+#pragma unroll
+        for (int c = 0; c < NX; ++c) in[c] = (stx[c] - s.smean[c]) * s.sinv[c];
+        const float2 pc = *reinterpret_cast<const float2*>(&s.stage_p[x][row][0]);
+        in[NX] = pc.x; in[NX + 1] = pc.y;
+        f2_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x0 = (2 * i < Lp) ? in[2 * i < Lp ? 2 * i : 0] : (2 * i == Lp ? 1.0f : 0.0f);
+          const float x1 = (2 * i + 1 < Lp) ? in[2 * i + 1 < Lp ? 2 * i + 1 : 0] : (2 * i + 1 == Lp ? 1.0f : 0.0f);
+          v[i] = pk2(x0, x1);
+        }
+        uint32_t ph[8], pl[8];
+        pack16<kSplit3>(v, ph, pl);
+        const uint32_t tA = tlane + kGroupCols * x + kColA;
+        tmem_st8(tA, ph);
+        if (kSplit3) tmem_st8(tA + 64, pl);
+      }
+    };
+    // hidden layer epilogue: (+ bias,) tanh, re-written as the fp16 hi/lo A operand of the next layer
+    auto hidden = [&](int x, bool with_bias) {
+      const uint32_t tA = tlane + kGroupCols * x + kColA, tD = tlane + kGroupCols * x + kColD;
+      if ((amask >> x) & 1) {
+        f2_t vv[2][8];
+        ldtm16p(tD + 32 * cg, vv[0]);
+        ldtm16p(tD + 32 * cg + 16, vv[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+          const int n0 = 32 * cg + 16 * c16;
+          f2_t (&v)[8] = vv[c16];
+          if (with_bias) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b = *reinterpret_cast<const float4*>(s.b2 + n0 + 4 * i);
+              v[2 * i] = add2(v[2 * i], pk2(b.x, b.y));
+              v[2 * i + 1] = add2(v[2 * i + 1], pk2(b.z, b.w));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = tanh2_scaled<kSplit3, kRcp / 10>(v[i]);
+          uint32_t ph[8], pl[8];
+          pack16<kSplit3>(v, ph, pl);
+          tmem_st8(tA + n0 / 2, ph);
+          if (kSplit3) tmem_st8(tA + 64 + n0 / 2, pl);
+        }
+      }
+    };
+    // first (kHalf == 0) or second half of the (theta, phi) columns: this thread's units -> partial sums in shared memory
+    auto l3_half = [&](int x, auto half_tag) {
+      constexpr int kHalf = decltype(half_tag)::value;
+      constexpr int kBeg = kHalf == 0 ? 0 : kChunksA, kEnd = kHalf == 0 ? kChunksA : kChunks;
+      const uint32_t tD = tlane + kGroupCols * x + kColD;
+      float delta[NX];
+#pragma unroll
+      for (int c = 0; c < NX; ++c) delta[c] = 0.0f;
+      if ((amask >> x) & 1) {
+        // unit u of this half belongs to column group (u - first unit of the half) mod 4
+        constexpr int kU0 = 2 * kBeg, kU1 = 2 * kEnd;
+        if (cg == 0) L3Units<NX, S, kU0 + 0, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+        else if (cg == 1) L3Units<NX, S, kU0 + 1, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+        else if (cg == 2) L3Units<NX, S, kU0 + 2, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+        else L3Units<NX, S, kU0 + 3, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+      }
+      float* e = &s.exch[x][cg][row];
+#pragma unroll
+      for (int c = 0; c < NX; ++c) e[c * kRows] = (kHalf == 0) ? delta[c] : e[c * kRows] + delta[c];
+    };
+
+    write_a1(0, st0); handoff(0);
+    write_a1(1, st1); handoff(1);
+
+    for (int t = 0; t < a.T; ++t) {
+      // operands of the END of this step - the next step's p_action (column group 2) and the action this step applies, for
+      // the running cost (column group 3) - start their way now as cp.async copies into per-sample shared-memory slots:
+      // no registers held across the step (held in registers they were spilled right after the load, and the spill
+      // store stalled the warp on the load at the top of every step)
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x) {
+        const int kx = x ? kk1 : kk0;
+        if (cg == 2 && t + 1 < a.T)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.stage_p[x][row][0])), "l"(a.p + ((size_t)kx * a.T + t + 1) * 2) : "memory");
+        if (cg == 3 && ((lmask >> x) & 1) && a.cost_total) {
+          const float* up = a.hist + ((size_t)kx * a.L + t + a.B - 1) * a.nu;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s.stage_u[x][row][0])), "l"(up) : "memory");
+          if (a.nu > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s.stage_u[x][row][1])), "l"(up + 1) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      mark(11);
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x) { wait_mma(x); mark(0 + x); hidden(x, false); handoff(x); }   // E1 -> M2
+      ++nphase;
+      mark(12);
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x) { wait_mma(x); mark(2 + x); hidden(x, true); handoff(x); }    // E2 -> M3a
+      ++nphase;
+      mark(13);
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x) {                                                             // E3a (-> M3b)
+        wait_mma(x);
+        mark(4 + x);
+        l3_half(x, std::integral_constant<int, 0>());
+        if (N3b > 0) handoff(x);
+      }
+      ++nphase;
+      if (N3b > 0) {
+        mark(14);
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x) { wait_mma(x); mark(6 + x); l3_half(x, std::integral_constant<int, 1>()); }  // E3b
+        ++nphase;
+      }
+      mark(15);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's own copies: it reads only its own slots
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x) {                                                   // U: residual, cost, next A1 -> M1
+        asm volatile("bar.sync %0, %1;" ::"r"(5 + 4 * x + q), "n"(128) : "memory");
+        mark(8 + x);
+        const int kx = x ? kk1 : kk0;
+        const bool lv = (lmask >> x) & 1;
+        // every thread of a sample adds the partials in the same order: the replicated state stays bit-identical
+        float stx[NX];
+#pragma unroll
+        for (int c = 0; c < NX; ++c) {
+          const float* e = &s.exch[x][0][c * kRows + row];
+          const float d = ((e[0] + e[NX * kRows]) + e[2 * NX * kRows]) + e[3 * NX * kRows];
+          stx[c] = (x ? st1[c] : st0[c]) + d;                     // mppi_with_model.py:121
+          if (x) st1[c] = stx[c]; else st0[c] = stx[c];
+          if (cg == 2 && lv) {
+            if (a.states) a.states[((size_t)kx * a.T + t) * NX + c] = stx[c];
+            if (a.delta_out) a.delta_out[(size_t)kx * NX + c] = d;
+          }
+        }
+        // running cost of the new state with the action just applied (mppi_delay.py:288-290)
+        if (cg == 3 && lv && a.cost_total) {
+          const float2 uv = *reinterpret_cast<const float2*>(&s.stage_u[x][row][0]);
+          const float uc[2] = {uv.x, uv.y};   // zero-padded for nu == 1: a static count keeps the action in registers
+          const float c = env_running_cost_fast(a.o, stx, uc, 2);
+          if (x) cost1 += c; else cost0 += c;
+        }
+        if (t + 1 < a.T) {
+          write_a1(x, stx);
+          handoff(x);
+        }
+      }
+      mark(10);
+      ++tstep;
+    }
+    if (cg == 3 && a.cost_total) {
+      if (lmask & 1) a.cost_total[kk0] = cost0 + (a.pert_cost ? a.pert_cost[kk0] : 0.0f);
+      if (lmask & 2) a.cost_total[kk1] = cost1 + (a.pert_cost ? a.pert_cost[kk1] : 0.0f);
+    }
+  }
+  if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[(51 * 16 + warp) * 16 + 2] = clock64();
+  }  // epilogue warps
+  fence_before_sync();
+  __syncthreads();
+  if (a.trace && tid == 0) {  // measurement only: every CTA's own span and SM
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    a.trace[2 * 52 * 256 + 4 * blockIdx.x] = clock64() - cta_t0;
+    a.trace[2 * 52 * 256 + 4 * blockIdx.x + 1] = smid;
+    a.trace[2 * 52 * 256 + 4 * blockIdx.x + 2] = (long long)cta_g0;
+    a.trace[2 * 52 * 256 + 4 * blockIdx.x + 3] = (long long)g1;
+  }
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int NX, int S, bool kSplit3, int kRcp>
+static int launch_pp(const Args& a, cudaStream_t stream) {
+  constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
+  const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3t * kH * 2 + sizeof(SmemTailPP<NX>) + 128;
+  NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
+  auto kern = rollout_pp_kernel<NX, S, kSplit3, kRcp>;
+  NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (a.K + 63) / 64;   // at least one warp of samples per tile slot, at most one CTA per SM
+  if (grid > 148) grid = 148;
+  kern<<<grid, kThreadsPP, smem, stream>>>(a);
+  NLC_LAUNCH_OK("rollout_pp_kernel");
+  return NLC_OK;
+}
+
 template <int NX, int S, bool kSplit3, int kRcp, int kTiles>
 static int launch_one_t(const Args& a, cudaStream_t stream) {
   constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
@@ -489,6 +959,7 @@ static int launch_one_t(const Args& a, cudaStream_t stream) {
 // two tiles per CTA once the plan is more than one wave of 128-sample tiles, else one tile on all 16 warps
 template <int NX, int S, bool kSplit3, int kRcp>
 static int launch_one(const Args& a, int tiles, cudaStream_t stream) {
+  if (tiles == 3) return launch_pp<NX, S, kSplit3, kRcp>(a, stream);
   return tiles == 1 ? launch_one_t<NX, S, kSplit3, kRcp, 1>(a, stream) : launch_one_t<NX, S, kSplit3, kRcp, 2>(a, stream);
 }
 
@@ -505,16 +976,13 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
   a.trace = g_roll_trace;
-  // reciprocal flavour of the fp32-class epilogues: 3 = Newton on the FMA pipe (default: 1.71 ms at config 4),
-  // 0 = MUFU.RCP (1.85 ms: shorter chains, but the MUFU pipe is the scarcer one).  NLC_ROLLOUT_RCP is a measurement knob.
-  static const int rcp = [] { const char* e = getenv("NLC_ROLLOUT_RCP"); return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 33; }();
-#define NLC_RT2_CASE(NX_, S_)                                                                                   \
-  if (m->nx == NX_ && m->S == S_) {                                                                             \
-    if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, tiles_per_cta, stream);  /* digits: (MLP tanh, L3 pair) reciprocal flavour */                                          \
-    if (rcp == 0) return rt2::launch_one<NX_, S_, true, 0>(a, tiles_per_cta, stream);                                          \
-    if (rcp == 3) return rt2::launch_one<NX_, S_, true, 3>(a, tiles_per_cta, stream);                                          \
-    if (rcp == 30) return rt2::launch_one<NX_, S_, true, 30>(a, tiles_per_cta, stream);                                        \
-    return rt2::launch_one<NX_, S_, true, 33>(a, tiles_per_cta, stream);                                                       \
+  // reciprocal flavour of the fp32-class epilogues: Newton on the FMA pipe for both the MLP tanh and the L3 pair ("33":
+  // 1.71 ms at config 4; MUFU.RCP "00": 1.85 ms - shorter chains, but the MUFU pipe is the scarcer one; measured with the
+  // two-group form, profiles/r1_rollout_sweep.md)
+#define NLC_RT2_CASE(NX_, S_)                                                                \
+  if (m->nx == NX_ && m->S == S_) {                                                          \
+    if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, tiles_per_cta, stream);        \
+    return rt2::launch_one<NX_, S_, true, 33>(a, tiles_per_cta, stream);                     \
   }
   NLC_RT2_CASE(3, 17)
   NLC_RT2_CASE(5, 17)

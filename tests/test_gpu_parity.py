@@ -126,14 +126,14 @@ def test_plan_matches_reference(env, case):
     _check_plan(env, case)
 
 
-@pytest.mark.parametrize("form", ["two_tiles", "one_tile"])
+@pytest.mark.parametrize("form", ["two_tiles", "one_tile", "ping_pong"])
 @pytest.mark.parametrize("env", ENVS)
 @pytest.mark.parametrize("case", ["raw", "cal_calls1", "cal_calls2", "cal_stateK"])
 def test_plan_matches_reference_tensor_core_split3(env, case, form, monkeypatch):
     """Same golden plans through the tcgen05 encoder + tcgen05 rollout in fp16 hi/lo split-3 mode: holds the SAME 1e-4
     bound as the fp32 path.  Both forms of the rollout kernel are forced in turn (the library picks by plan size):
     rollout_tc2.cu with two tiles or one tile per CTA."""
-    monkeypatch.setenv("NLC_ROLLOUT_TILES", "2" if form == "two_tiles" else "1")
+    monkeypatch.setenv("NLC_ROLLOUT_TILES", {"two_tiles": "2", "one_tile": "1", "ping_pong": "3"}[form])
     # The exploding raw-weight case (|delta state| ~ 1e2 per step) amplifies the 22-bit operand split to 1.1-1.4e-4 on the
     # states (fp32 path: < 1e-4); its bound is 3e-4.  The calibrated (trained-model-like) cases hold 1e-4.
     _check_plan(env, case, tol_scale=3.0 if case == "raw" else 1.0, math_mode="tc_split3")

@@ -298,7 +298,7 @@ def test_tc_encoder_window_lengths_and_ragged_tiles(env, B, K, T):
     assert relerr(outs["fp32"], outs["tc_fp16"]) < 5e-3, relerr(outs["fp32"], outs["tc_fp16"])
 
 
-@pytest.mark.parametrize("tiles", ["1", "2"])
+@pytest.mark.parametrize("tiles", ["1", "2", "3"])
 @pytest.mark.parametrize("mode,tol", [("tc_split3", 1e-4), ("tc_fp16", 2e-2)])
 def test_tc_plan_cfg1(mode, tol, tiles, monkeypatch):
     """BASELINE config 1 end to end with the tensor-core encoder and either form of the tensor-core rollout.  tc_split3
@@ -344,7 +344,8 @@ def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
     ro = L.RolloutOpts()
     ro.env, ro.state_constraint, ro.goal_x, ro.dynamics, ro.delay, ro.dt = L.ENV_IDS[env], 0, 0.0, 0, 0, DT
     outs = {}
-    for name, mode, tiles in (("fp32", "fp32", "1"), ("two_tiles", "tc_split3", "2"), ("one_tile", "tc_split3", "1"), ("auto", "tc_split3", "")):
+    for name, mode, tiles in (("fp32", "fp32", "1"), ("two_tiles", "tc_split3", "2"), ("one_tile", "tc_split3", "1"), ("ping_pong", "tc_split3", "3"),
+                              ("auto", "tc_split3", "")):
         if tiles:
             monkeypatch.setenv("NLC_ROLLOUT_TILES", tiles)
         else:
@@ -357,7 +358,7 @@ def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
         assert torch.isfinite(cost).all() and torch.isfinite(states).all(), name
         outs[name] = (cost, states)
     assert torch.equal(outs["auto"][0], outs["two_tiles"][0])  # the library picks the two-tile form for this size
-    for name in ("one_tile", "two_tiles"):
+    for name in ("one_tile", "two_tiles", "ping_pong"):
         assert relerr(outs["fp32"][0], outs[name][0]) < 1e-4, (name, relerr(outs["fp32"][0], outs[name][0]))
         assert relerr(outs["fp32"][1], outs[name][1]) < 1e-4, (name, relerr(outs["fp32"][1], outs[name][1]))
 
@@ -393,7 +394,7 @@ def test_rollout_s_terms_and_tiny_plans(S, K, T, monkeypatch):
     ro = L.RolloutOpts()
     ro.env, ro.state_constraint, ro.goal_x, ro.dynamics, ro.delay, ro.dt = L.ENV_IDS[env], 0, 0.0, 0, 0, DT
     outs = {}
-    for name, mode, tiles in (("fp32", "fp32", "1"), ("one_tile", "tc_split3", "1"), ("two_tiles", "tc_split3", "2")):
+    for name, mode, tiles in (("fp32", "fp32", "1"), ("one_tile", "tc_split3", "1"), ("two_tiles", "tc_split3", "2"), ("ping_pong", "tc_split3", "3")):
         monkeypatch.setenv("NLC_ROLLOUT_TILES", tiles)
         cost = torch.full((K,), float("nan"), device="cuda")
         states = torch.full((K, T, nx), float("nan"), device="cuda")
@@ -402,7 +403,7 @@ def test_rollout_s_terms_and_tiny_plans(S, K, T, monkeypatch):
         torch.cuda.synchronize()
         assert torch.isfinite(cost).all() and torch.isfinite(states).all(), name
         outs[name] = (cost, states)
-    for name in ("one_tile", "two_tiles"):
+    for name in ("one_tile", "two_tiles", "ping_pong"):
         assert relerr(outs["fp32"][0], outs[name][0]) < 1e-4, (name, relerr(outs["fp32"][0], outs[name][0]))
         assert relerr(outs["fp32"][1], outs[name][1]) < 1e-4, (name, relerr(outs["fp32"][1], outs[name][1]))
 
