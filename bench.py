@@ -295,8 +295,8 @@ def run_gpu(args, env, K, H, desc):
         e2e = steps_per_plan / (ms_e2e * 1e-3)
         enc_flop = ENCODER_FLOP * Kl * H
         roll_flop = (HOISTED_FLOP[env] - ENCODER_FLOP) * Kl * H
-        two_tiles = (Kl + 127) // 128 > 148  # the library's own choice: two 128-sample tiles per CTA beyond one wave
-        roll_name = "rollout_nl_kernel" if args.math == "fp32" else "rollout_tc2_kernel"
+        two_tiles = (Kl + 127) // 128 > 148  # the library's own choice: the ping-pong form (two tiles per CTA) beyond one wave
+        roll_name = "rollout_nl_kernel" if args.math == "fp32" else ("rollout_pp_kernel" if two_tiles else "rollout_tc2_kernel")
         kernels = {"encoder": {"name": "encode_gru_kernel" if args.math == "fp32" else "encode_tc2_kernel", "ms": ms_enc, "flop": enc_flop},
                    "rollout": {"name": roll_name, "ms": ms_roll, "flop": roll_flop}}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
@@ -311,7 +311,7 @@ def run_gpu(args, env, K, H, desc):
         achieved = kernels[dom]["tflops"]
         # secondary roofline: transcendental (MUFU / XU pipe) throughput.  Counts per rollout-step from the kernels' code:
         # encoder 8 GRU cells x 64 units x (3 ex2 + 1 rcp; the (r,z) reciprocal is a Newton iteration on the FMA pipe) =
-        # 2048 (3 tanh.approx in tc_fp16); two-tile rollout 2 x 128 tanh (1 ex2 each) + nx*S pairs x (2 ex2 + cos + rcp);
+        # 2048 (3 tanh.approx in tc_fp16); rollout 2 x 128 tanh (1 ex2 each) + nx*S pairs x (2 ex2 + cos + rcp);
         # Peak: 16 /clk/SM measured by tools/mufu_bench.cu (15.9) x 148 SMs x the
         # SM clock seen during the run.
         if args.math != "fp32":
@@ -332,7 +332,7 @@ def run_gpu(args, env, K, H, desc):
             "ms_per_step": ms_dev, "plan_latency_ms": ms_dev, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "env": env, "K": K, "H": H, "S": inp["S"], "hidden": 128, "history_window": B,
-                       "parallelism": f"K-sharded x{world}", "K_per_gpu": K // world, "rollout_tiles_per_cta": 2 if two_tiles else 1, "math": args.math, "noise": "on-device Philox4x32-10",
+                       "parallelism": f"K-sharded x{world}", "K_per_gpu": K // world, "rollout_form": "ping-pong, 2 tiles per CTA" if two_tiles else "1 tile per CTA", "math": args.math, "noise": "on-device Philox4x32-10",
                        "l2": "flushed between timed steps (256 MiB fill)", "keep_states": True},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 4 * (nx + B * nu),
@@ -345,8 +345,9 @@ def run_gpu(args, env, K, H, desc):
                          "kernel_ms": kernels[dom]["ms"], "flop_per_launch": kernels[dom]["flop"], "kernels": kernels,
                          "note": "frac = algorithmic (hoisted) FLOPs per launch / CUDA-event time / measured sustained bf16 tensor "
                                  "TFLOP/s.  tc_split3 issues 3 fp16 MMAs per algorithmic product (fp32-class result), so frac <= 1/3 "
-                                 "by construction; issued_frac counts the MMA FLOPs the tensor pipe executes against the same peak; both kernels are bound by their CUDA-core gate / sphere-map "
-                                 "epilogues (MUFU + issue), not by the MMAs (see profiles/ and DESIGN.md 3).",
+                                 "by construction; issued_frac counts the MMA FLOPs the tensor pipe executes against the same peak.  The encoder alternates a "
+                                 "tensor-bound phase (the 25-MMA layer-1 burst) with a gate-epilogue-bound one, the rollout is bound by its CUDA-core "
+                                 "epilogues (MUFU + issue + phase hand-offs): see profiles/ and DESIGN.md 3.",
                          "whole_step_achieved": HOISTED_FLOP[env] * steps_per_plan / (ms_dev * 1e-3) / 1e12},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -54,7 +54,6 @@ struct Args {
   const float* hist;
   float* p_out;
   int K, T, B, L, hist_ch;
-  int ablate;  // measurement only (NLC_ENC_ABLATE): 1 no MMA issue, 8 no gate math
   long long rows;
   long long* trace;  // measurement only: clock64 timeline of CTA 0, [step][warp][8 events]
   ModelDev m;
@@ -153,6 +152,7 @@ __device__ __forceinline__ void issue_gemm192(uint32_t d_tmem, uint32_t a_hi, ui
 }
 
 constexpr int kThreadsAll = kThreads + 32;        // 16 epilogue warps + the MMA warp
+constexpr int kBarH0 = 2, kBarH1 = 3;             // named barriers: layer-0 / layer-1 operands published (1: output exchange)
 // Layer 0's input projection and biases ride on the tensor cores as one extra K block of the layer-0 state operand:
 //   A block (per window)  [x0_hi x0_lo x0_hi | x1_hi x1_lo x1_hi | 1 1 | 0 ...]      (16 halves)
 //   B block (per column)  [W0_hi W0_hi W0_lo | W1_hi W1_hi W1_lo | b_hi b_lo | 0 ...]
@@ -174,7 +174,7 @@ struct Smem {
   alignas(128) unsigned char h1[2][kOpBytes];
   alignas(16) float c[kC2Count];
   alignas(16) float pout[3][kRows * 2];
-  alignas(8) uint64_t bar_a, bar_b, h0_ready, h1_ready;
+  alignas(8) uint64_t bar_a, bar_b;
   uint32_t tmem_base;
 };
 
@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   const int row = 32 * q + lane;   // window within the tile == TMEM lane
   const int ubase = 16 * grp;      // first of the 16 hidden units (per layer) this thread owns
   const int B = a.B;
-  const int abl = a.ablate;
   int tstep = 0;
   auto mark = [&](int ev) {
     if (a.trace && blockIdx.x == 0 && lane == 0 && tstep < 32) a.trace[(tstep * 16 + warp) * 8 + ev] = clock64();
@@ -208,7 +207,6 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     if (tid < 2) s.c[kC2Bout + tid] = a.m.enc2_c[kE2Bout + tid];
     if (tid == 0) {
       mbar_init(&s.bar_a, 1); mbar_init(&s.bar_b, 1);
-      mbar_init(&s.h0_ready, kThreads / 32); mbar_init(&s.h1_ready, kThreads / 32);  // one arrival per epilogue warp
       mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&s.tmem_base, kTmemCols);
@@ -233,48 +231,51 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     // =====================================  MMA warp  =====================================
     // mirrors the epilogue warps' publication order: h0 + the next cell's [x | 1] block (-> layer-0 product of the next
     // cell), then h1 / D1 re-armed (-> layer-1 product of the next cell: input part from h0, hidden part from h1)
-    uint32_t n_h0 = 0, n_h1 = 0;
+    // "operand published" hand-offs are NAMED barriers (epilogue warps bar.arrive, this warp bar.sync): as mbarriers, each of
+    // the 16 arrivals woke every warp sleeping in a try_wait loop (this one, and epilogue warps waiting for a commit) for
+    // another SYNCS / NANOSLEEP / BRA round - 12 % of all executed instructions in the ncu source view.  An epilogue warp
+    // cannot arrive twice in one generation: its next arrival on the same barrier lies behind a wait for a product that
+    // this warp issues only after the generation has completed.
+    auto wait_ready = [&](int id) {
+      asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreadsAll) : "memory");
+    };
     auto issue_a = [&](bool with_hidden) {
-      if (lane == 0) {
+      if (elect_one()) {
         fence_after_sync();
-        if (!(abl & 1)) {
-          mma_f16_ss(tmem + kColD0, smem_desc(a_h0_hi + 8 * kLbo, kLbo, kSboX), smem_desc(w_x0, kLbo, 128), idesc_f16_f32(kRows, 256), 0u);
-          if (with_hidden) issue_gemm192<kSplit3>(tmem + kColD0, a_h0_hi, kSboX, a_h0_lo, kSbo, w_hh0_hi, w_hh0_lo);
-        }
+        mma_f16_ss(tmem + kColD0, smem_desc(a_h0_hi + 8 * kLbo, kLbo, kSboX), smem_desc(w_x0, kLbo, 128), idesc_f16_f32(kRows, 256), 0u);
+        if (with_hidden) issue_gemm192<kSplit3>(tmem + kColD0, a_h0_hi, kSboX, a_h0_lo, kSbo, w_hh0_hi, w_hh0_lo);
         mma_commit(&s.bar_a);
       }
       __syncwarp();
     };
     auto issue_b = [&](bool with_h1) {
-      if (lane == 0) {
+      if (elect_one()) {
         fence_after_sync();
-        if (!(abl & 1)) {
-          // biases first (accumulate = 0 over all of D1 = [in | r | z | hn]): the 1-columns of the [x | 1] block
-          mma_f16_ss(tmem + kColD1, smem_desc(a_h0_hi + 8 * kLbo, kLbo, kSboX), smem_desc(w_x1, kLbo, 128), idesc_f16_f32(kRows, 256), 0u);
-          issue_gemm192<kSplit3>(tmem + kColD1, a_h0_hi, kSboX, a_h0_lo, kSbo, w_ih1_hi, w_ih1_lo);
-          if (with_h1) issue_gemm192<kSplit3>(tmem + kColD1 + 64, a_h1_hi, kSbo, a_h1_lo, kSbo, w_hh1_hi, w_hh1_lo);
-        }
+        // biases first (accumulate = 0 over all of D1 = [in | r | z | hn]): the 1-columns of the [x | 1] block
+        mma_f16_ss(tmem + kColD1, smem_desc(a_h0_hi + 8 * kLbo, kLbo, kSboX), smem_desc(w_x1, kLbo, 128), idesc_f16_f32(kRows, 256), 0u);
+        issue_gemm192<kSplit3>(tmem + kColD1, a_h0_hi, kSboX, a_h0_lo, kSbo, w_ih1_hi, w_ih1_lo);
+        if (with_h1) issue_gemm192<kSplit3>(tmem + kColD1 + 64, a_h1_hi, kSbo, a_h1_lo, kSbo, w_hh1_hi, w_hh1_lo);
         mma_commit(&s.bar_b);
       }
       __syncwarp();
     };
     if ((long long)blockIdx.x < n_tiles) {
-      mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;  // [x(0) | 1]
+      wait_ready(kBarH0);  // [x(0) | 1]
       issue_a(false);
-      mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;  // h0(0), [x(1) | 1]
+      wait_ready(kBarH0);  // h0(0), [x(1) | 1]
       issue_a(true);
-      mbar_wait_sleep(&s.h1_ready, n_h1 & 1); ++n_h1;
+      wait_ready(kBarH1);
       issue_b(false);
     }
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const bool has_next = tile + gridDim.x < n_tiles;
       for (int st = 0; st < B; ++st) {
         if (st + 1 < B || has_next) {
-          mbar_wait_sleep(&s.h0_ready, n_h0 & 1); ++n_h0;
+          wait_ready(kBarH0);
           if (st + 2 < B || st + 1 == B) issue_a(true);   // next cell of this tile, or cell 1 of the next tile
           else if (has_next) issue_a(false);              // st + 2 == B: cell 0 of the next tile (zero state)
         }
-        mbar_wait_sleep(&s.h1_ready, n_h1 & 1); ++n_h1;
+        wait_ready(kBarH1);
         if (st + 1 < B) issue_b(true);
         else if (has_next) issue_b(false);
       }
@@ -342,8 +343,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (abl & 8) h0r[4 * c + i] = add2(add2(gr[i], gz[i]), add2(gn[i], gh[i]));
-        else h0r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], from_zero ? 0ull : h0r[4 * c + i]);
+        h0r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], from_zero ? 0ull : h0r[4 * c + i]);
       }
     }
   };
@@ -359,8 +359,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     if (with_x) write_x();
     fence_proxy_async_smem();
     fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s.h0_ready);
+    asm volatile("bar.arrive %0, %1;" ::"r"(kBarH0), "n"(kThreadsAll) : "memory");
   };
   // after the layer-1 epilogue: D1 read (and h1 stored when `with_h1`)
   auto publish_h1 = [&](bool with_h1) {
@@ -373,8 +372,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       fence_proxy_async_smem();
     }
     fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s.h1_ready);
+    asm volatile("bar.arrive %0, %1;" ::"r"(kBarH1), "n"(kThreadsAll) : "memory");
   };
 
   // ---- head of the first tile: layer-0 cell 0 (zero state: the [x | 1] product alone), then A(1) and the input part of B(0) ----
@@ -428,8 +426,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (abl & 8) h1r[4 * c + i] = add2(add2(gr[i], gz[i]), add2(gn[i], gh[i]));
-          else h1r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], st > 0 ? h1r[4 * c + i] : 0ull);
+          h1r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], st > 0 ? h1r[4 * c + i] : 0ull);
         }
       }
       mark(5);
@@ -491,7 +488,6 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   a.rows = (long long)K * T;
   a.m = m->d;
   a.trace = g_enc_trace;
-  { const char* e = getenv("NLC_ENC_ABLATE"); a.ablate = e ? atoi(e) : 0; }
   const int smem = (int)sizeof(Smem) + 128;
   // fp32-class mode: Newton (3 steps) for the (r, z) reciprocal, MUFU for n  (pipe_bench "v3");
   // single-pass fp16 mode: three tanh.approx per unit (that mode's accuracy class, 2e-2 bound).

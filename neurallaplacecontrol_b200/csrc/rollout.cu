@@ -269,11 +269,12 @@ static int launch_rollout(nlc_model_s* m, const nlc_rollout_opts* o, const float
                           const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
                           float* delta_out, int math_mode, cudaStream_t stream) {
   if (math_mode != NLC_MATH_FP32 && 2 * m->nx * m->S <= 256) {
-    // rollout_tc2.cu: two tiles per CTA once the plan is more than one wave of 128-sample tiles, one tile on all 16 warps
-    // below that (the step latency is then all that matters).  NLC_ROLLOUT_TILES=1|2 forces a form (read at every call:
-    // the parity tests run both).
+    // rollout_tc2.cu: beyond one wave of 128-sample tiles the ping-pong form (two tiles per CTA, all 16 warps alternating
+    // between them: form 3), below that one tile on all 16 warps (form 1: the step latency is then all that matters).
+    // NLC_ROLLOUT_TILES=1|2|3 forces a form (2 = two free-running 8-warp groups, the ping-pong form's predecessor);
+    // read at every call: the parity tests run all three.
     const char* f = getenv("NLC_ROLLOUT_TILES");
-    const int tiles = (f && (f[0] == '1' || f[0] == '2' || f[0] == '3')) ? f[0] - '0' : ((K + 127) / 128 > 148 ? 2 : 1);
+    const int tiles = (f && (f[0] == '1' || f[0] == '2' || f[0] == '3')) ? f[0] - '0' : ((K + 127) / 128 > 148 ? 3 : 1);
     int rc = launch_rollout_tc2(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out,
                                 math_mode == NLC_MATH_TC_SPLIT3, tiles, stream);
     if (rc != NLC_ERR_UNSUPPORTED) return rc;

@@ -143,14 +143,7 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, 
 // inlined, so that the compiler cannot hoist the descriptors of every product of the step loop into registers (inlined,
 // that spilled 246 words under the small budget); inside, fully unrolled with the descriptors advanced by immediates
 // (a rolled loop that rebuilt them issued one MMA per ~130 clocks: the MMAs, not the epilogues, then set the step time).
-// Called by the whole (converged) warp; ONE thread chosen by elect.sync issues and commits.  With elect.sync ptxas knows
-// the region is single-threaded and moves the operands to uniform registers once; under `if (lane == 0)` it wraps every
-// UTCHMMA in a generic divergence loop (ELECT + 6 R2UR + branch): ~100-170 clocks per MMA next to busy epilogue warps.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
-  return p != 0;
-}
+// Called by the whole (converged) warp; ONE thread chosen by elect.sync issues and commits (tc_umma.cuh: elect_one).
 template <int kSteps, bool kSplit3>
 __device__ __noinline__ void issue_gemm_ts_fn(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_hi_desc, uint64_t b_lo_desc, uint32_t idesc,
                                               uint64_t* done) {
@@ -420,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
       tmem_st_wait();
       fence_before_sync();
       asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGroupT) : "memory");
-      if (wl == 0 && lane == 0) {
+      if (wl == 0 && elect_one()) {
         fence_after_sync();
         if (ev == 0) issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w1_hi, w1_lo, kH, 1, kSbo16);
         else if (ev == 1) issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w2_hi, w2_lo, kH, kH / 16, kSbo);
@@ -601,8 +594,8 @@ struct SmemTailPP {
   float smean[kMaxNx], sinv[kMaxNx];
   alignas(16) float exch[2][4][NX * kRows];  // [tile][column group][channel][row] partial ILT sums
   alignas(8) float stage_p[2][kRows][2];     // cp.async landing slots: p_action of the next step ...
-  alignas(8) float stage_u[2][kRows][2];     // ... and the action this step applies (running cost), per tile and sample
-  alignas(8) uint64_t done[2], ready[2];
+  alignas(8) float stage_u[2][2][kRows][2];  // ... and the action this step applies (running cost): [step parity][tile][sample]
+  alignas(8) uint64_t done[2];
   uint32_t tmem_base;
 };
 constexpr int kThreadsPP = kThreads + 128;    // 16 epilogue warps + the MMA warp's group (setmaxnreg works on groups of 4 warps)
@@ -640,9 +633,9 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
     for (int i = tid; i < 256; i += kThreadsPP) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
     for (int i = tid; i < S; i += kThreadsPP) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
     if (tid < NX) { s.smean[tid] = a.m.state_mean[tid]; s.sinv[tid] = a.m.state_inv_std[tid]; }
-    for (int i = tid; i < 2 * kRows * 2; i += kThreadsPP) (&s.stage_u[0][0][0])[i] = 0.0f;
+    for (int i = tid; i < 2 * 2 * kRows * 2; i += kThreadsPP) (&s.stage_u[0][0][0][0])[i] = 0.0f;
     if (tid == 0) {
-      for (int g = 0; g < 2; ++g) { mbar_init(&s.done[g], 1); mbar_init(&s.ready[g], kThreads / 32); }
+      for (int g = 0; g < 2; ++g) mbar_init(&s.done[g], 1);
       mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&s.tmem_base, kTmemCols);
@@ -680,11 +673,11 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
       // products in the epilogue warps' hand-off order, the two tiles strictly alternating: (M1x M1y) then per step
       // (M2x M2y M3ax M3ay [M3bx M3by] M1x' M1y').  ONE issuing warp on purpose: with a warp per tile the two M2 products
       // interleave on the tensor pipe and the one needed first completes last.
-      uint32_t gcount = 0;  // products so far: tile = gcount & 1, parity of its ready barrier = (gcount >> 1) & 1
       int mstep = 0, mprod = 0;  // measurement only: the MMA warp's own timeline, second half of the trace buffer
       auto product = [&](int x, int ev) {
-        mbar_wait_sleep(&s.ready[x], (gcount >> 1) & 1u);
-        ++gcount;
+        // named barrier 1 + x: the 16 epilogue warps bar.arrive, this warp bar.sync (as an mbarrier, every one of the 16
+        // arrivals woke all warps sleeping in try_wait loops: a quarter of the executed instructions were SYNCS/NANOSLEEP/BRA)
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + x), "n"(kThreads + 32) : "memory");
         if (lane == 0 && a.trace && blockIdx.x == 0 && mstep < 51 && mprod < 8) a.trace[52 * 256 + mstep * 256 + 2 * mprod] = clock64();
         __syncwarp();
         const uint32_t tg = tmem + kGroupCols * x;
@@ -727,8 +720,7 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
   auto handoff = [&](int x) {
     tmem_st_wait();
     fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s.ready[x]);
+    asm volatile("bar.arrive %0, %1;" ::"r"(1 + x), "n"(kThreads + 32) : "memory");
   };
   auto wait_mma = [&](int x) {
     mbar_wait_sleep(&s.done[x], nphase & 1u);
@@ -826,6 +818,28 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
       for (int c = 0; c < NX; ++c) e[c * kRows] = (kHalf == 0) ? delta[c] : e[c * kRows] + delta[c];
     };
 
+    // duties of step tt's END state that nothing waits for - its row of `states` (column group 2) and its running cost
+    // (column group 3; mppi_delay.py:288-290: the post-step state with the action just applied) - are carried out one
+    // step later, behind these groups' units of the last L3 phase: they have one unit less there than groups 0 and 1 and
+    // would otherwise idle at the exchange barrier, while after the state update they would delay the next step's M1
+    auto deferred = [&](int x, int tt) {
+      const int kx = x ? kk1 : kk0;
+      if (!((lmask >> x) & 1)) return;
+      if (cg == 2 && a.states) {
+#pragma unroll
+        for (int c = 0; c < NX; ++c) a.states[((size_t)kx * a.T + tt) * NX + c] = x ? st1[c] : st0[c];
+      }
+      if (cg == 3 && a.cost_total) {
+        const float2 uv = *reinterpret_cast<const float2*>(&s.stage_u[tt & 1][x][row][0]);
+        const float uc[2] = {uv.x, uv.y};   // zero-padded for nu == 1: a static count keeps the action in registers
+        float stx[NX];
+#pragma unroll
+        for (int c = 0; c < NX; ++c) stx[c] = x ? st1[c] : st0[c];
+        const float c = env_running_cost_fast(a.o, stx, uc, 2);
+        if (x) cost1 += c; else cost0 += c;
+      }
+    };
+
     write_a1(0, st0); handoff(0);
     write_a1(1, st1); handoff(1);
 
@@ -841,8 +855,8 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.stage_p[x][row][0])), "l"(a.p + ((size_t)kx * a.T + t + 1) * 2) : "memory");
         if (cg == 3 && ((lmask >> x) & 1) && a.cost_total) {
           const float* up = a.hist + ((size_t)kx * a.L + t + a.B - 1) * a.nu;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s.stage_u[x][row][0])), "l"(up) : "memory");
-          if (a.nu > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s.stage_u[x][row][1])), "l"(up + 1) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s.stage_u[t & 1][x][row][0])), "l"(up) : "memory");
+          if (a.nu > 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s.stage_u[t & 1][x][row][1])), "l"(up + 1) : "memory");
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -861,22 +875,33 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
         mark(4 + x);
         l3_half(x, std::integral_constant<int, 0>());
         if (N3b > 0) handoff(x);
+        else if (t > 0) {
+          if (x == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");  // the copies of the previous step (this thread's own)
+          deferred(x, t - 1);
+        }
       }
       ++nphase;
       if (N3b > 0) {
         mark(14);
 #pragma unroll 1
-        for (int x = 0; x < 2; ++x) { wait_mma(x); mark(6 + x); l3_half(x, std::integral_constant<int, 1>()); }  // E3b
+        for (int x = 0; x < 2; ++x) {                                                           // E3b
+          wait_mma(x);
+          mark(6 + x);
+          l3_half(x, std::integral_constant<int, 1>());
+          if (t > 0) {
+            if (x == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");  // the copies of the previous step (this thread's own)
+            deferred(x, t - 1);
+          }
+        }
         ++nphase;
       }
       mark(15);
       asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's own copies: it reads only its own slots
+      // ONE barrier among the four warps of a row quarter covers the partial sums of both tiles (tile 1's were written last)
+      asm volatile("bar.sync %0, %1;" ::"r"(5 + q), "n"(128) : "memory");
+      mark(8);
 #pragma unroll 1
-      for (int x = 0; x < 2; ++x) {                                                   // U: residual, cost, next A1 -> M1
-        asm volatile("bar.sync %0, %1;" ::"r"(5 + 4 * x + q), "n"(128) : "memory");
-        mark(8 + x);
-        const int kx = x ? kk1 : kk0;
-        const bool lv = (lmask >> x) & 1;
+      for (int x = 0; x < 2; ++x) {                                                   // U: residual, next A1 -> M1
         // every thread of a sample adds the partials in the same order: the replicated state stays bit-identical
         float stx[NX];
 #pragma unroll
@@ -885,26 +910,19 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
           const float d = ((e[0] + e[NX * kRows]) + e[2 * NX * kRows]) + e[3 * NX * kRows];
           stx[c] = (x ? st1[c] : st0[c]) + d;                     // mppi_with_model.py:121
           if (x) st1[c] = stx[c]; else st0[c] = stx[c];
-          if (cg == 2 && lv) {
-            if (a.states) a.states[((size_t)kx * a.T + t) * NX + c] = stx[c];
-            if (a.delta_out) a.delta_out[(size_t)kx * NX + c] = d;
-          }
-        }
-        // running cost of the new state with the action just applied (mppi_delay.py:288-290)
-        if (cg == 3 && lv && a.cost_total) {
-          const float2 uv = *reinterpret_cast<const float2*>(&s.stage_u[x][row][0]);
-          const float uc[2] = {uv.x, uv.y};   // zero-padded for nu == 1: a static count keeps the action in registers
-          const float c = env_running_cost_fast(a.o, stx, uc, 2);
-          if (x) cost1 += c; else cost0 += c;
+          if (cg == 2 && ((lmask >> x) & 1) && a.delta_out) a.delta_out[(size_t)(x ? kk1 : kk0) * NX + c] = d;
         }
         if (t + 1 < a.T) {
           write_a1(x, stx);
           handoff(x);
         }
+        mark(9);
       }
       mark(10);
       ++tstep;
     }
+    deferred(0, a.T - 1);   // the last step's state: its copies were waited for in the U phase
+    deferred(1, a.T - 1);
     if (cg == 3 && a.cost_total) {
       if (lmask & 1) a.cost_total[kk0] = cost0 + (a.pert_cost ? a.pert_cost[kk0] : 0.0f);
       if (lmask & 2) a.cost_total[kk1] = cost1 + (a.pert_cost ? a.pert_cost[kk1] : 0.0f);

@@ -131,6 +131,15 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One thread of the (converged) warp, chosen by elect.sync.  Issue tcgen05.mma under THIS predicate, not under
+// `lane == 0`: ptxas then knows the region is single-threaded and keeps the operands in uniform registers; under a lane
+// test it wraps every UTCHMMA in a generic divergence loop (ELECT, R2UR of all six operands, predicate shuffling, branch) -
+// 8-12 instructions and ~100-170 clocks per MMA next to busy epilogue warps (measured in the ping-pong rollout form).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
 // all MMAs issued so far by this thread -> one arrival on the mbarrier when they complete
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -322,9 +322,9 @@ def test_tc_plan_cfg1(mode, tol, tiles, monkeypatch):
 
 @pytest.mark.parametrize("env,K,T", [("oderl-acrobot", 20011, 6), ("oderl-cartpole", 19000, 5), ("oderl-pendulum", 40000, 4)])
 def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
-    """Plans larger than one wave of 128-sample tiles take the two-tiles-per-CTA rollout (partially filled and ragged
-    last tiles, K not a multiple of 32): same costs and states as the one-tile form (which then walks several tiles per
-    CTA) and as the fp32 anchor kernel."""
+    """Plans larger than one wave of 128-sample tiles take the ping-pong rollout (two tiles per CTA; partially filled and
+    ragged last tiles, K not a multiple of 32): same costs and states as the one-tile form (which then walks several tiles
+    per CTA), the free-running two-tile form and the fp32 anchor kernel."""
     import ctypes as C
 
     from oracle import costs
@@ -357,7 +357,7 @@ def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
         torch.cuda.synchronize()
         assert torch.isfinite(cost).all() and torch.isfinite(states).all(), name
         outs[name] = (cost, states)
-    assert torch.equal(outs["auto"][0], outs["two_tiles"][0])  # the library picks the two-tile form for this size
+    assert torch.equal(outs["auto"][0], outs["ping_pong"][0])  # the library picks the ping-pong form for this size
     for name in ("one_tile", "two_tiles", "ping_pong"):
         assert relerr(outs["fp32"][0], outs[name][0]) < 1e-4, (name, relerr(outs["fp32"][0], outs[name][0]))
         assert relerr(outs["fp32"][1], outs[name][1]) < 1e-4, (name, relerr(outs["fp32"][1], outs[name][1]))

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Timeline of the rollout kernel's first CTA (clock64 per warp at the phase boundaries).  Measurement tool only."""
+"""Timeline of the rollout kernel's first CTA (clock64 per warp at the phase boundaries), forms 1 and 2 of rollout_tc2.cu
+(NLC_ROLLOUT_TILES, default here 2); the ping-pong form has its own tool, trace_rollout_pp.py.  Measurement tool only."""
 import ctypes as C
 import os
 import sys
@@ -19,6 +20,7 @@ EV = ["A1 written", "M1 done", "E1 done", "M2 done", "E2 done", "M3a done", "E3a
 
 
 def main():
+    os.environ.setdefault("NLC_ROLLOUT_TILES", "2")
     torch.set_grad_enabled(False)
     dev = torch.device("cuda", 0)
     env = "oderl-acrobot"

@@ -17,7 +17,7 @@ from _util import DT, S_TERMS, weights  # noqa: E402
 from oracle import costs  # noqa: E402
 
 ORDER = [(11, "step start"), (0, "E1x go"), (1, "E1y go"), (12, "E1y end"), (2, "E2x go"), (3, "E2y go"), (13, "E2y end"), (4, "E3ax go"),
-         (5, "E3ay go"), (14, "E3ay end"), (6, "E3bx go"), (7, "E3by go"), (15, "E3by end"), (8, "Ux go"), (9, "Uy go"), (10, "step end")]
+         (5, "E3ay go"), (14, "E3ay end"), (6, "E3bx go"), (7, "E3by go"), (15, "E3by end"), (8, "U go"), (9, "U end"), (10, "step end")]
 
 
 def main():
