@@ -1,12 +1,17 @@
 // Stages 2+3 for the Neural Laplace dynamics, representation MLP on the 5th-generation tensor cores
-// (rollout.cu is the fp32 CUDA-core anchor).
+// (rollout.cu is the fp32 CUDA-core anchor).  Three forms of one recurrence, chosen by plan size in rollout.cu:
+//   rollout_pp_kernel            "ping-pong": two 128-sample tiles per CTA, all 16 epilogue warps on one tile's phase at a
+//                                time + a dedicated MMA warp - plans beyond one wave of tiles (documented at the kernel)
+//   rollout_tc2_kernel<kTiles=1> one tile per CTA on all 16 warps - plans within one wave: the step latency is what counts
+//   rollout_tc2_kernel<kTiles=2> two free-running 8-warp groups - the ping-pong form's predecessor, kept for comparison
+//                                (NLC_ROLLOUT_TILES=2) and as the second opinion of the parity suite
 //
 // Same recurrence as rollout.cu: state <- state + ILT(MLP([s | obs_n | p_action])), cost += running_cost, whole horizon in
 // one launch, state in registers.  The recurrence is a strict chain per sample (L1 -> L2 -> L3 -> ILT -> next step), so
 // inside ONE tile the tensor pipe and the CUDA cores can only alternate; the first form measured 22.7 k clocks per step
-// = MUFU time + issue time + MMA time, nothing overlapping.  Here every CTA runs TWO independent tiles ("groups" of 8
-// warps = 128 samples each) that share the weight images in shared memory and otherwise never synchronise with each
-// other: one group's MMAs and barrier round trips run under the other group's epilogues.  (Holding the two groups
+// = MUFU time + issue time + MMA time, nothing overlapping.  In the two-group form every CTA runs TWO independent tiles
+// ("groups" of 8 warps = 128 samples each) that share the weight images in shared memory and otherwise never synchronise
+// with each other: one group's MMAs and barrier round trips run under the other group's epilogues.  (Holding the two groups
 // exactly half a step apart with named barriers was tried: 29.5 k instead of 31.3 k clocks per step in the trace, but
 // slower end to end - tools/trace_rollout.py shows long transients with every phase stretched - so they run free.)
 //
@@ -29,9 +34,9 @@
 //
 //   Samples are dealt to the 2 x gridDim groups in contiguous ranges (multiples of 32 rows), each walked in tiles of up
 //   to 128 rows: a plan that is not a whole number of waves ends on partially filled tiles instead of an idle wave.
-//   Threads: group g = warps 8g .. 8g+7; warp w of a group owns TMEM lanes 32 (w & 3).. (its 32 samples) and column
-//   half w >> 2.  After a group barrier its first warp issues the group's MMAs: the group waits for that product anyway,
-//   so the issuing thread being held by the MMA queue costs nothing (unlike in the encoder).
+//   Threads (two-group form): group g = warps 8g .. 8g+7; warp w of a group owns TMEM lanes 32 (w & 3).. (its 32 samples)
+//   and column half w >> 2.  After a group barrier its first warp issues the group's MMAs under elect.sync: the group waits
+//   for that product anyway, so the issuing thread being held by the MMA queue costs nothing (unlike in the encoder).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -575,15 +580,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
 // phase of the OTHER tile to complete, so the CUDA cores never wait for the tensor pipe and every SM sub-partition always
 // has its four warps in the same instruction mix.  The free-running two-group form above leaves each tile with two warps
 // per sub-partition (latency-bound epilogues: 33.5 k clocks per step of a tile pair at config 4, issue slots 40 % busy).
-//   hand-off   a dedicated MMA warp (warp 16), coupled to the 16 epilogue warps only by mbarriers: an epilogue warp
-//              arrives on ready[tile] after its TMEM stores and moves on to the other tile's phase; the MMA warp waits for the
-//              16 arrivals, issues the product and commits it to done[tile].  (tcgen05.mma issue is back-pressured by MMA
-//              execution: with one of the epilogue warps issuing - even a different one every time - that warp falls
-//              behind by the whole product and the next hand-off waits for it: 43.9 k clocks per step, nothing
-//              overlapped.)  The register file cannot hold 17 warps at 128 registers, so the CTA is launched with 20 warps at
-//              96 and re-balanced with setmaxnreg: 112 for the epilogue warps, 24 for the MMA warp's group.
+//   hand-off   a dedicated MMA warp (warp 16): an epilogue warp arrives on the tile's NAMED barrier (bar.arrive: it does not
+//              block) after its TMEM stores and moves on to the other tile's phase; the MMA warp waits for the 16 arrivals
+//              (bar.sync), issues the product under elect.sync and commits it to the mbarrier done[tile], which the epilogue
+//              warps wait on one phase later.  (tcgen05.mma issue is back-pressured by MMA execution: with one of the
+//              epilogue warps issuing - even a different one every time - that warp falls behind by the whole product and
+//              the next hand-off waits for it: 43.9 k clocks per step, nothing overlapped.)  The register file cannot hold
+//              17 warps at 128 registers, so the CTA is launched with 20 warps at 96 and re-balanced with setmaxnreg: 112
+//              for the epilogue warps, 32 for the MMA warp's group (whose issue code is a non-inlined, fully unrolled
+//              function so that it fits that budget).
 //   threads    warp w: TMEM lanes 32 (w & 3).. (its 32 samples of BOTH tiles), column group w >> 2 (32 of the 128 hidden
-//              units; chunks c = cg (mod 4) of the (theta, phi) columns).  The state of a sample is replicated in its four
+//              units; units u = cg (mod 4) of the (theta, phi) columns, 8 columns each).  The state of a sample is replicated in its four
 //              threads; partial ILT sums are exchanged through shared memory among the four warps of a row quarter.
 //   L3         first half N3a = min(N3t, 128) columns, second half the rest (<= 128): A 128 + D 128 columns per tile.
 template <int NX>
