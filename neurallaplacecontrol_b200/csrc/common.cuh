@@ -14,6 +14,10 @@ namespace nlc {
 void set_error(const char* fmt, ...);
 int check_device_arch(int device);
 void count_launch(int n = 1);
+// one line on stderr, once per process and per `slot` (0..15): a shape that has no tensor-core instantiation runs on the
+// fp32 CUDA-core kernels - correct, but an order of magnitude slower, so it must not be silent
+void warn_once(int slot, const char* fmt, ...);
+enum { kWarnEncoderFfma = 0, kWarnRolloutFfma = 1, kWarnForwardTsFfma = 2 };
 
 #define NLC_CUDA_OK(expr)                                                                      \
   do {                                                                                         \
@@ -121,6 +125,10 @@ struct nlc_model_s {
   nlc::ModelHost h;
   void* arena;  // single device allocation backing every pointer in d
   size_t arena_bytes;
+  // planners hold the model by pointer: nlc_planner_create takes a reference, nlc_planner_destroy drops it, and
+  // nlc_model_destroy on a model that is still referenced only marks it (freed with the last planner)
+  int refs;
+  bool destroy_requested;
 };
 
 namespace nlc {

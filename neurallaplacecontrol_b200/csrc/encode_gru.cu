@@ -197,12 +197,9 @@ int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, in
   a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.gin = m->gin;
   a.rows = (long long)K * T;
   a.m = m->d;
-  static bool attr_set = false;
   const int smem = (int)sizeof(EncSmem);
-  if (!attr_set) {
-    NLC_CUDA_OK(cudaFuncSetAttribute(encode_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  // function attributes are per device: set on every launch, like every other kernel of the library
+  NLC_CUDA_OK(cudaFuncSetAttribute(encode_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long n_tiles = (a.rows + kEncRows - 1) / kEncRows;
   int grid = (int)(n_tiles < 148 ? n_tiles : 148);
   encode_gru_kernel<<<grid, 256, smem, stream>>>(a);
@@ -225,7 +222,12 @@ int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K
     case NLC_MATH_TC_SPLIT3:
     case NLC_MATH_TC_FP16:
       // shapes without a tensor-core instantiation run on the fp32 kernel
-      if (B < 2 || B * m->gin > 8 || m->gin > 2) return launch_encode_fp32(m, hist_dev, hist_ch, K, T, B, p_dev, s);
+      if (B < 2 || B * m->gin > 8 || m->gin > 2) {
+        if ((long long)K * T >= 4096)
+          warn_once(kWarnEncoderFfma, "encoder: window length %d x input width %d has no tcgen05 instantiation; %lld windows run on the "
+                    "fp32 CUDA-core kernel", B, m->gin, (long long)K * T);
+        return launch_encode_fp32(m, hist_dev, hist_ch, K, T, B, p_dev, s);
+      }
       return launch_encode_tc2(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
     default: set_error("nlc_encode_history: unknown math_mode %d", math_mode); return NLC_ERR_ARG;
   }

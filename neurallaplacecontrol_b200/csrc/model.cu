@@ -1,6 +1,7 @@
 // Model handle: packs a reference NeuralLaplaceModel state_dict (w_nl.py:66-145) into the device
 // layouts the kernels read, and folds the constants of a fixed prediction time in fp64.
 #include <stdarg.h>
+#include <cmath>
 #include <string.h>
 
 #include <atomic>
@@ -21,6 +22,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+void warn_once(int slot, const char* fmt, ...) {
+  static std::atomic<unsigned> seen{0};
+  const unsigned bit = 1u << (slot & 15);
+  if (seen.fetch_or(bit) & bit) return;
+  va_list ap;
+  va_start(ap, fmt);
+  fputs("libnlc_b200: warning: ", stderr);
+  vfprintf(stderr, fmt, ap);
+  fputc('\n', stderr);
+  va_end(ap);
+}
 
 int check_device_arch(int device) {
   int n = 0;
@@ -121,6 +134,9 @@ static int fold_prediction_time(nlc_model_s* m, double ts_pred) {
     nlc::tc_pack_weight_split(w1.data(), Hm, 16, w1img.data(), w1img.data() + (size_t)Hm * 16);
   }
   NLC_CUDA_OK(cudaSetDevice(m->device));
+  // the folded constants are rewritten in place: kernels of an earlier control step (possibly on a non-blocking
+  // stream, which a plain cudaMemcpy does not order against) must have finished reading them
+  NLC_CUDA_OK(cudaDeviceSynchronize());
   NLC_CUDA_OK(cudaMemcpy(m->d.mlp2_w1, w1img.data(), w1img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   NLC_CUDA_OK(cudaMemcpy(m->d.b1_fold, b1.data(), sizeof(float) * Hm, cudaMemcpyHostToDevice));
   NLC_CUDA_OK(cudaMemcpy(m->d.ilt_phase, phase.data(), sizeof(float) * S, cudaMemcpyHostToDevice));
@@ -153,11 +169,26 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   for (const void* p : ptrs) NLC_REQUIRE(p != nullptr, NLC_ERR_ARG, "null weight pointer in nlc_model_desc");
 
   const int Hg = Hm / 2, G3 = 3 * Hg, L = nx + 2, in0 = 2 * S + L, N3 = 2 * nx * S, N3p = (N3 + 3) / 4 * 4, N3t = (N3 + 15) / 16 * 16;
+  {
+    // Every parameter must be finite.  Besides being meaningless otherwise, the tensor-core encoder's [x | 1] operand
+    // block lets the zero half of its A side multiply neighbouring (weight) data of the B side (encode_tc2.cu): that
+    // product is exactly zero only for finite data.
+    const struct { const double* p; size_t n; const char* name; } chk[] = {
+        {d->state_mean, (size_t)nx, "state_mean"}, {d->state_std, (size_t)nx, "state_std"}, {d->action_mean, (size_t)nu, "action_mean"},
+        {d->action_std, (size_t)d->action_std_len, "action_std"}, {d->gru_w_ih_l0, (size_t)G3 * gin, "gru.weight_ih_l0"},
+        {d->gru_w_hh_l0, (size_t)G3 * Hg, "gru.weight_hh_l0"}, {d->gru_b_ih_l0, (size_t)G3, "gru.bias_ih_l0"}, {d->gru_b_hh_l0, (size_t)G3, "gru.bias_hh_l0"},
+        {d->gru_w_ih_l1, (size_t)G3 * Hg, "gru.weight_ih_l1"}, {d->gru_w_hh_l1, (size_t)G3 * Hg, "gru.weight_hh_l1"}, {d->gru_b_ih_l1, (size_t)G3, "gru.bias_ih_l1"},
+        {d->gru_b_hh_l1, (size_t)G3, "gru.bias_hh_l1"}, {d->enc_out_w, (size_t)2 * Hg, "linear_out.weight"}, {d->enc_out_b, 2, "linear_out.bias"},
+        {d->mlp_w0, (size_t)Hm * in0, "mlp.0.weight"}, {d->mlp_b0, (size_t)Hm, "mlp.0.bias"}, {d->mlp_w2, (size_t)Hm * Hm, "mlp.2.weight"},
+        {d->mlp_b2, (size_t)Hm, "mlp.2.bias"}, {d->mlp_w4, (size_t)N3 * Hm, "mlp.4.weight"}, {d->mlp_b4, (size_t)N3, "mlp.4.bias"}};
+    for (const auto& c : chk)
+      for (size_t i = 0; i < c.n; ++i) NLC_REQUIRE(std::isfinite(c.p[i]), NLC_ERR_ARG, "model parameter %s[%zu] is not finite", c.name, i);
+  }
   nlc_model_s* m = new nlc_model_s();
   memset(&m->d, 0, sizeof(m->d));
   m->device = device; m->nx = nx; m->nu = nu; m->gin = gin; m->Hm = Hm; m->Hg = Hg; m->S = S; m->N3 = N3; m->N3p = N3p; m->N3t = N3t;
   m->normalize = d->normalize; m->normalize_time = d->normalize_time; m->encode_obs_time = d->encode_obs_time;
-  m->dt = d->dt; m->arena = nullptr;
+  m->dt = d->dt; m->arena = nullptr; m->refs = 0; m->destroy_requested = false;
 
   Arena A;
   auto put = [&](size_t off, size_t i, double v) { A.data[off + i] = (float)v; };
@@ -336,6 +367,10 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
 
 extern "C" int nlc_model_destroy(nlc_model_t m) {
   if (!m) return NLC_OK;
+  if (m->refs > 0) {  // a planner still rolls out on this model: the last nlc_planner_destroy frees it
+    m->destroy_requested = true;
+    return NLC_OK;
+  }
   cudaSetDevice(m->device);
   if (m->arena) cudaFree(m->arena);
   delete[] m->h.w0;

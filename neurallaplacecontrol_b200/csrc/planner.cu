@@ -1,6 +1,7 @@
 // Planner handle: the device-resident state of one MPPIDelay object (planners/mppi_delay.py:64-230) and
 // the control step as a fixed sequence of kernel launches on one stream:
 //   perturb -> encode_history -> rollout_cost -> softmax (init, min, sum) -> [exchange triples] -> combine
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -55,6 +56,7 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
     NLC_REQUIRE(model->device == device, NLC_ERR_ARG, "planner: model lives on device %d, planner on %d", model->device, device);
     NLC_REQUIRE(model->nx == d->nx && model->nu == mp.nu, NLC_ERR_SHAPE, "planner: model dims do not match");
   }
+  NLC_REQUIRE(model == nullptr || !model->destroy_requested, NLC_ERR_ARG, "planner: the model handle has been destroyed");
   nlc_planner_s* p = new nlc_planner_s();
   p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;
   p->call_ctr = nullptr; p->cap_stream = nullptr; p->graph_core = nullptr; p->graph_host = nullptr;
@@ -91,13 +93,34 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   if (cudaMallocHost(&p->h_in, sizeof(float) * (nx + B * nu)) != cudaSuccess || cudaMallocHost(&p->h_out, sizeof(float) * 4) != cudaSuccess) {
     cudaGetLastError(); set_error("planner: pinned allocation failed"); return fail(NLC_ERR_NOMEM);
   }
+  if (model) model->refs++;
   *out = p;
+  return NLC_OK;
+}
+
+// drop a planner's reference on its model; frees the model if nlc_model_destroy was called while it was in use
+static void model_release(nlc_model_t m) {
+  if (!m) return;
+  if (--m->refs <= 0 && m->destroy_requested) { m->refs = 0; nlc_model_destroy(m); }
+}
+
+// The planner rolls out on constants folded into the model for ONE prediction time.  NeuralLaplaceModel.forward at
+// another uniform time re-folds them in place (nlc_model_set_prediction_time): refuse to plan on that silently.
+static int planner_check_model(nlc_planner_t p) {
+  if (p->d.rollout.dynamics != NLC_DYN_NEURAL_LAPLACE) return NLC_OK;
+  NLC_REQUIRE(!p->model->destroy_requested, NLC_ERR_ARG, "planner: its model handle has been destroyed");
+  const double want = (double)p->d.rollout.dt;
+  NLC_REQUIRE(fabs(p->model->ts_pred - want) <= 1e-6 * fabs(want), NLC_ERR_ARG,
+              "planner: the model is folded for prediction time %.9g, the planner steps by dt = %.9g; call "
+              "nlc_model_set_prediction_time(model, dt) before the control step", p->model->ts_pred, want);
   return NLC_OK;
 }
 
 extern "C" int nlc_planner_destroy(nlc_planner_t p) {
   if (!p) return NLC_OK;
   cudaSetDevice(p->device);
+  cudaDeviceSynchronize();  // no kernel of this planner may still read the model when the last reference goes
+  model_release(p->model);
   if (p->graph_core) cudaGraphExecDestroy(p->graph_core);
   if (p->graph_host) cudaGraphExecDestroy(p->graph_host);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
@@ -161,7 +184,9 @@ extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int 
   NLC_REQUIRE(p && state_dev && action_buffer_dev, NLC_ERR_ARG, "nlc_planner_rollout: null argument");
   const nlc_mppi_params& mp = p->d.mppi;
   NLC_CUDA_OK(cudaSetDevice(p->device));
-  int rc = perturb_launch(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, 0, p->call_ctr, action_buffer_dev, p->perturbed,
+  int rc = planner_check_model(p);
+  if (rc != NLC_OK) return rc;
+  rc = perturb_launch(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, 0, p->call_ctr, action_buffer_dev, p->perturbed,
                           p->noise, p->hist, p->actions, p->pert_cost, stream);
   if (rc != NLC_OK) return rc;
   rc = launch_bump_counter(p->call_ctr, static_cast<cudaStream_t>(stream));  // the next control step draws fresh samples
@@ -253,6 +278,7 @@ extern "C" int nlc_planner_step(nlc_planner_t p, void* stream) {
   NLC_REQUIRE(p, NLC_ERR_ARG, "nlc_planner_step: null planner");
   NLC_REQUIRE(p->d.n_shards == 1, NLC_ERR_UNSUPPORTED, "nlc_planner_step is the single-shard entry point");
   NLC_CUDA_OK(cudaSetDevice(p->device));
+  { int rc = planner_check_model(p); if (rc != NLC_OK) return rc; }
   if (!p->graph_core_tried) { p->graph_core_tried = true; p->graph_core = planner_capture_preserving_state(p, false); }
   if (p->graph_core) {
     NLC_CUDA_OK(cudaGraphLaunch(p->graph_core, static_cast<cudaStream_t>(stream)));
@@ -271,6 +297,7 @@ extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_hos
   const int nx = p->d.nx, nb = mp.B * mp.nu;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   NLC_CUDA_OK(cudaSetDevice(p->device));
+  { int rc = planner_check_model(p); if (rc != NLC_OK) return rc; }
   if (!noise_in_dev && !p->graph_host_tried) { p->graph_host_tried = true; p->graph_host = planner_capture_preserving_state(p, true); }
   for (int i = 0; i < nx; ++i) p->h_in[i] = (float)state_host[i];
   for (int i = 0; i < nb; ++i) p->h_in[nx + i] = (float)action_buffer_host[i];
@@ -331,6 +358,9 @@ extern "C" int nlc_batch_planner_create(nlc_batch_planner_t* out, nlc_model_t mo
     NLC_REQUIRE(model->device == device, NLC_ERR_ARG, "batch planner: model lives on device %d, planner on %d", model->device, device);
     NLC_REQUIRE(model->nx == d->nx && model->nu == mp.nu, NLC_ERR_SHAPE, "batch planner: model dims do not match");
   }
+  // stage 4 reads each instance's cost slice 16 bytes wide (nlc_softmax_partial): instance i starts at cost_total + i*K
+  NLC_REQUIRE(n_instances == 1 || mp.K % 4 == 0, NLC_ERR_SHAPE, "batch planner: samples per instance (%d) must be a multiple of 4", mp.K);
+  NLC_REQUIRE(model == nullptr || !model->destroy_requested, NLC_ERR_ARG, "batch planner: the model handle has been destroyed");
   nlc_batch_planner_s* p = new nlc_batch_planner_s();
   p->device = device; p->I = n_instances; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr;
   p->seeds.assign(seeds, seeds + n_instances);
@@ -351,6 +381,7 @@ extern "C" int nlc_batch_planner_create(nlc_batch_planner_t* out, nlc_model_t mo
   for (size_t i = 0; i < sizeof(slots) / sizeof(slots[0]); ++i) *slots[i] = base + offs[i];
   if (!d->keep_states) p->states = nullptr;
   p->softmax_ws = reinterpret_cast<char*>(base + offs[13]);
+  if (model) model->refs++;
   *out = p;
   return NLC_OK;
 }
@@ -358,6 +389,8 @@ extern "C" int nlc_batch_planner_create(nlc_batch_planner_t* out, nlc_model_t mo
 extern "C" int nlc_batch_planner_destroy(nlc_batch_planner_t p) {
   if (!p) return NLC_OK;
   cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  model_release(p->model);
   if (p->arena) cudaFree(p->arena);
   delete p;
   return NLC_OK;
@@ -395,6 +428,11 @@ extern "C" int nlc_batch_planner_command(nlc_batch_planner_t p, const float* sta
   NLC_CUDA_OK(cudaSetDevice(p->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
+  if (p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
+    const double want = (double)p->d.rollout.dt;
+    NLC_REQUIRE(!p->model->destroy_requested && fabs(p->model->ts_pred - want) <= 1e-6 * fabs(want), NLC_ERR_ARG,
+                "batch planner: the model is folded for prediction time %.9g, not dt = %.9g", p->model->ts_pred, want);
+  }
   for (int i = 0; i < I; ++i) {  // stage 1 per instance (its own U, action buffer and RNG stream)
     const size_t o = (size_t)i * K;
     rc = nlc_perturb(&mp, p->U + i * TN, p->U_rolled + i * TN, 1, noise_in_dev ? noise_in_dev + o * TN : nullptr, p->seeds[i], p->calls,

@@ -279,6 +279,9 @@ static int launch_rollout(nlc_model_s* m, const nlc_rollout_opts* o, const float
                                 math_mode == NLC_MATH_TC_SPLIT3, tiles, stream);
     if (rc != NLC_ERR_UNSUPPORTED) return rc;
   }
+  if (math_mode != NLC_MATH_FP32 && (long long)K * T >= 4096)
+    warn_once(kWarnRolloutFfma, "rollout: nx = %d with %d Fourier terms (%d output columns) has no tcgen05 instantiation; %lld "
+              "rollout-steps run on the fp32 CUDA-core kernel", m->nx, m->S, 2 * m->nx * m->S, (long long)K * T);
   return launch_rollout_fp32(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, delta_out, stream);
 }
 

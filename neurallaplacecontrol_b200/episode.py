@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .closures import NLDynamics
 from .planners.mppi_delay import MPPIDelay, _DevView
 
 
@@ -55,12 +56,21 @@ class BatchedMPPIDelay:
             U = U.reshape(1, self.T, self.nu).repeat(self.I, 1, 1) if U.numel() == self.T * self.nu else U.reshape(self.I, self.T, self.nu)
         self._U_host = U.contiguous()
         self._lib = _lib.load()
-        self._handle, self._handle_B, self._views, self._calls = None, None, {}, 0
+        self._handle, self._handle_B, self._handle_model, self._views, self._calls = None, None, None, {}, 0
 
     def _ensure(self, B):
-        if self._handle is not None and self._handle_B == B:
+        # the packed model is re-fetched on every call (see MPPIDelay._ensure): a rebuilt or re-folded model handle
+        # must never be planned on silently
+        model_h = None
+        if isinstance(self._tpl.F, NLDynamics):
+            if self._tpl.F.model._cuda_device is None:
+                self._tpl.F.model._cuda_device = self.d
+            model_h = self._tpl.F.model.set_prediction_time(self._tpl.F.dt)
+        key = None if model_h is None else model_h.value
+        if self._handle is not None and self._handle_B == B and self._handle_model == key:
             return self._handle
         self._destroy()
+        self._handle_model = key
         d, model_h = self._tpl._desc(B, self.K, 0, self.K, 1, 0)
         seeds = (C.c_uint64 * self.I)(*self.seeds)
         h = C.c_void_p()
@@ -72,8 +82,22 @@ class BatchedMPPIDelay:
 
     def _destroy(self):
         if self._handle is not None:
+            # keep the planned control sequences: a new handle (another buffer length, a rebuilt model) starts from them
+            self._U_host = self._buf(_lib.BUF_U, (self.I, self.T, self.nu)).detach().to("cpu", torch.float64).contiguous()
             self._lib.nlc_batch_planner_destroy(self._handle)
             self._handle, self._views = None, {}
+
+    def _set_U(self, value):
+        U = torch.as_tensor(value).detach().to("cpu", torch.float64)
+        U = U.reshape(1, self.T, self.nu).repeat(self.I, 1, 1) if U.numel() == self.T * self.nu else U.reshape(self.I, self.T, self.nu)
+        self._U_host = U.contiguous()
+        if self._handle is not None:
+            ptr, keep = _lib.as_double_array(self._U_host.numpy())
+            _lib.check(self._lib.nlc_batch_planner_set_U(self._handle, ptr), "nlc_batch_planner_set_U")
+
+    def reset(self):
+        """``MPPIDelay.reset`` (``mppi_delay.py:226-230``) for every instance: resample each control sequence."""
+        self._set_U(self.noise_dist.sample((self.I, self.T)))
 
     def __del__(self):
         try:
@@ -96,7 +120,8 @@ class BatchedMPPIDelay:
         return None if self._handle is None or self._calls == 0 else self._buf(which, shape)
 
     # the single planner's attributes, with a leading instance axis
-    U = property(lambda self: self._U_host.to(self.dtype) if self._handle is None else self._buf(_lib.BUF_U, (self.I, self.T, self.nu)))
+    U = property(lambda self: self._U_host.to(self.dtype) if self._handle is None else self._buf(_lib.BUF_U, (self.I, self.T, self.nu)),
+                 lambda self, value: self._set_U(value))
     noise = property(lambda self: self._after(_lib.BUF_NOISE, (self.I, self.K, self.T, self.nu)))
     perturbed_action = property(lambda self: self._after(_lib.BUF_PERTURBED, (self.I, self.K, self.T, self.nu)))
     cost_total = property(lambda self: self._after(_lib.BUF_COST_TOTAL, (self.I, self.K)))
@@ -146,7 +171,12 @@ def env_step(env_name, states, action_buffers, actions, action_delay, dt=0.05, r
 
 def run_closed_loop(planner: BatchedMPPIDelay, env_name, states0, action_delay, n_steps, dt=0.05, noise_fn=None):
     """``loop()`` of ``mppi_with_model.py:244-317`` for ``planner.I`` instances: zero action buffers (``:245``), then
-    ``n_steps`` x (command, step_env); rewards accumulate on the device.  ``noise_fn(it)`` may return injected noise for
+    ``n_steps`` x (command, step_env); rewards accumulate on the device.
+
+    NOT the reference environment's integrator: ``env_step`` takes ONE EXPLICIT EULER step of the dynamics as the
+    reference's ``oracle.py`` states them (what its "oracle" planner model uses), whereas the reference's gym envs
+    integrate the same right-hand side with ``torchdiffeq.odeint`` (``base_env.py:136-173``, dopri5 by default).
+    Closed-loop rewards are therefore those of the Euler-discretised plant, not the reference environment's.  ``noise_fn(it)`` may return injected noise for
     step ``it`` (parity tests).  Returns the reference's result keys (``:289-302``) with per-instance arrays."""
     I, B, nu, dev = planner.I, planner.B, planner.nu, planner.d
     states = torch.as_tensor(states0).to(device=dev, dtype=torch.float32).reshape(I, planner.nx).clone()

@@ -15,9 +15,10 @@ Differences a caller can see, all deliberate:
   with ``encode_obs_time=True`` is supported: the closure-level time channel of ``mppi_with_model.py:110-119`` is
   synthesised inside the encoder kernels).
 * Extra keyword arguments (not in the reference): ``process_group`` shards the K samples over the ranks of a
-  ``torch.distributed`` group (one all-gather of the (beta, eta, W) triple per control step), ``seed`` keys the
-  on-device Philox sampler, ``math_mode`` selects the contraction arithmetic, ``keep_states`` can drop the
-  ``states`` trajectory output.
+  ``torch.distributed`` group (one exchange of the (beta, eta, W) triple per control step), ``seed`` keys the
+  on-device Philox sampler, ``math_mode`` selects the contraction arithmetic (default ``"tc_split3"``: tcgen05 tensor
+  cores, fp16 hi/lo split operands, fp32 accumulate - fp32-class, the 1e-4 bound; ``"fp32"`` = CUDA-core FFMA anchor;
+  ``"tc_fp16"`` = single pass, 2e-2 bound), ``keep_states`` can drop the ``states`` trajectory output.
 
 Noise injection for parity tests works as on the reference: replace ``planner.noise_dist.sample`` with a callable
 returning the ``(K, T, nu)`` tensor (it is called once per ``command`` with ``(K, T)``, ``mppi_delay.py:319``).
@@ -56,8 +57,8 @@ class MPPIDelay:
                  terminal_state_cost=None, lambda_=1.0, noise_mu=None, u_min=None, u_max=None, u_init=None,
                  U_init=None, u_scale=1, u_per_command=1, step_dependent_dynamics=False, rollout_samples=1,
                  rollout_var_cost=0, rollout_var_discount=0.95, dt=0.05, sample_null_action=False,
-                 noise_abs_cost=False, encode_obs_time=False, *, process_group=None, seed=0, math_mode="fp32",
-                 keep_states=True, action_buffer_size=4):
+                 noise_abs_cost=False, encode_obs_time=False, *, process_group=None, seed=0, math_mode="tc_split3",
+                 keep_states=True, action_buffer_size=4, shard=None):
         if not isinstance(dynamics, (NLDynamics, AnalyticDelayDynamics)):
             raise TypeError("dynamics must be an NLDynamics or AnalyticDelayDynamics handle: the fused rollout kernel "
                             "cannot call an opaque Python callable and this package has no CPU fallback")
@@ -136,6 +137,10 @@ class MPPIDelay:
 
             self.G = dist.get_world_size(process_group)
             self.rank = dist.get_rank(process_group)
+        elif shard is not None:
+            # (rank, G) without a process group: the caller moves the triples between the shards itself and drives the
+            # control step through _rollout_phase / _finish_phase (single-GPU tests of the sharded arithmetic)
+            self.rank, self.G = int(shard[0]), int(shard[1])
         else:
             self.G, self.rank = 1, 0
         self.k_offset, self.K_local = sharding.shard_range(self.K, self.G, self.rank)
@@ -143,11 +148,24 @@ class MPPIDelay:
         self._lib = _lib.load()
         self._handle = None
         self._handle_B = None
+        self._handle_model = None
         self._views = {}
         if U_init is None:
-            U_init = self.noise_dist.sample((self.T,))  # mppi_delay.py:163-164
+            U_init = self._replicated(self.noise_dist.sample((self.T,)))  # mppi_delay.py:163-164
         self._U_host = torch.as_tensor(U_init).detach().to("cpu", torch.float64).reshape(self.T, self.nu).clone()
         self._U_dirty = True
+
+    def _replicated(self, t):
+        """A tensor drawn from this rank's own RNG, made identical on every rank of the shard group (rank 0's draw wins):
+        U must start replicated for the sharded plan to equal the unsharded one."""
+        if self.G == 1:
+            return t
+        import torch.distributed as dist
+
+        backend = dist.get_backend(self.process_group)
+        buf = t.detach().to(self.d if backend == "nccl" else "cpu", torch.float64).contiguous()
+        dist.broadcast(buf, src=dist.get_global_rank(self.process_group, 0), group=self.process_group)
+        return buf.cpu()
 
     # ---- device handle ---------------------------------------------------------------------------------------
     def _desc(self, B, K_local, k_offset, k_total, n_shards, shard_index):
@@ -188,13 +206,25 @@ class MPPIDelay:
         return d, model_h
 
     def _ensure(self, B):
-        if self._handle is not None and self._handle_B == B:
+        """The device planner for a B-entry action buffer.  The packed model is re-fetched on EVERY call: the model
+        rebuilds its handle when a parameter changed (``load_state_dict``, an optimizer step) and re-folds its
+        constants when ``forward`` ran at another prediction time, and the planner must never roll out on a stale
+        or re-folded handle - so the prediction time is folded back to this planner's ``dt`` and the planner handle
+        is recreated when the model handle is a new one."""
+        model_h = None
+        if isinstance(self.F, NLDynamics):
+            if self.F.model._cuda_device is None:
+                self.F.model._cuda_device = self.d
+            model_h = self.F.model.set_prediction_time(self.F.dt)
+        key = None if model_h is None else model_h.value
+        if self._handle is not None and self._handle_B == B and self._handle_model == key:
             return self._handle
         self._destroy()
         d, model_h = self._desc(B, self.K_local, self.k_offset, self.K, self.G, self.rank)
         h = C.c_void_p()
         _lib.check(self._lib.nlc_planner_create(C.byref(h), model_h, C.byref(d), self.d.index), "nlc_planner_create")
         self._handle, self._handle_B, self._views = h, B, {}
+        self._handle_model = None if model_h is None else model_h.value
         self._U_dirty = True
         return h
 
@@ -290,6 +320,21 @@ class MPPIDelay:
     def command(self, state, action_buffer):
         """:param state: (nx) or (K x nx) current state; :param action_buffer: (B x nu) past actions, env units.
         :returns action: (nu) best action (``mppi_delay.py:193-224``)."""
+        action = self._begin(state, action_buffer)
+        if action is not None:  # single shard, host or planner-owned inputs: the whole step was one graph launch
+            return action
+        if self.G > 1:
+            if self.process_group is None:
+                raise RuntimeError("a planner built with shard=(rank, G) has no process group to exchange the triples: "
+                                   "drive it through _begin / all_triples / _finish")
+            sharding.gather_triples(self.shard_triple, self.all_triples, group=self.process_group)
+        return self._finish()
+
+    # The control step of a shard in its two halves; the exchange of the triples sits between them (the parity tests
+    # drive the G shards of one plan through these on a single GPU).
+    def _begin(self, state, action_buffer):
+        """Stages 1-3 and the shard-local half of stage 4: fills ``shard_triple`` = (beta_g, eta_g, W_g[T][nu]).
+        Returns the action when the fused single-shard path ran the whole step, else None."""
         action_buffer = torch.as_tensor(action_buffer)
         if self.encode_obs_time:
             action_buffer = action_buffer[:, :self.nu]  # the time column is not read by the analytic dynamics (oracle.py:23)
@@ -328,20 +373,63 @@ class MPPIDelay:
                 return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
             _lib.check(self._lib.nlc_planner_rollout(h, st.data_ptr(), int(per_sample), ab.data_ptr(), _lib.ptr(noise), stream),
                        "nlc_planner_rollout")
-            if self.G > 1:
-                triple = self._buf(_lib.BUF_TRIPLE, (2 + self.T * self.nu,))
-                allt = self._buf(_lib.BUF_ALL_TRIPLES, (self.G, 2 + self.T * self.nu))
-                sharding.gather_triples(triple, allt, group=self.process_group)
-            _lib.check(self._lib.nlc_planner_finish(h, stream), "nlc_planner_finish")
-            self._calls += 1
-            return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
+        return None
+
+    def _finish(self):
+        """Log-sum-exp combine of ``all_triples`` (G > 1) or of the own triple, ``U`` update, action."""
+        with torch.cuda.device(self.d):
+            _lib.check(self._lib.nlc_planner_finish(self._handle, _lib.current_stream_ptr()), "nlc_planner_finish")
+        self._calls += 1
+        return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
+
+    @property
+    def shard_triple(self):
+        return self._buf(_lib.BUF_TRIPLE, (2 + self.T * self.nu,))
+
+    @property
+    def all_triples(self):
+        return self._buf(_lib.BUF_ALL_TRIPLES, (self.G, 2 + self.T * self.nu))
 
     def reset(self):
         """Clear controller state after finishing a trial (``mppi_delay.py:226-230``)."""
-        self.U = self.noise_dist.sample((self.T,))
+        self.U = self._replicated(self.noise_dist.sample((self.T,)))
 
     def get_rollouts(self, state, num_rollouts=1):
-        """Nominal rollout of ``U`` (``mppi_delay.py:358-381``).  The reference passes a single action, not a
-        history window, to the dynamics here, which the delay closures cannot consume; this
-        implementation keeps the signature and raises."""
-        raise NotImplementedError("get_rollouts is incompatible with history-window dynamics in the reference itself")
+        """Nominal rollout of the planned sequence ``U`` (``mppi_delay.py:358-381``): ``states[:, t+1] =
+        F(states[:, t], u_scale * U[t])``, returns ``(num_rollouts, T, nx)``.
+
+        As in the reference, the dynamics receive a single ``(n, nu)`` action here, not a B-entry history window;
+        ``NeuralLaplaceModel.forward`` turns that into a window of length one (``w_nl.py:131-132``), so the encoder
+        sees the current action only.  The analytic delay dynamics index ``action[:, -(delay+1)]`` on that 2-D tensor
+        in the reference (``oracle.py:23``) - an action component, not a time step - so they raise here.
+        ``U[t].view(num_rollouts, -1)`` (``:377``) only has a meaning for ``num_rollouts == 1``; for more rollouts every
+        row gets the same action (what the reference's docstring describes)."""
+        if not isinstance(self.F, NLDynamics):
+            raise NotImplementedError("get_rollouts passes one action, not a history window: only the Neural Laplace "
+                                      "closure can consume it (oracle.py:23 indexes a window)")
+        n = int(num_rollouts)
+        state = torch.as_tensor(state).reshape(-1, self.nx)
+        if state.shape[0] == 1:
+            state = state.repeat(n, 1)
+        if state.shape[0] != n:
+            raise ValueError("state must be (nx) or (num_rollouts, nx)")
+        model = self.F.model
+        if model._cuda_device is None:
+            model._cuda_device = self.d
+        mh = model.set_prediction_time(self.F.dt)
+        U = self.U.to(device=self.d, dtype=torch.float32).reshape(self.T, self.nu)
+        hist = (float(self.u_scale) * U).reshape(1, self.T, self.nu).repeat(n, 1, 1).contiguous()  # B = 1: L = T
+        st = state.to(device=self.d, dtype=torch.float32).contiguous()
+        p = torch.empty((n, self.T, 2), dtype=torch.float32, device=self.d)
+        cost = torch.empty((n,), dtype=torch.float32, device=self.d)
+        states = torch.empty((n, self.T, self.nx), dtype=torch.float32, device=self.d)
+        ro = _lib.RolloutOpts()
+        ro.env, ro.state_constraint, ro.goal_x = _lib.ENV_IDS[self.running_cost.env_name], 0, 0.0
+        ro.dynamics, ro.delay, ro.dt = self.F.kind, 0, float(self.F.dt)
+        fp32 = _lib.MATH_MODES["fp32"]  # a handful of rows: the CUDA-core kernels (the tensor-core encoder needs B >= 2)
+        with torch.cuda.device(self.d):
+            stream = _lib.current_stream_ptr()
+            _lib.check(self._lib.nlc_encode_history(mh, hist.data_ptr(), n, self.T, 1, p.data_ptr(), fp32, stream), "nlc_encode_history")
+            _lib.check(self._lib.nlc_rollout_cost(mh, C.byref(ro), st.data_ptr(), 1, p.data_ptr(), hist.data_ptr(), None, n, self.T, 1,
+                                                  self.nu, cost.data_ptr(), states.data_ptr(), fp32, stream), "nlc_rollout_cost")
+        return states.to(self.dtype)

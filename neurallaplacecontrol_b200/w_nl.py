@@ -47,7 +47,7 @@ class _RepFuncParams(nn.Module):
 class NeuralLaplaceModel(nn.Module):
     def __init__(self, state_dim, action_dim, latent_dim, hidden_units=64, s_recon_terms=33, ilt_algorithm="fourier",
                  encode_obs_time=False, state_mean=None, state_std=None, action_mean=None, action_std=None,
-                 normalize=False, normalize_time=False, dt=0.05, device=None, math_mode="fp32"):
+                 normalize=False, normalize_time=False, dt=0.05, device=None, math_mode="tc_split3"):
         super().__init__()
         if ilt_algorithm != "fourier":
             raise NotImplementedError("only ilt_algorithm='fourier' is on this path (w_nl.py:86-88 'cme' is not)")

@@ -6,8 +6,10 @@ What is the reference's own code in these vectors: ``MPPIDelay`` (noise injected
 ``noise_dist.sample``, the one sampling call per ``command()``, ``mppi_delay.py:319``),
 ``NeuralLaplaceModel`` with its GRU encoder and representation MLP, the ``dynamics`` closure shape
 of ``mppi_with_model.py:103-122``, and ``oracle.py``'s analytic delayed dynamics.  What is NOT: the
-inverse Laplace transform (``oracle.ilt`` restatement, parity unpinned) and the reward formulas
-(``oracle.costs`` restatement; the env modules need ``gym``).
+inverse Laplace transform (``oracle.ilt`` restatement, parity unpinned).  The running cost is the
+reference env classes' own ``diff_obs_reward_`` / ``diff_ac_reward_`` (``oracle/ref_envs.py`` imports
+the env modules with placeholder ``gym`` / ``torchdiffeq`` modules); ``cost_pin.npz`` pins
+``oracle.costs`` against them.
 
 Weight families:
 * ``raw``        - the reference modules' own random init under ``torch.manual_seed(0)``.
@@ -25,7 +27,7 @@ import os
 import numpy as np
 import torch
 
-from . import costs, mppi, ref_harness
+from . import costs, mppi, ref_envs, ref_harness
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 PHI_BIAS_SHIFT = -4.0
@@ -66,7 +68,8 @@ def reference_plan(model, env, K, T, U_init, state, action_buffer, noise, n_call
         def dynamics(state, window):
             return state + model(state, window, ts_pred)
 
-    planner = MPPIDelay(dynamics, costs.running_cost(env), nx, mppi.noise_sigma_for(nu), num_samples=K,
+    # the reward is the reference env class's own diff_obs_reward_ / diff_ac_reward_ (oracle/ref_envs.py)
+    planner = MPPIDelay(dynamics, ref_envs.running_cost(env), nx, mppi.noise_sigma_for(nu), num_samples=K,
                         horizon=T, device="cpu", lambda_=1.0, u_min=torch.tensor(-act_high),
                         u_max=torch.tensor(act_high), u_scale=act_high, U_init=U_init.clone())
     out = None
@@ -81,6 +84,60 @@ def reference_plan(model, env, K, T, U_init, state, action_buffer, noise, n_call
                "U": planner.U, "action": action}
         buf, _ = mppi.get_action(buf, action, 1)
     return out
+
+
+def cost_pin():
+    """``cost_pin.npz``: the reference env classes' own reward arithmetic on seeded states/actions (every env, every
+    cartpole option of ``mppi_with_model.py:145-171``) - pins ``oracle.costs`` (tests/test_oracle_golden.py)."""
+    out = {}
+    g = torch.Generator().manual_seed(40)
+    for env in ENVS:
+        nx, nu = costs.ENV_DIMS[env]
+        short = env.split("-")[1]
+        s = torch.randn(256, nx, generator=g, dtype=torch.float64) * torch.tensor(costs.ENV_STATE_STD[env])
+        a = (torch.rand(256, nu, generator=g, dtype=torch.float64) * 2 - 1) * costs.ENV_ACT_HIGH[env]
+        out[f"{short}_state"], out[f"{short}_action"] = s, a
+        out[f"{short}_cost"] = ref_envs.running_cost(env)(s, a)
+        if env == "oderl-cartpole":
+            s2 = s.clone()
+            s2[:, 0] = s2[:, 0] * 0.2 - 0.8  # keep exp(10 err + 7) of the state-constraint variant finite and varied
+            out["cartpole_state_sc"] = s2
+            out["cartpole_cost_state_constraint"] = ref_envs.running_cost(env, state_constraint=True)(s2, a)
+            out["cartpole_cost_change_goal"] = ref_envs.running_cost(env, change_goal=True)(s, a)
+            out["cartpole_cost_change_goal_flipped"] = ref_envs.running_cost(env, change_goal=True, change_goal_flipped=True)(s, a)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "cost_pin.npz"), **_np(out))
+
+
+N_SPREAD = 64
+
+
+def full_size_plan(env, K, T, family, name):
+    """BASELINE configs 3 and 4 at their full K x H through the reference's own ``MPPIDelay`` + ``NeuralLaplaceModel``
+    (fp64, SURVEY 8d inputs: zero U / buffer, start state, ``injected_noise(seed=1)``), outputs trimmed:
+    every ``cost_total``, whole trajectories of ``N_SPREAD`` evenly spread samples, every final state (fp32 storage,
+    2^-24 relative: far inside the 1e-4 bound), the 64 largest ``omega`` with their indices, ``U`` and the action.
+    ``family``: ``cal`` = calibrated weights (trained-model operating range), ``raw`` = the reference modules' own
+    random init, whose rollouts saturate (|state| ~ 1e4, costs ~ 1e7..1e9, omega one-hot) and are chaotic."""
+    nx, nu = costs.ENV_DIMS[env]
+    model = ref_harness.build_reference_model(env, seed=0, s_recon_terms=S_TERMS, dt=DT)
+    if family == "cal":
+        model.load_state_dict(calibrate_({k: v.clone() for k, v in model.state_dict().items()}, nx))
+    out = reference_plan(model, env, K, T, torch.zeros(T, nu, dtype=torch.float64), START_STATE[env],
+                         torch.zeros(4, nu, dtype=torch.float64), injected_noise(K, T, nu, seed=1))
+    idx = torch.linspace(0, K - 1, N_SPREAD).round().long()
+    top = torch.topk(out["omega"], 64)
+    keep = {"spread_idx": idx, "states_spread": out["states"][idx], "cost_spread": out["cost_total"][idx],
+            "U": out["U"], "action": out["action"], "argmin": int(out["cost_total"].argmin()),
+            "noise_seed": 1, "phi_bias_shift": PHI_BIAS_SHIFT if family == "cal" else 0.0}
+    if family == "cal":
+        keep.update({"cost_total": out["cost_total"], "states_last": out["states"][:, -1].to(torch.float32),
+                     "omega_top": top.values, "omega_top_idx": top.indices})
+    # raw: the random-init dynamics are CHAOTIC (a 1e-16 perturbation grows ~6x per step: the fp64 oracle and the fp64
+    # reference, which differ only in summation order, are 1e-13 apart after step 0 and O(1e3) apart after step 29), so
+    # only the spread trajectories are kept; tests compare their first steps.
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **_np(keep))
+    print(f"  {name}: cost [{float(out['cost_total'].min()):.4g}, {float(out['cost_total'].max()):.4g}]"
+          f"  omega max {float(out['omega'].max()):.3g}  action {out['action'].tolist()}")
 
 
 def main():
@@ -202,10 +259,25 @@ def main():
             "states_first16": out["states"][:16], "states_last": out["states"][:, -1],
             "noise_seed": 1, "phi_bias_shift": PHI_BIAS_SHIFT}
     np.savez_compressed(os.path.join(GOLDEN_DIR, "plan_cfg1_pendulum_K1000_H20.npz"), **_np(keep))
+    cost_pin()
+    for env, K, T, name in (("oderl-cartpole", 8192, 30, "cfg3_cartpole_K8192_H30"),
+                            ("oderl-acrobot", 65536, 50, "cfg4_acrobot_K65536_H50")):
+        for family in ("cal", "raw"):
+            full_size_plan(env, K, T, family, f"plan_{name}_{family}")
     print("golden vectors written to", GOLDEN_DIR)
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f"  {f}  {os.path.getsize(os.path.join(GOLDEN_DIR, f)) / 1024:.0f} KiB")
 
 
+def main_full_size_only():
+    torch.set_grad_enabled(False)
+    for env, K, T, name in (("oderl-cartpole", 8192, 30, "cfg3_cartpole_K8192_H30"),
+                            ("oderl-acrobot", 65536, 50, "cfg4_acrobot_K65536_H50")):
+        for family in ("cal", "raw"):
+            full_size_plan(env, K, T, family, f"plan_{name}_{family}")
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+
+    main_full_size_only() if "--full-size-only" in sys.argv else main()

@@ -51,3 +51,34 @@ def action_relerr(ref_action, got_action, ref_U, u_scale):
     got = torch.as_tensor(got_action).detach().cpu().to(torch.float64).reshape(-1)
     scale = float(torch.as_tensor(ref_U).detach().cpu().to(torch.float64).abs().max()) * float(u_scale)
     return (ref_action - got).abs().max().item() / max(scale, 1e-30)
+
+
+def relerr_per_channel(ref, got):
+    """max over the LAST axis' channels c of  max |ref_c - got_c| / max |ref_c|:  every state channel is held to the bound
+    against its own magnitude (cos/sin channels of size 1 are not measured against velocities of size 10)."""
+    ref = torch.as_tensor(ref).detach().cpu().to(torch.float64)
+    got = torch.as_tensor(got).detach().cpu().to(torch.float64).reshape(ref.shape)
+    C = ref.shape[-1]
+    r, g = ref.reshape(-1, C), got.reshape(-1, C)
+    denom = r.abs().amax(dim=0).clamp_min(1e-30)
+    return float(((r - g).abs().amax(dim=0) / denom).max())
+
+
+FULL_SIZE = {  # BASELINE configs 3 and 4 (SURVEY 8d inputs)
+    "cfg3": ("oderl-cartpole", 8192, 30, "plan_cfg3_cartpole_K8192_H30"),
+    "cfg4": ("oderl-acrobot", 65536, 50, "plan_cfg4_acrobot_K65536_H50"),
+}
+START_STATE = {
+    "oderl-pendulum": [-1.0, 1.2246467991473532e-16, 1.0],
+    "oderl-cartpole": [0.0, 0.0, -1.0, 1.2246467991473532e-16, 0.0],
+    "oderl-acrobot": [1.0, 0.0, 1.0, 0.0, 0.0, 0.0],
+}
+
+
+def injected_noise(K, T, nu, seed=1, sigma=1.0):
+    """The SURVEY 8d noise tensor: randn(K, T, nu; seed) @ chol(Sigma)^T in fp64 (same as oracle/gen_golden.py)."""
+    from oracle import mppi
+
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(K, T, nu, generator=g, dtype=torch.float64)
+    return z @ torch.linalg.cholesky(mppi.noise_sigma_for(nu, sigma)).T
