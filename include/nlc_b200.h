@@ -235,6 +235,12 @@ int nlc_planner_finish(nlc_planner_t p, void* stream);
  * NLC_NO_GRAPH=1 in the environment keeps direct launches.                                          */
 int nlc_planner_step(nlc_planner_t p, void* stream);
 
+/* Measurement: the same control step as DIRECT launches with CUDA events at the stage boundaries, so that the kernels are
+ * timed inside the step (back to back, warm L2) - the bracket the reference puts around command()
+ * (mppi_with_model.py:257-259) split by stage.  ms_out[4] = {perturb, history encoder, rollout + cost, softmax update}.
+ * Single shard; synchronises the stream.                                                            */
+int nlc_planner_step_profile(nlc_planner_t p, float* ms_out, void* stream);
+
 /* MPPIDelay.command (mppi_delay.py:193-224) end to end with HOST buffers, single shard: copies the
  * state [nx] and action_buffer [B][nu] (fp64, as the reference's callers hold them) to the device,
  * runs both phases, copies the action [nu] back and synchronises the stream.  Without injected noise the whole step,

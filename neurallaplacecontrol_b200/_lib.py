@@ -91,6 +91,7 @@ SIGNATURES = {
     "nlc_planner_rollout": (C.c_int, [C.c_void_p, _fp, C.c_int, _fp, _fp, C.c_void_p]),
     "nlc_planner_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nlc_planner_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nlc_planner_step_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "nlc_planner_command_host": (C.c_int, [C.c_void_p, _dp, _dp, _fp, _dp, C.c_void_p]),
     "nlc_batch_planner_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(PlannerDesc), C.c_int,
                                            C.POINTER(C.c_uint64), C.c_int]),

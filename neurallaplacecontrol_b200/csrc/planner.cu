@@ -179,27 +179,61 @@ extern "C" int nlc_planner_buffer(nlc_planner_t p, int which, void** dev_ptr, in
   return NLC_OK;
 }
 
-extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int state_per_sample,
-                                   const float* action_buffer_dev, const float* noise_in_dev, void* stream) {
-  NLC_REQUIRE(p && state_dev && action_buffer_dev, NLC_ERR_ARG, "nlc_planner_rollout: null argument");
+// stages 1-3 + the shard-local half of stage 4; `ev` (optional, 4 events) receives the stage boundaries:
+// ev[0] start | perturb | ev[1] | encoder | ev[2] | rollout + cost | ev[3] | (softmax follows)
+static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int state_per_sample, const float* action_buffer_dev,
+                                const float* noise_in_dev, void* stream, cudaEvent_t* ev) {
   const nlc_mppi_params& mp = p->d.mppi;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   NLC_CUDA_OK(cudaSetDevice(p->device));
   int rc = planner_check_model(p);
   if (rc != NLC_OK) return rc;
+  if (ev) NLC_CUDA_OK(cudaEventRecord(ev[0], s));
   rc = perturb_launch(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, 0, p->call_ctr, action_buffer_dev, p->perturbed,
-                          p->noise, p->hist, p->actions, p->pert_cost, stream);
+                      p->noise, p->hist, p->actions, p->pert_cost, stream);
   if (rc != NLC_OK) return rc;
-  rc = launch_bump_counter(p->call_ctr, static_cast<cudaStream_t>(stream));  // the next control step draws fresh samples
+  rc = launch_bump_counter(p->call_ctr, s);  // the next control step draws fresh samples
   if (rc != NLC_OK) return rc;
   p->calls++;
+  if (ev) NLC_CUDA_OK(cudaEventRecord(ev[1], s));
   if (p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
     rc = nlc_encode_history(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, stream);
     if (rc != NLC_OK) return rc;
   }
+  if (ev) NLC_CUDA_OK(cudaEventRecord(ev[2], s));
   rc = nlc_rollout_cost(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,
                         mp.nu, p->cost_total, p->states, p->d.math_mode, stream);
   if (rc != NLC_OK) return rc;
+  if (ev) NLC_CUDA_OK(cudaEventRecord(ev[3], s));
   return nlc_softmax_partial(p->cost_total, p->noise, mp.K, mp.T, mp.nu, mp.lambda_, p->triple, p->weights, p->softmax_ws, stream);
+}
+
+extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int state_per_sample,
+                                   const float* action_buffer_dev, const float* noise_in_dev, void* stream) {
+  NLC_REQUIRE(p && state_dev && action_buffer_dev, NLC_ERR_ARG, "nlc_planner_rollout: null argument");
+  return planner_rollout_impl(p, state_dev, state_per_sample, action_buffer_dev, noise_in_dev, stream, nullptr);
+}
+
+// Measurement entry point: one control step on the planner's own input buffers as DIRECT launches (no graph) with CUDA
+// events at the stage boundaries, so the kernels are timed inside the step (warm L2, back to back) rather than alone.
+// ms_out[0..3] = perturb, history encoder, rollout + cost, softmax update (partial + combine).  Synchronises the stream.
+extern "C" int nlc_planner_step_profile(nlc_planner_t p, float* ms_out, void* stream) {
+  NLC_REQUIRE(p && ms_out, NLC_ERR_ARG, "nlc_planner_step_profile: null argument");
+  NLC_REQUIRE(p->d.n_shards == 1, NLC_ERR_UNSUPPORTED, "nlc_planner_step_profile is a single-shard entry point");
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t ev[5];
+  for (auto& e : ev) NLC_CUDA_OK(cudaEventCreate(&e));
+  int rc = planner_rollout_impl(p, p->state_in, 0, p->abuf_in, nullptr, stream, ev);
+  if (rc == NLC_OK) rc = nlc_planner_finish(p, stream);
+  if (rc == NLC_OK && cudaEventRecord(ev[4], s) != cudaSuccess) rc = NLC_ERR_CUDA;
+  if (rc == NLC_OK && cudaEventSynchronize(ev[4]) != cudaSuccess) rc = NLC_ERR_CUDA;
+  if (rc == NLC_OK)
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]) != cudaSuccess) rc = NLC_ERR_CUDA;
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc == NLC_ERR_CUDA) { set_error("nlc_planner_step_profile: CUDA event error: %s", cudaGetErrorString(cudaGetLastError())); }
+  return rc;
 }
 
 extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {

@@ -400,7 +400,11 @@ def test_full_size_sharded_plan_equals_unsharded(cfg, G):
     env, K, T, nu, ah, g, p1 = _full_size_planner(cfg, "cal")
     p1.noise_dist.sample = lambda shape: noise
     a1 = p1.command(state, buf)
-    assert torch.equal(p1.cost_total, cost)
+    # cfg3: shards and the whole plan run the same (one-tile) rollout kernel - bit-identical costs; cfg4: 8192-sample shards take
+    # the one-tile form, the 65536-sample plan the ping-pong form (L3 in two column halves): same arithmetic, other summation order
+    if cfg == "cfg3":
+        assert torch.equal(p1.cost_total, cost)
+    assert relerr(p1.cost_total, cost) < 2e-6
     assert relerr(p1.U, planners[0].U) < 1e-5 and action_relerr(a1, actions[0], p1.U, float(ah)) < 1e-5
 
 
