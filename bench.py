@@ -414,8 +414,15 @@ def sharded_vs_unsharded(ctx, env, K, H):
     U_sh = sharded.U.double().clone()
     res = torch.zeros(3, dtype=torch.float64, device=ctx.dev)
     if ctx.rank == 0:
+        # the whole plan through the same rollout kernel form as the shards (a 65536-sample plan would pick the ping-pong
+        # form on its own: same arithmetic, other summation order), so that per-sample costs are bit-identical and the
+        # comparison isolates what sharding changes: the order of stage 4's sums
+        pp_shard = (sharded.K_local + 127) // 128 > N_SM
+        os.environ["NLC_ROLLOUT_TILES"] = "3" if pp_shard else "1"
         _, _, whole = make_planner(ctx, env, K, H, group=None, seed=99)
         a1 = whole.command(state_dev, buf_dev).double()
+        torch.cuda.synchronize()
+        del os.environ["NLC_ROLLOUT_TILES"]
         U1 = whole.U.double()
         scale = max(float(U1.abs().max()), 1e-30)
         res[0] = (U1 - U_sh).abs().max() / scale
