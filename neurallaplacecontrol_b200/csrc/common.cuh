@@ -129,6 +129,9 @@ struct nlc_model_s {
   // nlc_model_destroy on a model that is still referenced only marks it (freed with the last planner)
   int refs;
   bool destroy_requested;
+  // layer 1 of the GRU: max over the (r, z) rows of log2(e) (|W_ih1 row|_1 + |W_hh1 row|_1 + |b_ih1 + b_hh1|) < 60 - both inputs
+  // are hidden states in (-1, 1), so the tensor-core encoder's exponent clamps are provably idle for that layer
+  bool enc_l1_bounded;
 };
 
 namespace nlc {

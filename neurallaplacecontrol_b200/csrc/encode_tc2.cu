@@ -81,7 +81,11 @@ __device__ __forceinline__ void ldtm8p(uint32_t taddr, f2_t (&v)[4]) {
 constexpr int kGateTanhApprox = 9;
 __device__ __forceinline__ float mufu_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-template <int RZ, int NN>
+//   kClampRZ: clamp the (r, z) exponents at 60 so that the shared-reciprocal product (1 + 2^pr)(1 + 2^pz) stays finite.  Not
+//   needed (and compiled out) when the pre-activations are provably inside +-60 - layer 1, whose inputs are hidden states in
+//   (-1, 1): the bound is the L1 norm of the weight rows, checked when the model is packed (model.cu: enc_l1_bounded).
+//   The n exponent needs no clamp with the MUFU reciprocal: 2^x = inf gives rcp = 0, n = -1, h - n = h + 1, all exact limits.
+template <int RZ, int NN, bool kClampRZ>
 __device__ __forceinline__ f2_t gru_pair(f2_t pr, f2_t pz, f2_t gi, f2_t gh, f2_t h_old) {
   if (RZ == kGateTanhApprox) {
     const f2_t c = pk2(-0.34657359027997264f, -0.34657359027997264f);  // -1 / (2 log2 e)
@@ -99,13 +103,15 @@ __device__ __forceinline__ f2_t gru_pair(f2_t pr, f2_t pz, f2_t gi, f2_t gh, f2_
   upk2(pr, a0, a1);
   upk2(pz, b0, b1);
   const f2_t one = pk2(1.0f, 1.0f);
-  const f2_t da = add2(pk2(mufu_ex2(fminf(a0, 60.0f)), mufu_ex2(fminf(a1, 60.0f))), one);
-  const f2_t db = add2(pk2(mufu_ex2(fminf(b0, 60.0f)), mufu_ex2(fminf(b1, 60.0f))), one);
+  if (kClampRZ) { a0 = fminf(a0, 60.0f); a1 = fminf(a1, 60.0f); b0 = fminf(b0, 60.0f); b1 = fminf(b1, 60.0f); }
+  const f2_t da = add2(pk2(mufu_ex2(a0), mufu_ex2(a1)), one);
+  const f2_t db = add2(pk2(mufu_ex2(b0), mufu_ex2(b1)), one);
   const f2_t inv = rcp2<RZ>(mul2(da, db));
   const f2_t r = mul2(db, inv), z = mul2(da, inv);
   float x0, x1;
   upk2(fma2(r, gh, gi), x0, x1);
-  const f2_t dn = add2(pk2(mufu_ex2(fminf(x0, 120.0f)), mufu_ex2(fminf(x1, 120.0f))), one);
+  if (NN != 0) { x0 = fminf(x0, 120.0f); x1 = fminf(x1, 120.0f); }  // the Newton reciprocal needs a finite argument
+  const f2_t dn = add2(pk2(mufu_ex2(x0), mufu_ex2(x1)), one);
   const f2_t invn = rcp2<NN>(dn);
   const f2_t n = fma2(pk2(2.0f, 2.0f), invn, pk2(-1.0f, -1.0f));
   const f2_t hm = fma2(pk2(-2.0f, -2.0f), invn, add2(h_old, one));  // h - n = (h + 1) - 2 invn
@@ -151,7 +157,10 @@ __device__ __forceinline__ void issue_gemm192(uint32_t d_tmem, uint32_t a_hi, ui
   }
 }
 
-constexpr int kThreadsAll = kThreads + 32;        // 16 epilogue warps + the MMA warp
+constexpr int kThreadsAll = kThreads + 32;        // 16 epilogue warps + the MMA warp: the participants of the named barriers
+// The CTA is launched with the MMA warp's whole register group (setmaxnreg works on groups of 4 warps): 20 warps at 96
+// registers, re-balanced to 112 for the 16 epilogue warps and 64 for the MMA group (16 x 112 + 4 x 64 = the whole file).
+constexpr int kThreadsLaunch = kThreads + 128;
 constexpr int kBarH0 = 2, kBarH1 = 3;             // named barriers: layer-0 / layer-1 operands published (1: output exchange)
 // Layer 0's input projection and biases ride on the tensor cores as one extra K block of the layer-0 state operand:
 //   A block (per window)  [x0_hi x0_lo x0_hi | x1_hi x1_lo x1_hi | 1 1 | 0 ...]      (16 halves)
@@ -174,12 +183,12 @@ struct Smem {
   alignas(128) unsigned char h1[2][kOpBytes];
   alignas(16) float c[kC2Count];
   alignas(16) float pout[3][kRows * 2];
-  alignas(8) uint64_t bar_a, bar_b;
+  alignas(8) uint64_t bar_a, bar_b, bar_h0;  // MMA A / MMA B complete; the part of MMA B that reads the layer-0 state image complete
   uint32_t tmem_base;
 };
 
-template <bool kSplit3, int GIN, int RZ, int NN>
-__global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
+template <bool kSplit3, int GIN, int RZ, int NN, bool kClamp1, bool kTrace = false>
+__global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -188,25 +197,25 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   const int ubase = 16 * grp;      // first of the 16 hidden units (per layer) this thread owns
   const int B = a.B;
   int tstep = 0;
-  auto mark = [&](int ev) {
-    if (a.trace && blockIdx.x == 0 && lane == 0 && tstep < 32) a.trace[(tstep * 16 + warp) * 8 + ev] = clock64();
+  auto mark = [&](int ev) {  // compiled in for tools/trace_encoder.py only: the tests cost instructions in the hot loop
+    if (kTrace && a.trace && blockIdx.x == 0 && lane == 0 && tstep < 32) a.trace[(tstep * 16 + warp) * 8 + ev] = clock64();
   };
 
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.m.enc2_w);
     uint4* dst = reinterpret_cast<uint4*>(&s.w[0][0][0]);
-    for (int i = tid; i < (int)(3 * 2 * kWBytes / 16); i += kThreadsAll) dst[i] = __ldg(src + i);
+    for (int i = tid; i < (int)(3 * 2 * kWBytes / 16); i += kThreadsLaunch) dst[i] = __ldg(src + i);
     const uint4* sx = reinterpret_cast<const uint4*>(a.m.enc2_x);
-    for (int i = tid; i < (int)(2 * (kWxBytes + 128) / 16); i += kThreadsAll) {
+    for (int i = tid; i < (int)(2 * (kWxBytes + 128) / 16); i += kThreadsLaunch) {
       const int l = i / (int)((kWxBytes + 128) / 16), j = i - l * (int)((kWxBytes + 128) / 16);
       reinterpret_cast<uint4*>(s.wx[l])[j] = j < (int)(kWxBytes / 16) ? __ldg(sx + l * (int)(kWxBytes / 16) + j) : make_uint4(0u, 0u, 0u, 0u);
     }
     uint4* dz = reinterpret_cast<uint4*>(s.h0_hi);  // the second half of the [x | 1] block stays zero for ever
-    for (int i = tid; i < (int)(kH0HiBytes / 16); i += kThreadsAll) dz[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < 128; i += kThreadsAll) s.c[kC2Wout + i] = a.m.enc2_c[kE2Wout + i];
+    for (int i = tid; i < (int)(kH0HiBytes / 16); i += kThreadsLaunch) dz[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 128; i += kThreadsLaunch) s.c[kC2Wout + i] = a.m.enc2_c[kE2Wout + i];
     if (tid < 2) s.c[kC2Bout + tid] = a.m.enc2_c[kE2Bout + tid];
     if (tid == 0) {
-      mbar_init(&s.bar_a, 1); mbar_init(&s.bar_b, 1);
+      mbar_init(&s.bar_a, 1); mbar_init(&s.bar_b, 1); mbar_init(&s.bar_h0, 1);
       mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&s.tmem_base, kTmemCols);
@@ -227,7 +236,12 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   const uint32_t w_x0 = smem_u32(s.wx[0]), w_x1 = smem_u32(s.wx[1]);
   const long long n_tiles = (a.rows + kRows - 1) / kRows;
 
-  if (warp == 16) {
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  }
+  if (warp > 16) {
+    // the rest of the MMA warp's register group: nothing to do
+  } else if (warp == 16) {
     // =====================================  MMA warp  =====================================
     // mirrors the epilogue warps' publication order: h0 + the next cell's [x | 1] block (-> layer-0 product of the next
     // cell), then h1 / D1 re-armed (-> layer-1 product of the next cell: input part from h0, hidden part from h1)
@@ -254,6 +268,9 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
         // biases first (accumulate = 0 over all of D1 = [in | r | z | hn]): the 1-columns of the [x | 1] block
         mma_f16_ss(tmem + kColD1, smem_desc(a_h0_hi + 8 * kLbo, kLbo, kSboX), smem_desc(w_x1, kLbo, 128), idesc_f16_f32(kRows, 256), 0u);
         issue_gemm192<kSplit3>(tmem + kColD1, a_h0_hi, kSboX, a_h0_lo, kSbo, w_ih1_hi, w_ih1_lo);
+        // everything that reads the layer-0 state image is issued: the layer-0 epilogue may overwrite it as soon as THIS much
+        // has completed (half a product earlier than bar_b), so its operand stores interleave with its gate math
+        mma_commit(&s.bar_h0);
         if (with_h1) issue_gemm192<kSplit3>(tmem + kColD1 + 64, a_h1_hi, kSbo, a_h1_lo, kSbo, w_hh1_hi, w_hh1_lo);
         mma_commit(&s.bar_b);
       }
@@ -282,13 +299,16 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     }
   } else {
   // =====================================  epilogue warps  =====================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
   float amean[GIN], ainv[GIN];
 #pragma unroll
   for (int v = 0; v < GIN; ++v) { amean[v] = a.m.act_mean[v]; ainv[v] = a.m.act_inv_std[v]; }
 
-  uint32_t n_a = 0, n_b = 0;    // waits completed on bar_a / bar_b
+  uint32_t n_a = 0, n_b = 0, n_h0 = 0;  // waits completed on bar_a / bar_b / bar_h0
   f2_t h0r[8], h1r[8];
-  float xn[GIN] = {};           // normalised window entry of the FOLLOWING layer-0 cell (threads with grp == 0 feed the operand)
+  // raw window entry of the FOLLOWING layer-0 cell (threads with grp == 0 feed the operand).  It is normalised only when it is
+  // written into the operand, a whole gate epilogue after the load was issued: nothing waits for global memory
+  float xraw[GIN] = {};
 
   // hist offset of this thread's window in a tile (one integer division per tile, not per cell)
   auto window_base = [&](long long tile_) -> size_t {
@@ -308,8 +328,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
 #pragma unroll
     for (int v = 0; v < GIN; ++v) {
       // channels beyond hist_ch: the time channel of encode_obs_time (mppi_with_model.py:110-119)
-      const float x = v < a.hist_ch ? __ldg(src + v) : (float)(B - 1 - j);
-      xn[v] = (x - amean[v]) * ainv[v];  // w_nl.py:121
+      xraw[v] = v < a.hist_ch ? __ldg(src + v) : (float)(B - 1 - j);
     }
   };
   // [x_hi x_lo x_hi | ... | 1 1] -> the extra K block of this window's row in the layer-0 state image
@@ -320,8 +339,9 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     for (int i = 0; i < 8; ++i) hv[i] = __float2half_rn(0.0f);
 #pragma unroll
     for (int v = 0; v < GIN; ++v) {
-      const __half hi = __float2half_rn(xn[v]);
-      const __half lo = __float2half_rn(xn[v] - __half2float(hi));
+      const float xn = (xraw[v] - amean[v]) * ainv[v];  // w_nl.py:121
+      const __half hi = __float2half_rn(xn);
+      const __half lo = __float2half_rn(xn - __half2float(hi));
       hv[3 * v] = hi; hv[3 * v + 1] = lo; hv[3 * v + 2] = hi;
     }
     hv[6] = __float2half_rn(1.0f); hv[7] = __float2half_rn(1.0f);
@@ -330,8 +350,15 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     for (int i = 0; i < 4; ++i) { const __half2 p2 = __halves2half2(hv[2 * i], hv[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&p2); }
     *reinterpret_cast<uint4*>(s.h0_hi + (uint32_t)(row >> 3) * kSboX + 8 * kLbo + (uint32_t)(row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   };
-  // layer-0 cell: complete pre-activations come out of D0 = [r | z | hn | in]
-  auto cell_a = [&](bool from_zero) {
+  // layer-0 cell: complete pre-activations come out of D0 = [r | z | hn | in].  With `store`, each 8-unit chunk goes into the
+  // layer-0 state image as soon as its gates are done (the conversion and the stores overlap the next chunk's MUFU work);
+  // the image is free once the part of the previous MMA B that reads it has completed (bar_h0), which `wait_h0` waits for
+  // before the first store.
+  auto cell_a = [&](bool from_zero, bool store, bool wait_h0) {
+    if (from_zero) {  // cell 0 of a window: h = 0 (one uniform branch instead of a select per use)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h0r[i] = 0ull;
+    }
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int u0 = ubase + 8 * c;
@@ -343,19 +370,18 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        h0r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], from_zero ? 0ull : h0r[4 * c + i]);
+        h0r[4 * c + i] = gru_pair<RZ, NN, true>(gr[i], gz[i], gn[i], gh[i], h0r[4 * c + i]);
+      }
+      if (store) {
+        if (c == 0 && wait_h0) { mbar_wait_sleep(&s.bar_h0, n_h0 & 1); ++n_h0; }
+        const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h0r[4 * c]);
+        store_operand8<kSplit3>(s.h0_hi, kSboX, s.h0_lo, kSbo, row, u0, hc);
       }
     }
   };
-  // publish h0r as the A operand (and, for grp 0, the following cell's [x | 1] block); the MMA warp takes it from there
-  auto publish_h0 = [&](bool with_h0, bool with_x) {
-    if (with_h0) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h0r[4 * c]);
-        store_operand8<kSplit3>(s.h0_hi, kSboX, s.h0_lo, kSbo, row, ubase + 8 * c, hc);
-      }
-    }
+  // the A operand of the next products is in shared memory (and, for grp 0, the following cell's [x | 1] block is added
+  // here): make it visible to the tensor core's proxy and tell the MMA warp
+  auto publish_h0 = [&](bool with_x) {
     if (with_x) write_x();
     fence_proxy_async_smem();
     fence_before_sync();
@@ -363,14 +389,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   };
   // after the layer-1 epilogue: D1 read (and h1 stored when `with_h1`)
   auto publish_h1 = [&](bool with_h1) {
-    if (with_h1) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h1r[4 * c]);
-        store_operand8<kSplit3>(s.h1[0], kSbo, s.h1[1], kSbo, row, ubase + 8 * c, hc);
-      }
-      fence_proxy_async_smem();
-    }
+    if (with_h1) fence_proxy_async_smem();
     fence_before_sync();
     asm volatile("bar.arrive %0, %1;" ::"r"(kBarH1), "n"(kThreadsAll) : "memory");
   };
@@ -379,12 +398,12 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   if ((long long)blockIdx.x < n_tiles) {
     base_cur = window_base(blockIdx.x);
     fetch_x(false, 0);
-    publish_h0(false, true);
+    publish_h0(true);
     fetch_x(false, 1);
     mbar_wait_sleep(&s.bar_a, n_a & 1); ++n_a;
     fence_after_sync();
-    cell_a(true);
-    publish_h0(true, true);
+    cell_a(true, true, false);  // nothing has read the state image yet
+    publish_h0(true);
     publish_h1(false);  // nothing of layer 1 exists yet: the input part of B(0) can go
   }
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -398,6 +417,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       // the cell after that one: its window entry is fetched now and joins the operand at the publication below
       const bool following = st + 2 < B || st + 1 == B || (st + 2 == B && has_next);
       if (a_slot) {
+        // the load is consumed at the publication below, after this cell's gate math
         if (st + 2 < B) fetch_x(false, st + 2);
         else if (st + 1 == B) fetch_x(true, 1);
         else if (has_next) fetch_x(true, 0);
@@ -405,16 +425,20 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
         mbar_wait_sleep(&s.bar_a, n_a & 1); ++n_a;
         fence_after_sync();
         mark(1);
-        cell_a(st + 1 == B);
+        // MMA B(st) reads the state image this cell overwrites: cell_a waits for that part of it (bar_h0) before its first store
+        cell_a(st + 1 == B, true, true);
+        mark(2);
+        publish_h0(following);
+        mark(3);
       }
-      // MMA B(st) reads the h0 image: wait for its commit before overwriting (it also gates the epilogue below)
-      mark(2);
+      // ======== layer-1 epilogue B(st)  ||  MMA A ========
+      if (st == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h1r[i] = 0ull;
+      }
       mbar_wait_sleep(&s.bar_b, n_b & 1); ++n_b;
       fence_after_sync();
-      mark(3);
-      if (a_slot) publish_h0(true, following);
       mark(4);
-      // ======== layer-1 epilogue B(st)  ||  MMA A ========
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int u0 = ubase + 8 * c;
@@ -426,7 +450,11 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          h1r[4 * c + i] = gru_pair<RZ, NN>(gr[i], gz[i], gn[i], gh[i], st > 0 ? h1r[4 * c + i] : 0ull);
+          h1r[4 * c + i] = gru_pair<RZ, NN, kClamp1>(gr[i], gz[i], gn[i], gh[i], h1r[4 * c + i]);
+        }
+        if (st + 1 < B) {  // MMA B(st), the last reader of the h1 image, has completed (bar_b above): store chunk by chunk
+          const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h1r[4 * c]);
+          store_operand8<kSplit3>(s.h1[0], kSbo, s.h1[1], kSbo, row, u0, hc);
         }
       }
       mark(5);
@@ -494,14 +522,21 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   // NLC_ENC_RCP=<rz><nn> (digits 0 or 3) overrides the fp32-class choice for measurements.
   static const int rcp_sel = [] { const char* e = getenv("NLC_ENC_RCP"); return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 30; }();
   void (*kern)(Args);
-  if (!split3) kern = m->gin == 1 ? encode_tc2_kernel<false, 1, kGateTanhApprox, 0> : encode_tc2_kernel<false, 2, kGateTanhApprox, 0>;
-  else if (rcp_sel == 0) kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 0, 0> : encode_tc2_kernel<true, 2, 0, 0>;
-  else if (rcp_sel == 33) kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 3, 3> : encode_tc2_kernel<true, 2, 3, 3>;
-  else kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 3, 0> : encode_tc2_kernel<true, 2, 3, 0>;
+  // layer-1 (r, z) clamps are compiled out when the packed weights prove |pre-activation| * log2(e) < 60 (model.cu)
+  const bool c1 = !m->enc_l1_bounded;
+#define NLC_ENC_PICK(S3, RZ_, NN_) \
+  (m->gin == 1 ? (c1 ? encode_tc2_kernel<S3, 1, RZ_, NN_, true> : encode_tc2_kernel<S3, 1, RZ_, NN_, false>) \
+               : (c1 ? encode_tc2_kernel<S3, 2, RZ_, NN_, true> : encode_tc2_kernel<S3, 2, RZ_, NN_, false>))
+  if (!split3) kern = m->gin == 1 ? encode_tc2_kernel<false, 1, kGateTanhApprox, 0, true> : encode_tc2_kernel<false, 2, kGateTanhApprox, 0, true>;
+  else if (rcp_sel == 0) kern = NLC_ENC_PICK(true, 0, 0);
+  else if (rcp_sel == 33) kern = NLC_ENC_PICK(true, 3, 3);
+  else kern = NLC_ENC_PICK(true, 3, 0);
+#undef NLC_ENC_PICK
+  if (a.trace && split3) kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 3, 0, true, true> : encode_tc2_kernel<true, 2, 3, 0, true, true>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long n_tiles = (a.rows + kRows - 1) / kRows;
   const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
-  kern<<<grid, kThreadsAll, smem, stream>>>(a);
+  kern<<<grid, kThreadsLaunch, smem, stream>>>(a);
   NLC_LAUNCH_OK("encode_tc2_kernel");
   return NLC_OK;
 }

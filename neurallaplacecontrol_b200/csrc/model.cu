@@ -189,6 +189,15 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   m->device = device; m->nx = nx; m->nu = nu; m->gin = gin; m->Hm = Hm; m->Hg = Hg; m->S = S; m->N3 = N3; m->N3p = N3p; m->N3t = N3t;
   m->normalize = d->normalize; m->normalize_time = d->normalize_time; m->encode_obs_time = d->encode_obs_time;
   m->dt = d->dt; m->arena = nullptr; m->refs = 0; m->destroy_requested = false;
+  {
+    double worst = 0.0;
+    for (int g = 0; g < 2 * Hg; ++g) {  // PyTorch gate order r, z, n: rows [0, 2 Hg) are r and z
+      double acc = fabs(d->gru_b_ih_l1[g] + d->gru_b_hh_l1[g]);
+      for (int k = 0; k < Hg; ++k) acc += fabs(d->gru_w_ih_l1[(size_t)g * Hg + k]) + fabs(d->gru_w_hh_l1[(size_t)g * Hg + k]);
+      worst = acc > worst ? acc : worst;
+    }
+    m->enc_l1_bounded = worst * 1.4426950408889634 < 59.0;  // one unit of slack for the fp16 split and fp32 accumulation
+  }
 
   Arena A;
   auto put = [&](size_t off, size_t i, double v) { A.data[off + i] = (float)v; };
