@@ -241,6 +241,25 @@ int nlc_planner_step(nlc_planner_t p, void* stream);
  * Single shard; synchronises the stream.                                                            */
 int nlc_planner_step_profile(nlc_planner_t p, float* ms_out, void* stream);
 
+/* Plans within half a wave of 128-sample tiles run their history encoder BESIDE the rollout kernel (the sequential rollout
+ * leaves most SMs idle): *overlapped = 1 if this planner does.  *status = 1 if, in the last control step, the rollout gave
+ * up polling for the encoder's output (~4 s: the two kernels were not co-resident - a serialising tool, a shared GPU;
+ * NLC_NO_OVERLAP=1 in the environment keeps the plain sequence); the step's results are then invalid.  Synchronises
+ * the device.                                                                                       */
+int nlc_planner_overlap_status(nlc_planner_t p, int* overlapped, int* status);
+
+/* K sharded over the GPUs of ONE node: exchange of the per-shard (beta, eta, W) triples on the device, without
+ * a collective library.  Every shard owns a mailbox in its HBM; nlc_planner_exchange_export returns its CUDA IPC handle
+ * (64 bytes, for peers in other processes) and/or its device pointer (for peers in the same process).  After
+ * nlc_planner_exchange_connect - kind 0: `data` = n_shards IPC handles of 64 bytes in shard order, kind 1: n_shards device
+ * pointers; the own slot is ignored - nlc_planner_rollout ends by storing the triple into every peer's mailbox over
+ * NVLink and nlc_planner_finish polls the own mailbox for the n_shards triples of the step before it combines; nothing
+ * crosses the host, and nlc_planner_step replays the whole sharded control step as one CUDA graph.  All shards must take
+ * the same number of control steps.  *status = 2 after a poll gave up (~8 s) because a peer never published.       */
+int nlc_planner_exchange_export(nlc_planner_t p, void* ipc_handle_64, void** local_ptr);
+int nlc_planner_exchange_connect(nlc_planner_t p, int kind, const void* data);
+int nlc_planner_exchange_status(nlc_planner_t p, int* connected, int* status);
+
 /* MPPIDelay.command (mppi_delay.py:193-224) end to end with HOST buffers, single shard: copies the
  * state [nx] and action_buffer [B][nu] (fp64, as the reference's callers hold them) to the device,
  * runs both phases, copies the action [nu] back and synchronises the stream.  Without injected noise the whole step,

@@ -92,6 +92,10 @@ SIGNATURES = {
     "nlc_planner_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nlc_planner_step": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nlc_planner_step_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
+    "nlc_planner_overlap_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nlc_planner_exchange_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nlc_planner_exchange_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nlc_planner_exchange_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nlc_planner_command_host": (C.c_int, [C.c_void_p, _dp, _dp, _fp, _dp, C.c_void_p]),
     "nlc_batch_planner_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(PlannerDesc), C.c_int,
                                            C.POINTER(C.c_uint64), C.c_int]),

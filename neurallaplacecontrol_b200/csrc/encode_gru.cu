@@ -207,7 +207,8 @@ int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, in
   return NLC_OK;
 }
 
-int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream);
+int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream,
+                      unsigned int* ready = nullptr, int max_ctas = 0);
 
 // hist_ch: channels stored per history entry (model gin for nlc_model_forward, whose caller supplies the time channel
 // like the reference's forward; action_dim on the planner path, where encode_obs_time's channel is synthesised)
@@ -231,6 +232,19 @@ int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K
       return launch_encode_tc2(m, hist_dev, hist_ch, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s);
     default: set_error("nlc_encode_history: unknown math_mode %d", math_mode); return NLC_ERR_ARG;
   }
+}
+
+// Does (model, window length, math mode) run on the tcgen05 encoder?  (planner.cu: only then can the encoder publish per-step
+// readiness to a rollout kernel running beside it.)
+bool encoder_is_tensor_core(nlc_model_t m, int B, int math_mode) {
+  return math_mode != NLC_MATH_FP32 && !(B < 2 || B * m->gin > 8 || m->gin > 2) && m->Hg == kHg;
+}
+
+// The planner's overlapped form: step-major tile order, ready[t] counts finished warps of step t (4 per tile), at most
+// max_ctas CTAs so that the rollout kernel keeps its SMs.
+int encode_history_overlapped(nlc_model_t m, const float* hist_dev, int K, int T, int B, float* p_dev, int math_mode,
+                              unsigned int* ready, int max_ctas, cudaStream_t s) {
+  return launch_encode_tc2(m, hist_dev, m->nu, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s, ready, max_ctas);
 }
 
 }  // namespace nlc

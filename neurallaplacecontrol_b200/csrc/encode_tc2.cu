@@ -55,6 +55,12 @@ struct Args {
   float* p_out;
   int K, T, B, L, hist_ch;
   long long rows;
+  // step-major tile order for the overlapped planner step (planner.cu): tile = t * tiles_per_t + sample block, so that all
+  // windows of rollout step t are encoded before any of step t + 1; every finished tile bumps ready[t] (4 warps x 1) after
+  // its outputs are visible device-wide - the rollout kernel, running beside this one, polls it.  tiles_per_t == 0: the
+  // plain sample-major order (window index = k * T + t).
+  int tiles_per_t;
+  unsigned int* ready;
   long long* trace;  // measurement only: clock64 timeline of CTA 0, [step][warp][8 events]
   ModelDev m;
 };
@@ -312,6 +318,12 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
 
   // hist offset of this thread's window in a tile (one integer division per tile, not per cell)
   auto window_base = [&](long long tile_) -> size_t {
+    if (a.tiles_per_t > 0) {  // step-major: one step t per tile, 128 consecutive samples
+      const int t = (int)((unsigned)tile_ / (unsigned)a.tiles_per_t);
+      int k = ((int)tile_ - t * a.tiles_per_t) * kRows + row;
+      if (k >= a.K) k = a.K - 1;
+      return ((size_t)k * a.L + t) * a.hist_ch;
+    }
     long long grow = tile_ * kRows + row;
     if (grow >= a.rows) grow = a.rows - 1;
     long long k;
@@ -482,9 +494,17 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
           const float2 p0 = *reinterpret_cast<const float2*>(&s.pout[0][row * 2]);
           const float2 p1 = *reinterpret_cast<const float2*>(&s.pout[1][row * 2]);
           const float2 p2 = *reinterpret_cast<const float2*>(&s.pout[2][row * 2]);
-          if (row0 + row < a.rows)
-            *reinterpret_cast<float2*>(a.p_out + (row0 + row) * 2) =
-                make_float2(((o0 + p0.x) + p1.x) + p2.x + cst[kC2Bout], ((o1 + p0.y) + p1.y) + p2.y + cst[kC2Bout + 1]);
+          const float2 pv = make_float2(((o0 + p0.x) + p1.x) + p2.x + cst[kC2Bout], ((o1 + p0.y) + p1.y) + p2.y + cst[kC2Bout + 1]);
+          if (a.tiles_per_t > 0) {
+            const int t = (int)((unsigned)tile / (unsigned)a.tiles_per_t);
+            const int k = ((int)tile - t * a.tiles_per_t) * kRows + row;
+            if (k < a.K) *reinterpret_cast<float2*>(a.p_out + ((size_t)k * a.T + t) * 2) = pv;
+            // publish: the warp's 32 outputs are ordered before lane 0's device-scope fence and counter bump
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicAdd(a.ready + t, 1u); }
+          } else if (row0 + row < a.rows) {
+            *reinterpret_cast<float2*>(a.p_out + (row0 + row) * 2) = pv;
+          }
         }
         // D1 is read: the input part of the next tile's B(0) can go (its h0 image was published above)
         publish_h1(false);
@@ -506,7 +526,8 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
 static long long* g_enc_trace = nullptr;
 void set_encoder_trace(long long* p) { g_enc_trace = p; }
 
-int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream) {
+int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream,
+                      unsigned int* ready, int max_ctas) {
   using namespace enc2;
   NLC_REQUIRE(B * m->gin <= 8, NLC_ERR_SHAPE, "tcgen05 encoder: window_length * input_width = %d exceeds 8", B * m->gin);
   NLC_REQUIRE(B >= 2, NLC_ERR_SHAPE, "tcgen05 encoder: window_length must be >= 2");
@@ -514,6 +535,8 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   Args a;
   a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.hist_ch = hist_ch;
   a.rows = (long long)K * T;
+  a.tiles_per_t = ready ? (K + kRows - 1) / kRows : 0;
+  a.ready = ready;
   a.m = m->d;
   a.trace = g_enc_trace;
   const int smem = (int)sizeof(Smem) + 128;
@@ -534,8 +557,10 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
 #undef NLC_ENC_PICK
   if (a.trace && split3) kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 3, 0, true, true> : encode_tc2_kernel<true, 2, 3, 0, true, true>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const long long n_tiles = (a.rows + kRows - 1) / kRows;
-  const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
+  const long long n_tiles = ready ? (long long)a.tiles_per_t * T : (a.rows + kRows - 1) / kRows;
+  if (ready) a.rows = n_tiles * kRows;  // step-major: every tile is walked; rows beyond K are masked at the output
+  const int cap = max_ctas > 0 && max_ctas < 148 ? max_ctas : 148;
+  const int grid = (int)(n_tiles < cap ? n_tiles : cap);
   kern<<<grid, kThreadsLaunch, smem, stream>>>(a);
   NLC_LAUNCH_OK("encode_tc2_kernel");
   return NLC_OK;

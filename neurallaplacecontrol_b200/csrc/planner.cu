@@ -29,6 +29,22 @@ struct nlc_planner_s {
   cudaStream_t cap_stream;
   cudaGraphExec_t graph_core, graph_host;  // [perturb .. combine] on the planner's own input buffers; same + H2D / D2H copies
   bool graph_core_tried, graph_host_tried;
+  // Plans within half a wave of 128-sample tiles leave most SMs idle during the sequential rollout: the history encoder
+  // then runs BESIDE the rollout kernel (side stream, fork/join on events - also inside the captured graphs) in step-major
+  // order, publishing per-step readiness counters the rollout polls (encode_tc2.cu / rollout_tc2.cu).
+  bool overlap;
+  cudaStream_t side_stream;
+  cudaEvent_t ev_fork, ev_join;
+  unsigned int* ready;   // [T] finished encoder warps per rollout step, + 1 status word (1 = a poll timed out)
+  // K sharded over the GPUs of one node: device-side exchange of the triples through peer-mapped mailboxes (stage4_update.cu)
+  float* mailbox;               // own: [2][G][xstride] floats + [2][G] sequence words
+  int xstride;
+  bool xchg;                    // peers connected: publish / poll-and-combine replace the host-side all-gather
+  void* peer[64];               // mailbox of every shard as mapped into this process (own slot = mailbox)
+  bool peer_ipc[64];            // opened with cudaIpcOpenMemHandle (to be closed)
+  float** mailboxes_dev;        // the same table in device memory
+  unsigned long long* xstep;    // control steps exchanged so far
+  unsigned int* xstatus;        // 2 = a poll for a peer's triple timed out
 };
 
 namespace nlc {
@@ -36,6 +52,17 @@ int perturb_launch(const nlc_mppi_params* p, const float* U_prev_dev, float* U_d
                    uint64_t seed, uint64_t call_index, const unsigned long long* call_index_dev, const float* action_buffer_dev,
                    float* perturbed_dev, float* noise_dev, float* hist_dev, float* actions_dev, float* pert_cost_dev, void* stream);
 int launch_bump_counter(unsigned long long* ctr, cudaStream_t stream);
+int launch_exchange_publish(const float* triple, float* const* mailboxes_dev, int G, int rank, int stride, int n,
+                            const unsigned long long* step_ctr, cudaStream_t s);
+int launch_combine_exchange(float* mailbox, int G, int stride, int T, int nu, float lambda_, float u_scale, float* U, float* action,
+                            float* stats, unsigned long long* step_ctr, unsigned int* status, cudaStream_t s);
+bool encoder_is_tensor_core(nlc_model_t m, int B, int math_mode);
+int encode_history_overlapped(nlc_model_t m, const float* hist_dev, int K, int T, int B, float* p_dev, int math_mode,
+                              unsigned int* ready, int max_ctas, cudaStream_t s);
+bool rollout_can_overlap(const nlc_model_s* m, int K, int T, int math_mode);
+int launch_rollout_overlapped(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p, const float* hist,
+                              const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states, int math_mode,
+                              const unsigned int* ready, unsigned int ready_target, unsigned int* status, cudaStream_t stream);
 }  // namespace nlc
 
 using namespace nlc;
@@ -49,7 +76,7 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   NLC_REQUIRE(mp.K >= 1 && mp.T >= 1 && mp.B >= 1 && mp.B <= 8, NLC_ERR_SHAPE, "planner: K, T >= 1 and 1 <= B <= 8 required");
   NLC_REQUIRE(mp.nu >= 1 && mp.nu <= 4 && d->nx >= 1 && d->nx <= kMaxNx, NLC_ERR_SHAPE, "planner: nu/nx out of range");
   NLC_REQUIRE(mp.T * mp.nu <= 256, NLC_ERR_SHAPE, "planner: T*nu exceeds 256");
-  NLC_REQUIRE(d->n_shards >= 1 && d->shard_index >= 0 && d->shard_index < d->n_shards, NLC_ERR_ARG, "planner: bad shard spec");
+  NLC_REQUIRE(d->n_shards >= 1 && d->n_shards <= 64 && d->shard_index >= 0 && d->shard_index < d->n_shards, NLC_ERR_ARG, "planner: bad shard spec");
   NLC_REQUIRE(mp.lambda_ > 0.0f, NLC_ERR_ARG, "planner: lambda must be positive");
   if (d->rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
     NLC_REQUIRE(model != nullptr, NLC_ERR_ARG, "planner: Neural Laplace dynamics need a model handle");
@@ -61,6 +88,9 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;
   p->call_ctr = nullptr; p->cap_stream = nullptr; p->graph_core = nullptr; p->graph_host = nullptr;
   p->graph_core_tried = p->graph_host_tried = false;
+  p->overlap = false; p->side_stream = nullptr; p->ev_fork = p->ev_join = nullptr; p->ready = nullptr;
+  p->mailbox = nullptr; p->xstride = 0; p->xchg = false; p->mailboxes_dev = nullptr; p->xstep = nullptr; p->xstatus = nullptr;
+  memset(p->peer, 0, sizeof(p->peer)); memset(p->peer_ipc, 0, sizeof(p->peer_ipc));
   const size_t K = mp.K, T = mp.T, nu = mp.nu, B = mp.B, nx = d->nx, L = B - 1 + T, TN = T * nu;
   std::vector<size_t> sizes = {
       TN, TN, K * TN, K * TN, K * L * nu, K * TN, K, K * T * 2, K, K, (d->keep_states ? K * T * nx : 0),
@@ -71,6 +101,10 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->arena_bytes = total * sizeof(float);
   auto fail = [&](int code) {
     if (p->arena) cudaFree(p->arena);
+    if (p->ready) cudaFree(p->ready);
+    if (p->side_stream) cudaStreamDestroy(p->side_stream);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->call_ctr) cudaFree(p->call_ctr);
     if (p->h_in) cudaFreeHost(p->h_in);
     if (p->h_out) cudaFreeHost(p->h_out);
@@ -92,6 +126,16 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->softmax_ws = base + offs[17];
   if (cudaMallocHost(&p->h_in, sizeof(float) * (nx + B * nu)) != cudaSuccess || cudaMallocHost(&p->h_out, sizeof(float) * 4) != cudaSuccess) {
     cudaGetLastError(); set_error("planner: pinned allocation failed"); return fail(NLC_ERR_NOMEM);
+  }
+  if (d->rollout.dynamics == NLC_DYN_NEURAL_LAPLACE && encoder_is_tensor_core(model, mp.B, d->math_mode) &&
+      rollout_can_overlap(model, mp.K, mp.T, d->math_mode) && d->rollout.env >= 0) {
+    if (cudaMalloc(&p->ready, sizeof(unsigned int) * (T + 1)) != cudaSuccess || cudaMemset(p->ready, 0, sizeof(unsigned int) * (T + 1)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError(); set_error("planner: overlap resources could not be created"); return fail(NLC_ERR_NOMEM);
+    }
+    p->overlap = true;
   }
   if (model) model->refs++;
   *out = p;
@@ -124,11 +168,97 @@ extern "C" int nlc_planner_destroy(nlc_planner_t p) {
   if (p->graph_core) cudaGraphExecDestroy(p->graph_core);
   if (p->graph_host) cudaGraphExecDestroy(p->graph_host);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  if (p->side_stream) cudaStreamDestroy(p->side_stream);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->ready) cudaFree(p->ready);
+  for (int g = 0; g < 64; ++g)
+    if (p->peer_ipc[g] && p->peer[g]) cudaIpcCloseMemHandle(p->peer[g]);
+  if (p->mailbox) cudaFree(p->mailbox);
+  if (p->mailboxes_dev) cudaFree(p->mailboxes_dev);
+  if (p->xstep) cudaFree(p->xstep);
   if (p->call_ctr) cudaFree(p->call_ctr);
   if (p->arena) cudaFree(p->arena);
   if (p->h_in) cudaFreeHost(p->h_in);
   if (p->h_out) cudaFreeHost(p->h_out);
+  cudaGetLastError();
   delete p;
+  return NLC_OK;
+}
+
+// ---- device-side exchange of the shard triples (no collective library; stage4_update.cu) -----------------------------
+static int planner_mailbox(nlc_planner_t p) {
+  if (p->mailbox) return NLC_OK;
+  const int G = p->d.n_shards, TN = p->d.mppi.T * p->d.mppi.nu;
+  p->xstride = (2 + TN + 3) / 4 * 4;
+  const size_t bytes = sizeof(float) * 2 * G * p->xstride + sizeof(unsigned int) * 2 * G;
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  NLC_CUDA_OK(cudaMalloc(&p->mailbox, bytes));  // its own allocation: CUDA IPC exports whole allocations
+  NLC_CUDA_OK(cudaMemset(p->mailbox, 0, bytes));
+  NLC_CUDA_OK(cudaMalloc(&p->mailboxes_dev, sizeof(float*) * G));
+  NLC_CUDA_OK(cudaMalloc(&p->xstep, sizeof(unsigned long long) + sizeof(unsigned int)));
+  NLC_CUDA_OK(cudaMemset(p->xstep, 0, sizeof(unsigned long long) + sizeof(unsigned int)));
+  p->xstatus = reinterpret_cast<unsigned int*>(p->xstep + 1);
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_exchange_export(nlc_planner_t p, void* ipc_handle_64, void** local_ptr) {
+  NLC_REQUIRE(p, NLC_ERR_ARG, "nlc_planner_exchange_export: null planner");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  int rc = planner_mailbox(p);
+  if (rc != NLC_OK) return rc;
+  if (ipc_handle_64) NLC_CUDA_OK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(ipc_handle_64), p->mailbox));
+  if (local_ptr) *local_ptr = p->mailbox;
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_exchange_connect(nlc_planner_t p, int kind, const void* data) {
+  NLC_REQUIRE(p && data, NLC_ERR_ARG, "nlc_planner_exchange_connect: null argument");
+  NLC_REQUIRE(kind == 0 || kind == 1, NLC_ERR_ARG, "nlc_planner_exchange_connect: kind must be 0 (IPC handles) or 1 (device pointers)");
+  NLC_REQUIRE(!p->xchg, NLC_ERR_ARG, "nlc_planner_exchange_connect: already connected");
+  int rc = planner_mailbox(p);
+  if (rc != NLC_OK) return rc;
+  const int G = p->d.n_shards, me = p->d.shard_index;
+  NLC_CUDA_OK(cudaSetDevice(p->device));
+  for (int g = 0; g < G; ++g) {
+    if (g == me) { p->peer[g] = p->mailbox; continue; }
+    if (kind == 1) {
+      p->peer[g] = static_cast<void* const*>(data)[g];
+      NLC_REQUIRE(p->peer[g] != nullptr, NLC_ERR_ARG, "nlc_planner_exchange_connect: null mailbox pointer for shard %d", g);
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char*>(data) + 64 * (size_t)g, 64);
+      void* ptr = nullptr;
+      const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        for (int j = 0; j < g; ++j)
+          if (p->peer_ipc[j]) { cudaIpcCloseMemHandle(p->peer[j]); p->peer_ipc[j] = false; p->peer[j] = nullptr; }
+        set_error("nlc_planner_exchange_connect: cudaIpcOpenMemHandle for shard %d failed: %s", g, cudaGetErrorString(e));
+        return NLC_ERR_CUDA;
+      }
+      p->peer[g] = ptr; p->peer_ipc[g] = true;
+    }
+  }
+  NLC_CUDA_OK(cudaMemcpy(p->mailboxes_dev, p->peer, sizeof(float*) * G, cudaMemcpyHostToDevice));
+  p->xchg = true;
+  // captured graphs (if any) predate the exchange: re-capture on next use
+  if (p->graph_core) { cudaGraphExecDestroy(p->graph_core); p->graph_core = nullptr; }
+  p->graph_core_tried = false;
+  return NLC_OK;
+}
+
+extern "C" int nlc_planner_exchange_status(nlc_planner_t p, int* connected, int* status) {
+  NLC_REQUIRE(p && connected && status, NLC_ERR_ARG, "nlc_planner_exchange_status: null argument");
+  *connected = p->xchg ? 1 : 0;
+  *status = 0;
+  if (p->xchg) {
+    unsigned int v = 0;
+    NLC_CUDA_OK(cudaSetDevice(p->device));
+    NLC_CUDA_OK(cudaDeviceSynchronize());
+    NLC_CUDA_OK(cudaMemcpy(&v, p->xstatus, sizeof(v), cudaMemcpyDeviceToHost));
+    *status = (int)v;
+  }
   return NLC_OK;
 }
 
@@ -196,16 +326,37 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
   if (rc != NLC_OK) return rc;
   p->calls++;
   if (ev) NLC_CUDA_OK(cudaEventRecord(ev[1], s));
-  if (p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
-    rc = nlc_encode_history(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, stream);
+  if (p->overlap && !ev) {
+    // encoder || rollout: fork after stage 1, the encoder on this stream with all SMs but the rollout's, the rollout (one
+    // 128-sample tile per CTA) on the side stream, join before stage 4.  The encoder is launched FIRST in host order: a
+    // tool that serialises kernels then runs it to completion before the rollout starts polling.
+    const int n_tiles = (mp.K + 127) / 128;
+    NLC_CUDA_OK(cudaMemsetAsync(p->ready, 0, sizeof(unsigned int) * (mp.T + 1), s));
+    NLC_CUDA_OK(cudaEventRecord(p->ev_fork, s));
+    NLC_CUDA_OK(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
+    rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148 - n_tiles, s);
+    if (rc != NLC_OK) return rc;
+    rc = launch_rollout_overlapped(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,
+                                   mp.nu, p->cost_total, p->states, p->d.math_mode, p->ready, 4u * (unsigned)n_tiles, p->ready + mp.T,
+                                   p->side_stream);
+    if (rc != NLC_OK) return rc;
+    NLC_CUDA_OK(cudaEventRecord(p->ev_join, p->side_stream));
+    NLC_CUDA_OK(cudaStreamWaitEvent(s, p->ev_join, 0));
+  } else {
+    if (p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE) {
+      rc = nlc_encode_history(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, stream);
+      if (rc != NLC_OK) return rc;
+    }
+    if (ev) NLC_CUDA_OK(cudaEventRecord(ev[2], s));
+    rc = nlc_rollout_cost(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,
+                          mp.nu, p->cost_total, p->states, p->d.math_mode, stream);
     if (rc != NLC_OK) return rc;
   }
-  if (ev) NLC_CUDA_OK(cudaEventRecord(ev[2], s));
-  rc = nlc_rollout_cost(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,
-                        mp.nu, p->cost_total, p->states, p->d.math_mode, stream);
-  if (rc != NLC_OK) return rc;
   if (ev) NLC_CUDA_OK(cudaEventRecord(ev[3], s));
-  return nlc_softmax_partial(p->cost_total, p->noise, mp.K, mp.T, mp.nu, mp.lambda_, p->triple, p->weights, p->softmax_ws, stream);
+  rc = nlc_softmax_partial(p->cost_total, p->noise, mp.K, mp.T, mp.nu, mp.lambda_, p->triple, p->weights, p->softmax_ws, stream);
+  if (rc != NLC_OK || !p->xchg) return rc;
+  // connected shards: this shard's triple goes straight into every peer's mailbox over NVLink
+  return launch_exchange_publish(p->triple, p->mailboxes_dev, p->d.n_shards, p->d.shard_index, p->xstride, 2 + mp.T * mp.nu, p->xstep, s);
 }
 
 extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int state_per_sample,
@@ -236,6 +387,20 @@ extern "C" int nlc_planner_step_profile(nlc_planner_t p, float* ms_out, void* st
   return rc;
 }
 
+extern "C" int nlc_planner_overlap_status(nlc_planner_t p, int* overlapped, int* status) {
+  NLC_REQUIRE(p && overlapped && status, NLC_ERR_ARG, "nlc_planner_overlap_status: null argument");
+  *overlapped = p->overlap ? 1 : 0;
+  *status = 0;
+  if (p->overlap) {
+    unsigned int v = 0;
+    NLC_CUDA_OK(cudaSetDevice(p->device));
+    NLC_CUDA_OK(cudaDeviceSynchronize());
+    NLC_CUDA_OK(cudaMemcpy(&v, p->ready + p->d.mppi.T, sizeof(v), cudaMemcpyDeviceToHost));
+    *status = (int)v;
+  }
+  return NLC_OK;
+}
+
 extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {
   NLC_REQUIRE(p, NLC_ERR_ARG, "nlc_planner_finish: null planner");
   const nlc_mppi_params& mp = p->d.mppi;
@@ -243,6 +408,9 @@ extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // U <- rolled U (the update is applied to the rolled sequence, mppi_delay.py:199-216)
   NLC_CUDA_OK(cudaMemcpyAsync(p->U, p->U_rolled, sizeof(float) * mp.T * mp.nu, cudaMemcpyDeviceToDevice, s));
+  if (p->xchg)  // wait (on the device) for the G triples of this control step in the own mailbox, then combine
+    return launch_combine_exchange(p->mailbox, p->d.n_shards, p->xstride, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats,
+                                   p->xstep, p->xstatus, s);
   const float* triples = p->d.n_shards == 1 ? p->triple : p->all_triples;
   return nlc_softmax_combine(triples, p->d.n_shards, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats, stream);
 }
@@ -259,7 +427,7 @@ static int planner_core_direct(nlc_planner_t p, void* stream) {
 // graph is then launched on the caller's stream.  Any failure leaves the planner on direct launches.
 static cudaGraphExec_t planner_capture(nlc_planner_t p, bool with_host_copies) {
   static const bool disabled = [] { const char* e = getenv("NLC_NO_GRAPH"); return e && e[0] == '1'; }();
-  if (disabled || p->d.n_shards != 1) return nullptr;
+  if (disabled || (p->d.n_shards != 1 && !p->xchg)) return nullptr;
   if (!p->cap_stream && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   // first use of every kernel outside capture: one-time function attributes and lazy module loading must not be captured
   const uint64_t calls0 = p->calls;
@@ -310,7 +478,8 @@ static cudaGraphExec_t planner_capture_preserving_state(nlc_planner_t p, bool wi
 
 extern "C" int nlc_planner_step(nlc_planner_t p, void* stream) {
   NLC_REQUIRE(p, NLC_ERR_ARG, "nlc_planner_step: null planner");
-  NLC_REQUIRE(p->d.n_shards == 1, NLC_ERR_UNSUPPORTED, "nlc_planner_step is the single-shard entry point");
+  NLC_REQUIRE(p->d.n_shards == 1 || p->xchg, NLC_ERR_UNSUPPORTED,
+              "nlc_planner_step needs a single shard, or shards connected by nlc_planner_exchange_connect");
   NLC_CUDA_OK(cudaSetDevice(p->device));
   { int rc = planner_check_model(p); if (rc != NLC_OK) return rc; }
   if (!p->graph_core_tried) { p->graph_core_tried = true; p->graph_core = planner_capture_preserving_state(p, false); }

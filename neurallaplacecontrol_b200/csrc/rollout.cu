@@ -262,7 +262,23 @@ int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K
                         cudaStream_t s);
 int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                        const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
-                       float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream);
+                       float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream, const unsigned int* ready = nullptr,
+                       unsigned int ready_target = 0, unsigned int* status = nullptr);
+bool rollout_has_tensor_core_form(const nlc_model_s* m);
+
+// planner.cu: can the rollout of this plan run BESIDE its history encoder (one-tile tcgen05 form on ceil(K/128) SMs, polling the
+// encoder's per-step readiness counters)?  Plans of at most half a wave of tiles: the encoder keeps at least half the SMs.
+bool rollout_can_overlap(const nlc_model_s* m, int K, int T, int math_mode) {
+  static const bool off = [] { const char* e = getenv("NLC_NO_OVERLAP"); return e && e[0] == '1'; }();
+  const char* f = getenv("NLC_ROLLOUT_TILES");  // a forced kernel form (parity tests) keeps the plain sequence
+  return !off && !(f && f[0]) && math_mode != NLC_MATH_FP32 && rollout_has_tensor_core_form(m) && T >= 2 && (K + 127) / 128 <= 74;
+}
+int launch_rollout_overlapped(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p, const float* hist,
+                              const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states, int math_mode,
+                              const unsigned int* ready, unsigned int ready_target, unsigned int* status, cudaStream_t stream) {
+  return launch_rollout_tc2(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, nullptr, math_mode == NLC_MATH_TC_SPLIT3, 1,
+                            stream, ready, ready_target, status);
+}
 
 // math_mode dispatch: the tensor-core kernel when it has an instantiation for (nx, S), else the FFMA kernel
 static int launch_rollout(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,

@@ -71,7 +71,31 @@ struct Args {
   float* states;
   float* delta_out;
   long long* trace;  // measurement only: clock64 timeline of CTA 0, [step][warp][8 events]
+  // overlapped planner step (planner.cu): the history encoder runs BESIDE this kernel on the other SMs in step-major order
+  // and bumps ready[t] as the windows of step t complete; p(., t) may be read once ready[t] >= ready_target.  A poll that
+  // does not complete within ~4 s (the encoder is not co-resident: a serialising profiler, a shared GPU) sets *status = 1
+  // and lets the step finish on whatever is there instead of hanging the device.
+  const unsigned int* ready;
+  unsigned int ready_target;
+  unsigned int* status;
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// warp-wide: lane 0 polls, the warp continues once the windows of step t are published
+__device__ __forceinline__ void wait_windows_ready(const Args& a, int t, int lane) {
+  if (lane == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(a.ready + t) < a.ready_target) {
+      if (clock64() - t0 > (1ll << 33)) { atomicExch(a.status, 1u); break; }  // ~4 s
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+}
 
 struct SmemTail {  // after the weight images
   alignas(16) float b2[kH];
@@ -444,14 +468,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         in[c] = (st[c] - s.smean[c]) * s.sinv[c];
       }
       {
-        const float2 pv = *reinterpret_cast<const float2*>(a.p + ((size_t)kk * a.T) * 2);
+        // (__ldcg: p may be written by the encoder kernel while this kernel runs - never through a stale L1 line)
+        if (kTiles == 1 && a.ready) wait_windows_ready(a, 0, lane);
+        const float2 pv = __ldcg(reinterpret_cast<const float2*>(a.p + ((size_t)kk * a.T) * 2));
         in[NX] = pv.x; in[NX + 1] = pv.y;
       }
       float cost_acc = 0.0f;
 
       for (int t = 0; t < a.T; ++t) {
         float2 pnext = make_float2(0.f, 0.f);
-        if (t + 1 < a.T) pnext = *reinterpret_cast<const float2*>(a.p + ((size_t)kk * a.T + t + 1) * 2);
+        if (!(kTiles == 1 && a.ready) && t + 1 < a.T) pnext = __ldcg(reinterpret_cast<const float2*>(a.p + ((size_t)kk * a.T + t + 1) * 2));
 
         // ---------------- A1 = [in | 1 | 0..] as the K = 16 operand (one thread per sample) ----------------
         if (cg == 0 && active) {
@@ -513,6 +539,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         }
         mark(4);
         issue(2);
+        // overlapped form: the next step's encoder output, polled for and loaded under the L3 product
+        if (kTiles == 1 && a.ready && t + 1 < a.T) {
+          wait_windows_ready(a, t + 1, lane);
+          pnext = __ldcg(reinterpret_cast<const float2*>(a.p + ((size_t)kk * a.T + t + 1) * 2));
+        }
         // cost of the previous step's state while the MMA runs (mppi_delay.py:288-290)
         if (cg == 0 && t > 0 && a.cost_total && live)
           cost_acc += env_running_cost_fast(a.o, st, a.hist + ((size_t)kk * a.L + (t - 1) + a.B - 1) * a.nu, a.nu);
@@ -976,6 +1007,8 @@ static int launch_one_t(const Args& a, cudaStream_t stream) {
   // one tile slot per 32..128 samples: enough CTAs to give every slot at least one warp of samples, at most one per SM
   int grid = (a.K + 32 * kTiles - 1) / (32 * kTiles);
   if (grid > 148) grid = 148;
+  // overlapped planner step: whole 128-sample tiles on as few SMs as possible - the encoder runs on the others
+  if (kTiles == 1 && a.ready) grid = (a.K + kRows - 1) / kRows;
   kern<<<grid, kThreads, smem, stream>>>(a);
   NLC_LAUNCH_OK("rollout_tc2_kernel");
   return NLC_OK;
@@ -990,14 +1023,22 @@ static int launch_one(const Args& a, int tiles, cudaStream_t stream) {
 
 }  // namespace rt2
 
+bool rollout_has_tensor_core_form(const nlc_model_s* m) {
+  return (m->S == 17 && (m->nx == 3 || m->nx == 5 || m->nx == 6)) || (m->S == 33 && m->nx == 3);
+}
+
 // returns NLC_ERR_UNSUPPORTED when the (nx, S) pair has no tensor-core instantiation (caller falls back)
 static long long* g_roll_trace = nullptr;
 void set_rollout_trace(long long* p) { g_roll_trace = p; }
 
 int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                        const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
-                       float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream) {
+                       float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream, const unsigned int* ready,
+                       unsigned int ready_target, unsigned int* status) {
   rt2::Args a;
+  a.ready = ready; a.ready_target = ready_target; a.status = status;
+  NLC_REQUIRE(!ready || (tiles_per_cta == 1 && (K + 127) / 128 <= 148 && status), NLC_ERR_ARG,
+              "rollout: the overlapped form is the one-tile form of plans within one wave");
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
   a.trace = g_roll_trace;

@@ -154,6 +154,80 @@ __global__ void softmax_combine_kernel(const float* __restrict__ triples, int G,
   if (threadIdx.x == 0 && stats) { stats[0] = beta; stats[1] = eta; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Exchange of the per-shard triples WITHOUT a collective library (K sharded over the GPUs of one node): every shard owns
+// a "mailbox" in its own HBM,  float triples[2][G][stride]  followed by  unsigned seq[2][G];  peers map it through CUDA IPC.
+//   publish  each shard stores its triple into slot [parity][rank] of EVERY shard's mailbox over NVLink (plain peer
+//            stores), fences system-wide, then releases seq[parity][rank] = step id in each mailbox;
+//   combine  polls its OWN mailbox until all G seq words carry the step id (acquire), then merges as softmax_combine_kernel.
+// Parity = step & 1: a shard can be at most one control step ahead of another (its next combine needs everybody's next
+// triple), so two slots are enough.  No host, no NCCL, no extra stream: the sharded control step is one CUDA graph.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) exchange_publish_kernel(const float* __restrict__ triple, float* const* __restrict__ mailboxes,
+                                                               int G, int rank, int stride, int n, const unsigned long long* step_ctr) {
+  const unsigned long long step = *step_ctr;
+  const int par = (int)(step & 1ull);
+  for (int g = 0; g < G; ++g) {
+    float* dst = mailboxes[g] + ((size_t)par * G + rank) * stride;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) dst[c] = triple[c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < G) {
+    unsigned int* seq = reinterpret_cast<unsigned int*>(mailboxes[threadIdx.x] + (size_t)2 * G * stride) + par * G + rank;
+    const unsigned int id = (unsigned int)(step + 1ull);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(seq), "r"(id) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(128) softmax_combine_exchange_kernel(float* mailbox, int G, int stride, int TN, int nu, float inv_lambda,
+                                                                       float u_scale, float* U, float* action, float* stats,
+                                                                       unsigned long long* step_ctr, unsigned int* status) {
+  const unsigned long long step = *step_ctr;
+  const int par = (int)(step & 1ull);
+  const unsigned int id = (unsigned int)(step + 1ull);
+  if (threadIdx.x < G) {
+    const unsigned int* seq = reinterpret_cast<const unsigned int*>(mailbox + (size_t)2 * G * stride) + par * G + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(seq) : "memory");
+      if (v == id) break;
+      if (clock64() - t0 > (1ll << 34)) { atomicExch(status, 2u); break; }  // ~8 s: a peer is gone; do not hang the device
+      __nanosleep(200);
+    } while (true);
+  }
+  __syncthreads();
+  const volatile float* triples = mailbox + (size_t)par * G * stride;
+  float beta = INFINITY;
+  for (int g = 0; g < G; ++g) beta = fminf(beta, triples[g * stride]);
+  float eta = 0.0f;
+  for (int g = 0; g < G; ++g) eta = fmaf(triples[g * stride + 1], exp_acc(-inv_lambda * (triples[g * stride] - beta)), eta);
+  for (int c = threadIdx.x; c < TN; c += blockDim.x) {
+    float W = 0.0f;
+    for (int g = 0; g < G; ++g) W = fmaf(triples[g * stride + 2 + c], exp_acc(-inv_lambda * (triples[g * stride] - beta)), W);
+    const float u = U[c] + W / eta;  // mppi_delay.py:214-216
+    U[c] = u;
+    if (c < nu && action) action[c] = u * u_scale;  // :217-224
+  }
+  if (threadIdx.x == 0 && stats) { stats[0] = beta; stats[1] = eta; }
+  __syncthreads();
+  if (threadIdx.x == 0) *step_ctr = step + 1ull;
+}
+
+int launch_exchange_publish(const float* triple, float* const* mailboxes_dev, int G, int rank, int stride, int n,
+                            const unsigned long long* step_ctr, cudaStream_t s) {
+  exchange_publish_kernel<<<1, 128, 0, s>>>(triple, mailboxes_dev, G, rank, stride, n, step_ctr);
+  NLC_LAUNCH_OK("exchange_publish_kernel");
+  return NLC_OK;
+}
+int launch_combine_exchange(float* mailbox, int G, int stride, int T, int nu, float lambda_, float u_scale, float* U, float* action,
+                            float* stats, unsigned long long* step_ctr, unsigned int* status, cudaStream_t s) {
+  softmax_combine_exchange_kernel<<<1, 128, 0, s>>>(mailbox, G, stride, T * nu, nu, 1.0f / lambda_, u_scale, U, action, stats, step_ctr, status);
+  NLC_LAUNCH_OK("softmax_combine_exchange_kernel");
+  return NLC_OK;
+}
+
 static int sum_grid(int K) {
   int g = (K + 255) / 256;  // >= 256 rows per block
   if (g > 148 * 4) g = 148 * 4;

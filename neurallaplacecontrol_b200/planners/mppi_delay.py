@@ -149,6 +149,7 @@ class MPPIDelay:
         self._handle = None
         self._handle_B = None
         self._handle_model = None
+        self._exchange = False
         self._views = {}
         if U_init is None:
             U_init = self._replicated(self.noise_dist.sample((self.T,)))  # mppi_delay.py:163-164
@@ -226,7 +227,69 @@ class MPPIDelay:
         self._handle, self._handle_B, self._views = h, B, {}
         self._handle_model = None if model_h is None else model_h.value
         self._U_dirty = True
-        return h
+        self._exchange = False
+        if self.G > 1 and self.process_group is not None:
+            self._connect_exchange(h)
+        return self._handle
+
+    # ---- device-side exchange of the shard triples (include/nlc_b200.h: nlc_planner_exchange_*) ----------------------------
+    def _connect_exchange(self, h):
+        """Map every rank's mailbox into this process through CUDA IPC (one all-gather of the 64-byte handles, at handle
+        creation only).  From then on a control step exchanges the triples on the device and is ONE graph launch.  If any
+        rank cannot map a peer (no P2P between the GPUs, ``NLC_NO_DEVICE_EXCHANGE=1``) every rank falls back to the
+        all-gather of ``sharding.gather_triples``.  Collective: every rank of the group creates its handle at the same call."""
+        import os
+
+        import torch.distributed as dist
+
+        backend = dist.get_backend(self.process_group)
+        cdev = self.d if backend == "nccl" else torch.device("cpu")
+        mine = (C.c_char * 64)()
+        want = os.environ.get("NLC_NO_DEVICE_EXCHANGE", "0") != "1"
+        if want:
+            want = self._lib.nlc_planner_exchange_export(h, mine, None) == _lib.NLC_OK
+        allh = torch.zeros(self.G * 64, dtype=torch.uint8, device=cdev)
+        dist.all_gather_into_tensor(allh, torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).to(cdev), group=self.process_group)
+        ok = torch.tensor([1 if want else 0], dtype=torch.int32, device=cdev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.process_group)
+        if int(ok) == 1:
+            buf = allh.cpu().numpy().tobytes()
+            ok[0] = 1 if self._lib.nlc_planner_exchange_connect(h, 0, buf) == _lib.NLC_OK else 0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.process_group)
+        if int(ok) == 1:
+            self._exchange = True
+        else:
+            # a half-connected group would deadlock in the device-side poll: drop the handle and keep the collective path
+            # (a connected handle cannot be disconnected, so it is rebuilt; nothing has been planned with it yet)
+            d, model_h = self._desc(self._handle_B, self.K_local, self.k_offset, self.K, self.G, self.rank)
+            self._lib.nlc_planner_destroy(h)
+            h2 = C.c_void_p()
+            _lib.check(self._lib.nlc_planner_create(C.byref(h2), model_h, C.byref(d), self.d.index), "nlc_planner_create")
+            self._handle = h2
+        return self._exchange
+
+    @staticmethod
+    def connect_local_shards(planners, action_buffer_size=4):
+        """Shards of one plan living in ONE process (``shard=(rank, G)``; single-GPU tests of the sharded step): connect their
+        mailboxes by device pointer.  The caller then drives ``_begin`` on every shard before any ``_finish``."""
+        ptrs = []
+        for p in planners:
+            h = p._ensure(action_buffer_size)
+            ptr = C.c_void_p()
+            _lib.check(p._lib.nlc_planner_exchange_export(h, None, C.byref(ptr)), "nlc_planner_exchange_export")
+            ptrs.append(ptr.value)
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        for p in planners:
+            _lib.check(p._lib.nlc_planner_exchange_connect(p._handle, 1, arr), "nlc_planner_exchange_connect")
+            p._exchange = True
+
+    def exchange_status(self):
+        """(connected, status): device-side exchange in use, and 2 if a poll for a peer's triple gave up."""
+        if self._handle is None:
+            return False, 0
+        a, b = C.c_int(), C.c_int()
+        _lib.check(self._lib.nlc_planner_exchange_status(self._handle, C.byref(a), C.byref(b)), "nlc_planner_exchange_status")
+        return bool(a.value), int(b.value)
 
     def _destroy(self):
         if self._handle is not None:
@@ -323,7 +386,7 @@ class MPPIDelay:
         action = self._begin(state, action_buffer)
         if action is not None:  # single shard, host or planner-owned inputs: the whole step was one graph launch
             return action
-        if self.G > 1:
+        if self.G > 1 and not self._exchange:
             if self.process_group is None:
                 raise RuntimeError("a planner built with shard=(rank, G) has no process group to exchange the triples: "
                                    "drive it through _begin / all_triples / _finish")
@@ -366,8 +429,9 @@ class MPPIDelay:
                 st[0].copy_(state.reshape(-1).to(device=self.d, dtype=torch.float32))
             ab = self._buf(_lib.BUF_ACTION_BUFFER, (B, self.nu))
             ab.copy_(action_buffer.reshape(B, self.nu).to(device=self.d, dtype=torch.float32))
-            if self.G == 1 and noise is None and not per_sample:
-                # fixed launch sequence on the planner's own buffers: one CUDA-graph launch (nlc_planner_step)
+            if (self.G == 1 or (self._exchange and self.process_group is not None)) and noise is None and not per_sample:
+                # fixed launch sequence on the planner's own buffers: one CUDA-graph launch (nlc_planner_step); with
+                # connected shards the exchange of the triples is part of the graph
                 _lib.check(self._lib.nlc_planner_step(h, stream), "nlc_planner_step")
                 self._calls += 1
                 return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
@@ -381,6 +445,15 @@ class MPPIDelay:
             _lib.check(self._lib.nlc_planner_finish(self._handle, _lib.current_stream_ptr()), "nlc_planner_finish")
         self._calls += 1
         return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
+
+    def overlap_status(self):
+        """(overlapped, status): whether this planner runs its history encoder beside the rollout kernel (plans within
+        half a wave of 128-sample tiles), and 1 if the last control step's rollout timed out waiting for the encoder."""
+        if self._handle is None:
+            return False, 0
+        a, b = C.c_int(), C.c_int()
+        _lib.check(self._lib.nlc_planner_overlap_status(self._handle, C.byref(a), C.byref(b)), "nlc_planner_overlap_status")
+        return bool(a.value), int(b.value)
 
     @property
     def shard_triple(self):

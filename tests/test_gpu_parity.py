@@ -499,3 +499,68 @@ def test_non_finite_weights_are_rejected():
     m._cuda_device = torch.device("cuda:0")
     with pytest.raises(RuntimeError, match="not finite"):
         m.handle()
+
+
+@pytest.mark.parametrize("env,K,T", [("oderl-cartpole", 8192, 30), ("oderl-pendulum", 1000, 20), ("oderl-acrobot", 8192, 50), ("oderl-acrobot", 333, 7)])
+def test_overlapped_step_equals_sequential_step(env, K, T, monkeypatch):
+    """Plans within half a wave of tiles run the encoder beside the rollout (step-major encoder order, per-step readiness
+    counters): same kernels, same per-sample arithmetic - bit-identical costs, states and U as the plain sequence
+    (NLC_NO_OVERLAP is latched per process, so the plain sequence is reached by forcing the one-tile rollout form, which the
+    overlap logic treats as a request for the plain launch order)."""
+    from oracle import costs
+    from _util import START_STATE
+
+    nx, nu = costs.ENV_DIMS[env]
+    res = {}
+    for name in ("overlap", "plain"):
+        if name == "plain":
+            monkeypatch.setenv("NLC_ROLLOUT_TILES", "1")
+        m = make_model(env, calibrated=True, math_mode="tc_split3")
+        p = make_planner(env, m, K, T, np.zeros((T, nu)), math_mode="tc_split3", seed=5)
+        acts = []
+        buf = torch.zeros(4, nu, dtype=torch.float64)
+        for it in range(3):  # the third step runs from the captured graph
+            acts.append(p.command(np.array(START_STATE[env]), buf).clone())
+        ov, status = p.overlap_status()
+        assert ov == (name == "overlap") and status == 0, (name, ov, status)
+        res[name] = (torch.stack(acts), p.cost_total.clone(), p.states.clone(), p.U.clone())
+    for a, b in zip(res["overlap"], res["plain"]):
+        assert torch.equal(a, b)
+
+
+def test_device_side_exchange_equals_host_gather():
+    """The shard triples exchanged through the peer mailboxes on the device (here: four shards of config 3 in one process,
+    connected by device pointer) give bit for bit the U and action of the host-side gather, over two control steps (both
+    mailbox parities)."""
+    from _util import START_STATE, injected_noise
+
+    G = 4
+    res = {}
+    for mode in ("mailbox", "gather"):
+        planners = []
+        for r in range(G):
+            env, K, T, nu, ah, g, p = _full_size_planner("cfg3", "cal", shard=(r, G))
+            planners.append(p)
+        if mode == "mailbox":
+            planners[0].connect_local_shards(planners)
+        state, buf = np.array(START_STATE[env]), torch.zeros(4, nu, dtype=torch.float64)
+        outs = []
+        for step in range(3):
+            noise = injected_noise(K, T, nu, seed=40 + step)
+            for p in planners:
+                p.noise_dist.sample = lambda shape, noise=noise: noise
+                assert p._begin(state, buf) is None
+            if mode == "gather":
+                triples = torch.stack([p.shard_triple.clone() for p in planners])
+                for p in planners:
+                    p.all_triples.copy_(triples)
+            acts = [p._finish().clone() for p in planners]
+            torch.cuda.synchronize()
+            for p, a in zip(planners[1:], acts[1:]):
+                assert torch.equal(p.U, planners[0].U) and torch.equal(a, acts[0])
+            outs.append((planners[0].U.clone(), acts[0]))
+        if mode == "mailbox":
+            assert planners[0].exchange_status() == (True, 0)
+        res[mode] = outs
+    for (Ua, aa), (Ub, ab) in zip(res["mailbox"], res["gather"]):
+        assert torch.equal(Ua, Ub) and torch.equal(aa, ab)
