@@ -189,6 +189,7 @@ struct Smem {
   alignas(128) unsigned char h1[2][kOpBytes];
   alignas(16) float c[kC2Count];
   alignas(16) float pout[3][kRows * 2];
+  alignas(8) uint64_t bar_w;                 // weight images landed (TMA bulk copies)
   alignas(8) uint64_t bar_a, bar_b, bar_h0;  // MMA A / MMA B complete; the part of MMA B that reads the layer-0 state image complete
   uint32_t tmem_base;
 };
@@ -208,14 +209,20 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
   };
 
   {
-    const uint4* src = reinterpret_cast<const uint4*>(a.m.enc2_w);
-    uint4* dst = reinterpret_cast<uint4*>(&s.w[0][0][0]);
-    for (int i = tid; i < (int)(3 * 2 * kWBytes / 16); i += kThreadsLaunch) dst[i] = __ldg(src + i);
-    const uint4* sx = reinterpret_cast<const uint4*>(a.m.enc2_x);
-    for (int i = tid; i < (int)(2 * (kWxBytes + 128) / 16); i += kThreadsLaunch) {
-      const int l = i / (int)((kWxBytes + 128) / 16), j = i - l * (int)((kWxBytes + 128) / 16);
-      reinterpret_cast<uint4*>(s.wx[l])[j] = j < (int)(kWxBytes / 16) ? __ldg(sx + l * (int)(kWxBytes / 16) + j) : make_uint4(0u, 0u, 0u, 0u);
+    // The weight images (144 KB + the two input/bias blocks) come in by TMA bulk copies issued by ONE thread and counted on
+    // an mbarrier that only the MMA warp waits for - no other thread ever reads them - so the load runs under the TMEM
+    // allocation, the zero fills and the first window fetch instead of in front of them.
+    if (tid == 0) {
+      mbar_init(&s.bar_w, 1);
+      mbar_fence_init();
+      mbar_expect_tx(&s.bar_w, (uint32_t)(3 * 2 * kWBytes + 2 * kWxBytes));
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(a.m.enc2_w);
+      for (int i = 0; i < 6; ++i) bulk_g2s(&s.w[0][0][0] + (size_t)i * kWBytes, src + (size_t)i * kWBytes, kWBytes, &s.bar_w);
+      const unsigned char* sx = reinterpret_cast<const unsigned char*>(a.m.enc2_x);
+      for (int l = 0; l < 2; ++l) bulk_g2s(s.wx[l], sx + (size_t)l * kWxBytes, kWxBytes, &s.bar_w);
     }
+    for (int i = tid; i < 2 * 8; i += kThreadsLaunch)  // the zero pad behind each input/bias block
+      reinterpret_cast<uint4*>(s.wx[i >> 3] + kWxBytes)[i & 7] = make_uint4(0u, 0u, 0u, 0u);
     uint4* dz = reinterpret_cast<uint4*>(s.h0_hi);  // the second half of the [x | 1] block stays zero for ever
     for (int i = tid; i < (int)(kH0HiBytes / 16); i += kThreadsLaunch) dz[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < 128; i += kThreadsLaunch) s.c[kC2Wout + i] = a.m.enc2_c[kE2Wout + i];
@@ -283,6 +290,7 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
       __syncwarp();
     };
     if ((long long)blockIdx.x < n_tiles) {
+      mbar_wait(&s.bar_w, 0);
       wait_ready(kBarH0);  // [x(0) | 1]
       issue_a(false);
       wait_ready(kBarH0);  // h0(0), [x(1) | 1]

@@ -212,7 +212,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   const size_t tc_halves = (size_t)3 * 2 * G3 * Hg;
   size_t o_enc2w = A.add(tc_halves / 2), o_enc2c = A.add(nlc::kE2Count), o_enc2x = A.add(2 * 256 * 8 / 2);
   size_t o_m2w1 = A.add((size_t)2 * Hm * 16 / 2), o_m2w2 = A.add((size_t)2 * Hm * Hm / 2), o_m2w3 = A.add((size_t)2 * N3t * Hm / 2);
-  size_t o_m2c = A.add(128 + 256);
+  size_t o_m2c = A.add(128 + 416);  // b2 | b3 (up to 416 (theta, phi) columns: rollout_tc2.cu kMaxN3)
 
   for (int i = 0; i < G3 * gin; ++i) put(o_w_ih0, i, d->gru_w_ih_l0[i]);
   for (int i = 0; i < G3; ++i) {
@@ -325,7 +325,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
     for (int i = 0; i < 2; ++i) put(o_enc2c, nlc::kE2Bout + i, d->enc_out_b[i]);
   }
 
-  if (N3t <= 256) {  // rollout_tc2.cu operands: -2 log2(e) folded
+  if (N3t <= 416) {  // rollout_tc2.cu operands: -2 log2(e) folded
     const double cN = -2.0 * 1.4426950408889634;
     std::vector<double> w2s((size_t)Hm * Hm);
     for (size_t i = 0; i < w2s.size(); ++i) w2s[i] = cN * d->mlp_w2[i];

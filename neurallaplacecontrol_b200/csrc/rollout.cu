@@ -284,7 +284,7 @@ int launch_rollout_overlapped(nlc_model_s* m, const nlc_rollout_opts* o, const f
 static int launch_rollout(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                           const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
                           float* delta_out, int math_mode, cudaStream_t stream) {
-  if (math_mode != NLC_MATH_FP32 && 2 * m->nx * m->S <= 256) {
+  if (math_mode != NLC_MATH_FP32 && rollout_has_tensor_core_form(m)) {
     // rollout_tc2.cu: beyond one wave of 128-sample tiles the ping-pong form (two tiles per CTA, all 16 warps alternating
     // between them: form 3), below that one tile on all 16 warps (form 1: the step latency is then all that matters).
     // NLC_ROLLOUT_TILES=1|2|3 forces a form (2 = two free-running 8-warp groups, the ping-pong form's predecessor);

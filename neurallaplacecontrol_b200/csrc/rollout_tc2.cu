@@ -97,9 +97,37 @@ __device__ __forceinline__ void wait_windows_ready(const Args& a, int t, int lan
   __syncwarp();
 }
 
+// W1 (2 x 4 KB), W2 (2 x 32 KB), W3 (2 x N3t x 256 B) -> shared memory; bulk copies of at most 32 KB each.  with_w3 = false:
+// W3 is streamed half by half instead (load_w3_rows)
+__device__ __forceinline__ void load_weight_images(const ModelDev& m, unsigned char* w1_img, unsigned char* w2_img, unsigned char* w3_img,
+                                                   int N3t, uint64_t* bar, bool with_w3 = true) {
+  const uint32_t b1 = 2 * kH * 16 * 2, b2 = 2 * kH * kH * 2, b3 = with_w3 ? 2u * (uint32_t)N3t * kH * 2 : 0u;
+  mbar_expect_tx(bar, b1 + b2 + b3);
+  bulk_g2s(w1_img, m.mlp2_w1, b1, bar);
+  for (uint32_t o = 0; o < b2; o += 32768) bulk_g2s(w2_img + o, static_cast<const unsigned char*>(m.mlp2_w2) + o, 32768, bar);
+  for (uint32_t o = 0; o < b3; o += 32768) {
+    const uint32_t n = b3 - o < 32768 ? b3 - o : 32768;
+    bulk_g2s(w3_img + o, static_cast<const unsigned char*>(m.mlp2_w3) + o, n, bar);
+  }
+}
+// Rows [row0, row0 + nrows) of W3 (output columns of the third layer; multiples of 8, so whole 8-row groups of the K-major
+// image = contiguous bytes), hi and lo image, into a buffer that holds n_buf rows of each.  Issued by one thread.
+__device__ __forceinline__ void load_w3_rows(const ModelDev& m, unsigned char* w3_buf, int row0, int nrows, int N3t, int n_buf, uint64_t* bar) {
+  const uint32_t bytes = (uint32_t)nrows * kH * 2;
+  mbar_expect_tx(bar, 2 * bytes);
+  for (int img = 0; img < 2; ++img) {
+    const unsigned char* src = static_cast<const unsigned char*>(m.mlp2_w3) + ((size_t)img * N3t + row0) * kH * 2;
+    unsigned char* dst = w3_buf + (size_t)img * n_buf * kH * 2;
+    for (uint32_t o = 0; o < bytes; o += 32768) bulk_g2s(dst + o, src + o, bytes - o < 32768 ? bytes - o : 32768, bar);
+  }
+}
+
+constexpr int kMaxN3 = 416;  // (theta, phi) columns of the largest instantiation (nx = 6, S = 33: 396 -> 400)
 struct SmemTail {  // after the weight images
+  alignas(8) uint64_t bar_w;
+  alignas(8) uint64_t bar_w3;   // streamed W3 halves (instantiations whose W3 does not fit shared memory)
   alignas(16) float b2[kH];
-  alignas(16) float b3[256];
+  alignas(16) float b3[kMaxN3];
   float phase[kMaxS], weight[kMaxS];
   float smean[kMaxNx], sinv[kMaxNx];
   alignas(16) float exch[4][kRows * kMaxNx];     // [tile * column groups + column group] partial ILT sums
@@ -375,27 +403,33 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   constexpr int kCG = 4 / kTiles;                                   // column groups per tile
   constexpr int kGroupWarps = 4 * kCG, kGroupT = 32 * kGroupWarps;  // warps / threads per tile
   constexpr int kColsPerThread = kH / kCG, kC16 = kColsPerThread / 16;
-  constexpr int kChunksA = (kTiles == 1 || N3t <= 128) ? kChunks : (kChunks + 1) / 2;  // chunks in the first column half
+  // kStream (one tile, more than 256 (theta, phi) columns: S = 33 with nx >= 5, the reference class default w_nl.py:73): L3 in
+  // two column halves of at most 256 columns, and W3 - which no longer fits shared memory next to W1 and W2 - streamed: one
+  // buffer of N3a rows, reloaded by TMA bulk copies (L2-resident source) as soon as the product that read it has completed,
+  // each load hidden under the epilogue that follows.
+  constexpr bool kStream = kTiles == 1 && N3t > 256;
+  constexpr int kChunksA = ((kTiles == 1 && !kStream) || N3t <= 128) ? kChunks : (kChunks + 1) / 2;  // chunks in the first column half
   constexpr int N3a = 16 * kChunksA, N3b = N3t - N3a;
-  static_assert((kTiles == 1 || (N3a <= 128 && N3b <= 128)) && N3t <= 256 && Lp + 1 <= 16, "tile shape");
+  constexpr int N3buf = kStream ? N3a : N3t;                          // rows of W3 resident at a time
+  static_assert((kTiles == 1 ? (N3a <= 256 && N3b <= 256) : (N3a <= 128 && N3b <= 128 && N3t <= 256)) && N3t <= kMaxN3 && Lp + 1 <= 16, "tile shape");
   unsigned char* w1_img = smem_raw;                                   // [hi | lo] 128 x 16 halves = 4 KB each
   unsigned char* w2_img = w1_img + 2 * kH * 16 * 2;                   // [hi | lo] 32 KB each
-  unsigned char* w3_img = w2_img + 2 * kH * kH * 2;                   // [hi | lo] N3t * 256 B each
-  SmemTail& s = *reinterpret_cast<SmemTail*>(w3_img + 2 * (size_t)N3t * kH * 2);
+  unsigned char* w3_img = w2_img + 2 * kH * kH * 2;                   // [hi | lo] N3buf * 256 B each
+  SmemTail& s = *reinterpret_cast<SmemTail*>(w3_img + 2 * (size_t)N3buf * kH * 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   {
-    const uint4* s1 = reinterpret_cast<const uint4*>(a.m.mlp2_w1);
-    uint4* d1 = reinterpret_cast<uint4*>(w1_img);
-    for (int i = tid; i < 2 * kH * 16 * 2 / 16; i += kThreads) d1[i] = __ldg(s1 + i);
-    const uint4* s2 = reinterpret_cast<const uint4*>(a.m.mlp2_w2);
-    uint4* d2 = reinterpret_cast<uint4*>(w2_img);
-    for (int i = tid; i < 2 * kH * kH * 2 / 16; i += kThreads) d2[i] = __ldg(s2 + i);
-    const uint4* s3 = reinterpret_cast<const uint4*>(a.m.mlp2_w3);
-    uint4* d3 = reinterpret_cast<uint4*>(w3_img);
-    for (int i = tid; i < 2 * N3t * kH * 2 / 16; i += kThreads) d3[i] = __ldg(s3 + i);
+    // weight images by TMA bulk copies (one issuing thread, counted on bar_w): only the MMA-issuing warps wait for them, so the
+    // load runs under the TMEM allocation and the first operand's preparation - prologue latency is what small plans pay for
+    if (tid == 0) {
+      mbar_init(&s.bar_w, 1);
+      mbar_init(&s.bar_w3, 1);
+      mbar_fence_init();
+      load_weight_images(a.m, w1_img, w2_img, w3_img, N3t, &s.bar_w, !kStream);
+      if (kStream) load_w3_rows(a.m, w3_img, 0, N3a, N3t, N3buf, &s.bar_w3);
+    }
     for (int i = tid; i < kH; i += kThreads) s.b2[i] = a.m.mlp2_c[i];
-    for (int i = tid; i < 256; i += kThreads) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
+    for (int i = tid; i < kMaxN3; i += kThreads) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
     for (int i = tid; i < S; i += kThreads) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
     if (tid < NX) { s.smean[tid] = a.m.state_mean[tid]; s.sinv[tid] = a.m.state_inv_std[tid]; }
     if (tid == 0) {
@@ -428,9 +462,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
     const uint32_t tA = tlane + kColA, tD = tlane + kColD;
     const uint32_t w1_hi = smem_u32(w1_img), w1_lo = w1_hi + kH * 16 * 2;
     const uint32_t w2_hi = smem_u32(w2_img), w2_lo = w2_hi + kH * kH * 2;
-    const uint32_t w3_hi = smem_u32(w3_img), w3_lo = w3_hi + (uint32_t)N3t * kH * 2;
-    const uint32_t w3b_off = (uint32_t)(N3a / 8) * kSbo;
-    uint32_t n = 0;
+    const uint32_t w3_hi = smem_u32(w3_img), w3_lo = w3_hi + (uint32_t)N3buf * kH * 2;
+    const uint32_t w3b_off = kStream ? 0u : (uint32_t)(N3a / 8) * kSbo;
+    uint32_t n = 0, n_w3 = 0;  // products waited for; W3 halves waited for (issuing warp only)
     int tstep = 0;
     auto mark = [&](int ev) {
       if (a.trace && blockIdx.x == 0 && lane == 0 && tstep < 104) a.trace[(tstep * 16 + warp) * 8 + ev] = clock64();
@@ -438,10 +472,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
     // hand-off to the tensor pipe: every warp of the group has finished its TMEM stores / loads (group barrier), then
     // one thread issues product `ev` of the step.  The group waits for that product anyway (strict chain per sample),
     // so the issuing warp being held by the MMA queue costs nothing; the other group keeps the CUDA cores busy.
+    if (wl == 0) mbar_wait(&s.bar_w, 0);  // the issuing warp: weight images landed
     auto issue = [&](int ev) {
       tmem_st_wait();
       fence_before_sync();
       asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGroupT) : "memory");
+      if (kStream && wl == 0 && ev >= 2) { mbar_wait(&s.bar_w3, n_w3 & 1); ++n_w3; }  // this half of W3 has landed
       if (wl == 0 && elect_one()) {
         fence_after_sync();
         if (ev == 0) issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w1_hi, w1_lo, kH, 1, kSbo16);
@@ -553,6 +589,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         for (int c = 0; c < NX; ++c) delta[c] = 0.0f;
         wait_mma();
         mark(5);
+        // the first half's product has read the W3 buffer: the second half streams in under this epilogue
+        if (kStream && wl == 0 && elect_one()) load_w3_rows(a.m, w3_img, N3a, N3b, N3t, N3buf, &s.bar_w3);
         if (active) {
           if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
           else if (cg == 1) L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
@@ -564,11 +602,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
           issue(3);
           wait_mma();
           mark(7);
+          // ... and the first half again for the next step (or the next tile), under this epilogue and the next step's E1 / E2
+          if (kStream && wl == 0 && elect_one()) load_w3_rows(a.m, w3_img, 0, N3a, N3t, N3buf, &s.bar_w3);
           if (active) {
-            constexpr int kFirstB0 = kChunksA + (kChunksA & 1);        // first chunk >= kChunksA with even index
-            constexpr int kFirstB1 = kChunksA + 1 - (kChunksA & 1);    // ... with odd index
-            if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3, kRcp % 10, 2>::run(tD, s.b3, s.phase, s.weight, delta);
-            else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3, kRcp % 10, 2>::run(tD, s.b3, s.phase, s.weight, delta);
+            if constexpr (kCG == 4) {  // four column groups take the second half's chunks round-robin
+              if (cg == 0) L3Loop<NX, S, kChunksA, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
+              else if (cg == 1) L3Loop<NX, S, kChunksA + 1, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
+              else if (cg == 2) L3Loop<NX, S, kChunksA + 2, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
+              else L3Loop<NX, S, kChunksA + 3, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
+            } else {
+              constexpr int kFirstB0 = kChunksA + (kChunksA & 1);        // first chunk >= kChunksA with even index
+              constexpr int kFirstB1 = kChunksA + 1 - (kChunksA & 1);    // ... with odd index
+              if (cg == 0) L3Loop<NX, S, kFirstB0, kChunks, kChunksA, kSplit3, kRcp % 10, 2>::run(tD, s.b3, s.phase, s.weight, delta);
+              else L3Loop<NX, S, kFirstB1, kChunks, kChunksA, kSplit3, kRcp % 10, 2>::run(tD, s.b3, s.phase, s.weight, delta);
+            }
           }
         }
 #pragma unroll
@@ -596,6 +643,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         a.cost_total[kk] = cost_acc + (a.pert_cost ? a.pert_cost[kk] : 0.0f);
       }
     }
+    // the last streamed half (requested for a step that never comes) must have landed before the CTA's shared memory goes
+    if (kStream && wl == 0) mbar_wait(&s.bar_w3, n_w3 & 1);
   }
   fence_before_sync();
   __syncthreads();
@@ -626,6 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
 //   L3         first half N3a = min(N3t, 128) columns, second half the rest (<= 128): A 128 + D 128 columns per tile.
 template <int NX>
 struct SmemTailPP {
+  alignas(8) uint64_t bar_w;
   alignas(16) float b2[kH];
   alignas(16) float b3[256];
   float phase[kMaxS], weight[kMaxS];
@@ -658,15 +708,11 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0));
 
   {
-    const uint4* s1 = reinterpret_cast<const uint4*>(a.m.mlp2_w1);
-    uint4* d1 = reinterpret_cast<uint4*>(w1_img);
-    for (int i = tid; i < 2 * kH * 16 * 2 / 16; i += kThreadsPP) d1[i] = __ldg(s1 + i);
-    const uint4* s2 = reinterpret_cast<const uint4*>(a.m.mlp2_w2);
-    uint4* d2 = reinterpret_cast<uint4*>(w2_img);
-    for (int i = tid; i < 2 * kH * kH * 2 / 16; i += kThreadsPP) d2[i] = __ldg(s2 + i);
-    const uint4* s3 = reinterpret_cast<const uint4*>(a.m.mlp2_w3);
-    uint4* d3 = reinterpret_cast<uint4*>(w3_img);
-    for (int i = tid; i < 2 * N3t * kH * 2 / 16; i += kThreadsPP) d3[i] = __ldg(s3 + i);
+    if (tid == 0) {  // weight images by TMA bulk copies; only the MMA warp waits for them (see rollout_tc2_kernel)
+      mbar_init(&s.bar_w, 1);
+      mbar_fence_init();
+      load_weight_images(a.m, w1_img, w2_img, w3_img, N3t, &s.bar_w);
+    }
     for (int i = tid; i < kH; i += kThreadsPP) s.b2[i] = a.m.mlp2_c[i];
     for (int i = tid; i < 256; i += kThreadsPP) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
     for (int i = tid; i < S; i += kThreadsPP) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
@@ -711,6 +757,7 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
       // products in the epilogue warps' hand-off order, the two tiles strictly alternating: (M1x M1y) then per step
       // (M2x M2y M3ax M3ay [M3bx M3by] M1x' M1y').  ONE issuing warp on purpose: with a warp per tile the two M2 products
       // interleave on the tensor pipe and the one needed first completes last.
+      mbar_wait(&s.bar_w, 0);    // weight images landed
       int mstep = 0, mprod = 0;  // measurement only: the MMA warp's own timeline, second half of the trace buffer
       auto product = [&](int x, int ev) {
         // named barrier 1 + x: the 16 epilogue warps bar.arrive, this warp bar.sync (as an mbarrier, every one of the 16
@@ -1000,7 +1047,8 @@ static int launch_pp(const Args& a, cudaStream_t stream) {
 template <int NX, int S, bool kSplit3, int kRcp, int kTiles>
 static int launch_one_t(const Args& a, cudaStream_t stream) {
   constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
-  const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3t * kH * 2 + sizeof(SmemTail) + 128;
+  constexpr int N3buf = (kTiles == 1 && N3t > 256) ? 16 * ((N3t / 16 + 1) / 2) : N3t;  // streamed W3: one half resident
+  const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3buf * kH * 2 + sizeof(SmemTail) + 128;
   NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
   auto kern = rollout_tc2_kernel<NX, S, kSplit3, kRcp, kTiles>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1017,14 +1065,19 @@ static int launch_one_t(const Args& a, cudaStream_t stream) {
 // two tiles per CTA once the plan is more than one wave of 128-sample tiles, else one tile on all 16 warps
 template <int NX, int S, bool kSplit3, int kRcp>
 static int launch_one(const Args& a, int tiles, cudaStream_t stream) {
-  if (tiles == 3) return launch_pp<NX, S, kSplit3, kRcp>(a, stream);
-  return tiles == 1 ? launch_one_t<NX, S, kSplit3, kRcp, 1>(a, stream) : launch_one_t<NX, S, kSplit3, kRcp, 2>(a, stream);
+  if constexpr (2 * NX * S > 256) {
+    // more (theta, phi) columns than two tiles' accumulators hold: the one-tile form with W3 streamed, whatever the plan size
+    return launch_one_t<NX, S, kSplit3, kRcp, 1>(a, stream);
+  } else {
+    if (tiles == 3) return launch_pp<NX, S, kSplit3, kRcp>(a, stream);
+    return tiles == 1 ? launch_one_t<NX, S, kSplit3, kRcp, 1>(a, stream) : launch_one_t<NX, S, kSplit3, kRcp, 2>(a, stream);
+  }
 }
 
 }  // namespace rt2
 
 bool rollout_has_tensor_core_form(const nlc_model_s* m) {
-  return (m->S == 17 && (m->nx == 3 || m->nx == 5 || m->nx == 6)) || (m->S == 33 && m->nx == 3);
+  return (m->S == 17 || m->S == 33) && (m->nx == 3 || m->nx == 5 || m->nx == 6);
 }
 
 // returns NLC_ERR_UNSUPPORTED when the (nx, S) pair has no tensor-core instantiation (caller falls back)
@@ -1037,6 +1090,7 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
                        unsigned int ready_target, unsigned int* status) {
   rt2::Args a;
   a.ready = ready; a.ready_target = ready_target; a.status = status;
+  if (2 * m->nx * m->S > 256) tiles_per_cta = 1;
   NLC_REQUIRE(!ready || (tiles_per_cta == 1 && (K + 127) / 128 <= 148 && status), NLC_ERR_ARG,
               "rollout: the overlapped form is the one-tile form of plans within one wave");
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
@@ -1054,6 +1108,8 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   NLC_RT2_CASE(5, 17)
   NLC_RT2_CASE(6, 17)
   NLC_RT2_CASE(3, 33)
+  NLC_RT2_CASE(5, 33)
+  NLC_RT2_CASE(6, 33)
 #undef NLC_RT2_CASE
   set_error("tcgen05 rollout has no instantiation for nx=%d S=%d", m->nx, m->S);
   return NLC_ERR_UNSUPPORTED;

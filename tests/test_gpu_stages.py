@@ -363,22 +363,27 @@ def test_rollout_forms_agree_beyond_one_wave(env, K, T, monkeypatch):
         assert relerr(outs["fp32"][1], outs[name][1]) < 1e-4, (name, relerr(outs["fp32"][1], outs[name][1]))
 
 
-@pytest.mark.parametrize("S", [17, 33])
-@pytest.mark.parametrize("K,T", [(1, 1), (33, 3), (300, 9)])
-def test_rollout_s_terms_and_tiny_plans(S, K, T, monkeypatch):
-    """Randomly initialised pendulum models with 17 and 33 Fourier terms (both have tensor-core instantiations; S = 33 takes
-    the two-halves L3 path when two tiles share a CTA), plans down to a single sample and a single step: the tensor-core
-    rollout in both tile forms against the fp32 CUDA-core kernel."""
+@pytest.mark.parametrize("env,S", [("oderl-pendulum", 17), ("oderl-pendulum", 33), ("oderl-cartpole", 33), ("oderl-acrobot", 33)])
+@pytest.mark.parametrize("K,T", [(1, 1), (33, 3), (300, 9), (20000, 4)])
+def test_rollout_s_terms_and_tiny_plans(env, S, K, T, monkeypatch):
+    """Randomly initialised models with 17 and 33 Fourier terms (33 is the reference class default, w_nl.py:73), plans down to
+    a single sample and a single step and up to more than one wave of tiles: every tensor-core rollout form against the fp32
+    CUDA-core kernel.  Pendulum S = 33 takes the two-halves L3 path when two tiles share a CTA; cartpole / acrobot S = 33 have
+    330 / 396 (theta, phi) columns - more than two tiles' accumulators hold and a W3 image beyond shared memory - and always
+    take the one-tile form with L3 in two halves and W3 streamed by TMA (whatever form is asked for)."""
     import ctypes as C
 
     import neurallaplacecontrol_b200 as nlc
+    from oracle import costs
 
     L = _lib()
     lib = L.load()
-    env, nx, nu, B = "oderl-pendulum", 3, 1, 4
+    (nx, nu), B = costs.ENV_DIMS[env], 4
+    if K == 20000 and not (S == 33 and nx > 3):
+        pytest.skip("large plans of the resident-W3 shapes are covered by test_rollout_forms_agree_beyond_one_wave")
     torch.manual_seed(S)
     m = nlc.NeuralLaplaceModel(nx, nu, nx, hidden_units=128, s_recon_terms=S, state_mean=np.zeros(nx), state_std=np.ones(nx),
-                               action_mean=np.array([0.0]), action_std=np.array([1.0]), normalize=True, normalize_time=True, dt=DT,
+                               action_mean=np.array([0.0] * nu), action_std=np.array([1.0]), normalize=True, normalize_time=True, dt=DT,
                                device="cuda:0").double()
     with torch.no_grad():  # keep the Fourier sum in the operating range of a trained model (cf. oracle/gen_golden.py calibrate_)
         last = m.laplace_rep_func.linear_tanh_stack[4]
@@ -388,7 +393,7 @@ def test_rollout_s_terms_and_tiny_plans(S, K, T, monkeypatch):
     h = m.set_prediction_time(DT)
     gen = torch.Generator().manual_seed(K * 100 + T)
     hist = ((torch.rand(K, B - 1 + T, nu, generator=gen) * 2 - 1) * 2.0).cuda().contiguous()
-    state = (torch.tensor([-1.0, 0.0, 1.0]) + 0.05 * torch.randn(K, nx, generator=gen)).cuda().contiguous()
+    state = (torch.tensor(costs_start(env)) + 0.05 * torch.randn(K, nx, generator=gen)).cuda().contiguous()
     p = torch.empty(K, T, 2, device="cuda")
     L.check(lib.nlc_encode_history(h, hist.data_ptr(), K, T, B, p.data_ptr(), L.MATH_MODES["fp32"], L.current_stream_ptr()))
     ro = L.RolloutOpts()
