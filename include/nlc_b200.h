@@ -243,7 +243,7 @@ int nlc_planner_step_profile(nlc_planner_t p, float* ms_out, void* stream);
 
 /* Plans within half a wave of 128-sample tiles run their history encoder BESIDE the rollout kernel (the sequential rollout
  * leaves most SMs idle): *overlapped = 1 if this planner does.  *status = 1 if, in the last control step, the rollout gave
- * up polling for the encoder's output (~4 s: the two kernels were not co-resident - a serialising tool, a shared GPU;
+ * up polling for the encoder's output (~1 s: the two kernels were not co-resident - a serialising tool, a shared GPU;
  * NLC_NO_OVERLAP=1 in the environment keeps the plain sequence); the step's results are then invalid.  Synchronises
  * the device.                                                                                       */
 int nlc_planner_overlap_status(nlc_planner_t p, int* overlapped, int* status);

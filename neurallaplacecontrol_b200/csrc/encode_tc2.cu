@@ -164,9 +164,10 @@ __device__ __forceinline__ void issue_gemm192(uint32_t d_tmem, uint32_t a_hi, ui
 }
 
 constexpr int kThreadsAll = kThreads + 32;        // 16 epilogue warps + the MMA warp: the participants of the named barriers
-// The CTA is launched with the MMA warp's whole register group (setmaxnreg works on groups of 4 warps): 20 warps at 96
-// registers, re-balanced to 112 for the 16 epilogue warps and 64 for the MMA group (16 x 112 + 4 x 64 = the whole file).
-constexpr int kThreadsLaunch = kThreads + 128;
+// (Tried and dropped: launching the MMA warp's whole register group - 20 warps at 96 registers - and re-balancing with
+// setmaxnreg to 104 / 64 or 112 / 32 registers for the epilogue / MMA warps.  2.37 / 2.41 ms against 2.23 ms at config 4:
+// the epilogue does not use the extra registers and the MMA warp issues more slowly on 32.  setmaxnreg.inc draws only on
+// what setmaxnreg.dec released inside the CTA - releasing less than the increase needs blocks the CTA for ever.)
 constexpr int kBarH0 = 2, kBarH1 = 3;             // named barriers: layer-0 / layer-1 operands published (1: output exchange)
 // Layer 0's input projection and biases ride on the tensor cores as one extra K block of the layer-0 state operand:
 //   A block (per window)  [x0_hi x0_lo x0_hi | x1_hi x1_lo x1_hi | 1 1 | 0 ...]      (16 halves)
@@ -195,7 +196,7 @@ struct Smem {
 };
 
 template <bool kSplit3, int GIN, int RZ, int NN, bool kClamp1, bool kTrace = false>
-__global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
+__global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -221,11 +222,11 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
       const unsigned char* sx = reinterpret_cast<const unsigned char*>(a.m.enc2_x);
       for (int l = 0; l < 2; ++l) bulk_g2s(s.wx[l], sx + (size_t)l * kWxBytes, kWxBytes, &s.bar_w);
     }
-    for (int i = tid; i < 2 * 8; i += kThreadsLaunch)  // the zero pad behind each input/bias block
+    for (int i = tid; i < 2 * 8; i += blockDim.x)  // the zero pad behind each input/bias block
       reinterpret_cast<uint4*>(s.wx[i >> 3] + kWxBytes)[i & 7] = make_uint4(0u, 0u, 0u, 0u);
     uint4* dz = reinterpret_cast<uint4*>(s.h0_hi);  // the second half of the [x | 1] block stays zero for ever
-    for (int i = tid; i < (int)(kH0HiBytes / 16); i += kThreadsLaunch) dz[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < 128; i += kThreadsLaunch) s.c[kC2Wout + i] = a.m.enc2_c[kE2Wout + i];
+    for (int i = tid; i < (int)(kH0HiBytes / 16); i += blockDim.x) dz[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 128; i += blockDim.x) s.c[kC2Wout + i] = a.m.enc2_c[kE2Wout + i];
     if (tid < 2) s.c[kC2Bout + tid] = a.m.enc2_c[kE2Bout + tid];
     if (tid == 0) {
       mbar_init(&s.bar_a, 1); mbar_init(&s.bar_b, 1); mbar_init(&s.bar_h0, 1);
@@ -249,12 +250,7 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
   const uint32_t w_x0 = smem_u32(s.wx[0]), w_x1 = smem_u32(s.wx[1]);
   const long long n_tiles = (a.rows + kRows - 1) / kRows;
 
-  if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-  }
-  if (warp > 16) {
-    // the rest of the MMA warp's register group: nothing to do
-  } else if (warp == 16) {
+  if (warp == 16) {
     // =====================================  MMA warp  =====================================
     // mirrors the epilogue warps' publication order: h0 + the next cell's [x | 1] block (-> layer-0 product of the next
     // cell), then h1 / D1 re-armed (-> layer-1 product of the next cell: input part from h0, hidden part from h1)
@@ -313,7 +309,6 @@ __global__ void __launch_bounds__(kThreadsLaunch, 1) encode_tc2_kernel(Args a) {
     }
   } else {
   // =====================================  epilogue warps  =====================================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
   float amean[GIN], ainv[GIN];
 #pragma unroll
   for (int v = 0; v < GIN; ++v) { amean[v] = a.m.act_mean[v]; ainv[v] = a.m.act_inv_std[v]; }
@@ -555,21 +550,21 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   void (*kern)(Args);
   // layer-1 (r, z) clamps are compiled out when the packed weights prove |pre-activation| * log2(e) < 60 (model.cu)
   const bool c1 = !m->enc_l1_bounded;
-#define NLC_ENC_PICK(S3, RZ_, NN_) \
-  (m->gin == 1 ? (c1 ? encode_tc2_kernel<S3, 1, RZ_, NN_, true> : encode_tc2_kernel<S3, 1, RZ_, NN_, false>) \
-               : (c1 ? encode_tc2_kernel<S3, 2, RZ_, NN_, true> : encode_tc2_kernel<S3, 2, RZ_, NN_, false>))
+#define NLC_ENC_PICK(S3, RZ_, NN_, TR) \
+  (m->gin == 1 ? (c1 ? encode_tc2_kernel<S3, 1, RZ_, NN_, true, TR> : encode_tc2_kernel<S3, 1, RZ_, NN_, false, TR>) \
+               : (c1 ? encode_tc2_kernel<S3, 2, RZ_, NN_, true, TR> : encode_tc2_kernel<S3, 2, RZ_, NN_, false, TR>))
   if (!split3) kern = m->gin == 1 ? encode_tc2_kernel<false, 1, kGateTanhApprox, 0, true> : encode_tc2_kernel<false, 2, kGateTanhApprox, 0, true>;
-  else if (rcp_sel == 0) kern = NLC_ENC_PICK(true, 0, 0);
-  else if (rcp_sel == 33) kern = NLC_ENC_PICK(true, 3, 3);
-  else kern = NLC_ENC_PICK(true, 3, 0);
+  else if (rcp_sel == 0) kern = NLC_ENC_PICK(true, 0, 0, false);
+  else if (rcp_sel == 33) kern = NLC_ENC_PICK(true, 3, 3, false);
+  else kern = NLC_ENC_PICK(true, 3, 0, false);
+  if (a.trace && split3) kern = NLC_ENC_PICK(true, 3, 0, true);
 #undef NLC_ENC_PICK
-  if (a.trace && split3) kern = m->gin == 1 ? encode_tc2_kernel<true, 1, 3, 0, true, true> : encode_tc2_kernel<true, 2, 3, 0, true, true>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long n_tiles = ready ? (long long)a.tiles_per_t * T : (a.rows + kRows - 1) / kRows;
   if (ready) a.rows = n_tiles * kRows;  // step-major: every tile is walked; rows beyond K are masked at the output
   const int cap = max_ctas > 0 && max_ctas < 148 ? max_ctas : 148;
   const int grid = (int)(n_tiles < cap ? n_tiles : cap);
-  kern<<<grid, kThreadsLaunch, smem, stream>>>(a);
+  kern<<<grid, kThreadsAll, smem, stream>>>(a);
   NLC_LAUNCH_OK("encode_tc2_kernel");
   return NLC_OK;
 }

@@ -73,7 +73,7 @@ struct Args {
   long long* trace;  // measurement only: clock64 timeline of CTA 0, [step][warp][8 events]
   // overlapped planner step (planner.cu): the history encoder runs BESIDE this kernel on the other SMs in step-major order
   // and bumps ready[t] as the windows of step t complete; p(., t) may be read once ready[t] >= ready_target.  A poll that
-  // does not complete within ~4 s (the encoder is not co-resident: a serialising profiler, a shared GPU) sets *status = 1
+  // does not complete within ~1 s (the encoder is not co-resident: a serialising profiler, a shared GPU) sets *status = 1
   // and lets the step finish on whatever is there instead of hanging the device.
   const unsigned int* ready;
   unsigned int ready_target;
@@ -90,7 +90,10 @@ __device__ __forceinline__ void wait_windows_ready(const Args& a, int t, int lan
   if (lane == 0) {
     const long long t0 = clock64();
     while (ld_acquire_gpu(a.ready + t) < a.ready_target) {
-      if (clock64() - t0 > (1ll << 33)) { atomicExch(a.status, 1u); break; }  // ~4 s
+      // give up after ~1 s, and at once if any other warp of the launch already has: a plan that is not being encoded beside
+      // this kernel costs one second, not one second per step and CTA
+      if (ld_acquire_gpu(a.status) != 0u) break;
+      if (clock64() - t0 > (1ll << 31)) { atomicExch(a.status, 1u); break; }
       __nanosleep(100);
     }
   }
