@@ -300,7 +300,9 @@ def time_plan(ctx, env, K, H, group, steps, warmup):
     ms_dev, _, launches = ctx.timed(lambda: planner.command(state_dev, buf_dev), steps, warmup)
 
     def e2e_step():
-        return planner.command(inp["state"], inp["buffer"]).cpu()
+        a = planner.command(inp["state"], inp["buffer"])  # host buffers in
+        # one shard: the C entry point already synchronised and left the action on the host; sharded: read it back here
+        return planner.last_action_host if planner.G == 1 else a.cpu()
 
     _, ms_e2e, _ = ctx.timed(e2e_step, steps, warmup)
     return {"ms_dev": ms_dev, "ms_e2e": ms_e2e, "launches": launches, "inp": inp, "model": model, "planner": planner,

@@ -38,6 +38,7 @@ struct RollArgs {
   const float* row_b1;  // [K][128]
   const float* row_tn;  // [K]
   int termRows;  // rows of the a1/term buffer
+  int w3_smem;   // 0: W3 (128 x N3p floats) does not fit shared memory next to W2 (S = 33 with nx >= 5) and is read from L2
 };
 
 __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ act, const float* __restrict__ WT, int ldw,
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
   const int nx = a.nx, S = a.S, N3p = a.N3p, R = a.R, Lp = nx + 2, nP = nx * S;
   float* w2 = smem;                       // [128][128]
   float* w3 = w2 + kH * kH;               // [128][N3p]
-  float* a1 = w3 + kH * N3p;              // [R][128]; reused as term[R][nP] after L2 (nP may exceed 128)
+  float* a1 = w3 + (a.w3_smem ? kH * N3p : 0);  // [R][128]; reused as term[R][nP] after L2 (nP may exceed 128)
+  const float* w3r = a.w3_smem ? w3 : a.m.w3_t;
   float* a2 = a1 + R * (a.termRows);      // [R][128]
   float* w1x = a2 + R * kH;               // [Lp][128]
   float* b1 = w1x + Lp * kH;              // [128]
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
   const int k0 = blockIdx.x * R;
 
   for (int i = tid; i < kH * kH / 4; i += 256) reinterpret_cast<float4*>(w2)[i] = __ldg(reinterpret_cast<const float4*>(a.m.w2_t) + i);
-  for (int i = tid; i < kH * N3p / 4; i += 256) reinterpret_cast<float4*>(w3)[i] = __ldg(reinterpret_cast<const float4*>(a.m.w3_t) + i);
+  if (a.w3_smem)
+    for (int i = tid; i < kH * N3p / 4; i += 256) reinterpret_cast<float4*>(w3)[i] = __ldg(reinterpret_cast<const float4*>(a.m.w3_t) + i);
   for (int i = tid; i < Lp * kH; i += 256) w1x[i] = a.m.w1x_t[i];
   for (int i = tid; i < kH; i += 256) { b1[i] = a.m.b1_fold[i]; b2[i] = a.m.b2[i]; }
   for (int i = tid; i < N3p; i += 256) b3[i] = a.m.b3[i];
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
       float acc[kRT][4];
 #pragma unroll
       for (int i = 0; i < kRT; ++i) { acc[i][0] = b3[4 * cg]; acc[i][1] = b3[4 * cg + 1]; acc[i][2] = b3[4 * cg + 2]; acc[i][3] = b3[4 * cg + 3]; }
-      tile_gemm_128(a2, w3, N3p, rg * kRT, 4 * cg, acc);
+      tile_gemm_128(a2, w3r, N3p, rg * kRT, 4 * cg, acc);
       const int pair0 = 2 * cg;  // pairs pair0, pair0+1 ; pair = c*S + k
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
   }
 }
 
-static size_t rollout_smem_floats(int nx, int S, int N3p, int R, int termRows) {
+static size_t rollout_smem_floats(int nx, int S, int N3p, int R, int termRows, bool w3_smem = true) {
   const int Lp = nx + 2;
-  return (size_t)kH * kH + (size_t)kH * N3p + (size_t)R * termRows + (size_t)R * kH + (size_t)Lp * kH + 2 * kH + N3p +
+  return (size_t)kH * kH + (w3_smem ? (size_t)kH * N3p : 0) + (size_t)R * termRows + (size_t)R * kH + (size_t)Lp * kH + 2 * kH + N3p +
          2 * S + (size_t)R * Lp + (size_t)R * nx + 2 * nx + 2 * (size_t)R + 8;
 }
 
@@ -242,15 +245,18 @@ int launch_rollout_fp32(nlc_model_s* m, const nlc_rollout_opts* o, const float* 
   a.termRows = ((nP > kH ? nP : kH) + 3) / 4 * 4;
   const size_t max_bytes = 227 * 1024;
   int R = 64;
-  while (R > 8 && rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows) * sizeof(float) > max_bytes) R -= 8;
-  NLC_REQUIRE(rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows) * sizeof(float) <= max_bytes, NLC_ERR_SHAPE,
+  // W3 stays in shared memory when at least 16 rows fit beside it; else (S = 33 with nx >= 5) it is read through L2
+  bool w3s = rollout_smem_floats(m->nx, m->S, m->N3p, 16, a.termRows, true) * sizeof(float) <= max_bytes;
+  a.w3_smem = w3s ? 1 : 0;
+  while (R > 8 && rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float) > max_bytes) R -= 8;
+  NLC_REQUIRE(rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float) <= max_bytes, NLC_ERR_SHAPE,
               "rollout: model (nx=%d, S=%d) does not fit shared memory", m->nx, m->S);
   // spread small K over the SMs: the horizon is sequential, so latency is set by the rows one CTA owns
   int want = (K + 147) / 148;
   want = (want + 7) / 8 * 8;
   if (want < R) R = want;
   a.R = R;
-  const size_t smem = rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows) * sizeof(float);
+  const size_t smem = rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float);
   NLC_CUDA_OK(cudaFuncSetAttribute(rollout_nl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes));
   const int grid = (K + R - 1) / R;
   rollout_nl_kernel<<<grid, 256, smem, stream>>>(a);

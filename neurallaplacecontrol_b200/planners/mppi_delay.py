@@ -150,6 +150,7 @@ class MPPIDelay:
         self._handle_B = None
         self._handle_model = None
         self._exchange = False
+        self.last_action_host = None
         self._views = {}
         if U_init is None:
             U_init = self._replicated(self.noise_dist.sample((self.T,)))  # mppi_delay.py:163-164
@@ -419,7 +420,11 @@ class MPPIDelay:
                 _lib.check(self._lib.nlc_planner_command_host(h, sp, bp, None, out.ctypes.data_as(C.POINTER(C.c_double)), stream),
                            "nlc_planner_command_host")
                 self._calls += 1
-                return torch.from_numpy(out).to(device=self.d, dtype=self.dtype)
+                # the action already crossed PCIe inside the call: it is kept on the object for callers that want the host
+                # value (mppi_with_model.py:262 moves it to numpy at once); the returned tensor is the planner's own
+                # device-resident copy, cast like the reference's - no second transfer either way
+                self.last_action_host = out
+                return self._buf(_lib.BUF_ACTION, (self.nu,)).to(self.dtype)
             st = self._buf(_lib.BUF_STATE, (self.K_local, self.nx))
             if per_sample:
                 if state.shape[0] != self.K:
