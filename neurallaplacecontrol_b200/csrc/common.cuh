@@ -46,6 +46,23 @@ enum { kWarnEncoderFfma = 0, kWarnRolloutFfma = 1, kWarnForwardTsFfma = 2 };
     }                                 \
   } while (0)
 
+// publication of the shard's triple from the last block of softmax_sum_kernel (G = 0: none)
+struct ExchangePub {
+  float* const* mailboxes;
+  int G, rank, stride;
+  const unsigned long long* step_ctr;
+};
+
+// End-of-step housekeeping the planner folds into its combine kernel instead of launching tiny kernels / memsets for it
+// (planner.cu): every pointer optional.
+struct StepTail {
+  const float* U_src;            // the rolled control sequence the update applies to (nullptr: U is updated in place)
+  unsigned long long* call_ctr;  // sampler call index += 1: the next control step draws fresh samples
+  void* softmax_ws;              // stage 4 workspace header: re-armed for the next step (min = +inf, ticket = 0)
+  unsigned int* ready;           // encoder readiness counters of the overlapped step: zeroed for the next step
+  int n_ready;
+};
+
 constexpr int kMaxNx = 8;
 constexpr int kMaxNu = 4;   // GRU input width limit (nu, or nu+1 with encode_obs_time)
 constexpr int kMaxS = 136;  // s-terms supported by the fused rollout (planner uses 17 or 33)

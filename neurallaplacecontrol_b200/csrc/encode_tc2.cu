@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     // The weight images (144 KB + the two input/bias blocks) come in by TMA bulk copies issued by ONE thread and counted on
     // an mbarrier that only the MMA warp waits for - no other thread ever reads them - so the load runs under the TMEM
     // allocation, the zero fills and the first window fetch instead of in front of them.
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {  // (elect.sync, not tid == 0: the copies' operands then stay in uniform registers)
       mbar_init(&s.bar_w, 1);
       mbar_fence_init();
       mbar_expect_tx(&s.bar_w, (uint32_t)(3 * 2 * kWBytes + 2 * kWxBytes));

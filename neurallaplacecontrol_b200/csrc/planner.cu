@@ -51,11 +51,12 @@ namespace nlc {
 int perturb_launch(const nlc_mppi_params* p, const float* U_prev_dev, float* U_dev, int roll, const float* noise_in_dev,
                    uint64_t seed, uint64_t call_index, const unsigned long long* call_index_dev, const float* action_buffer_dev,
                    float* perturbed_dev, float* noise_dev, float* hist_dev, float* actions_dev, float* pert_cost_dev, void* stream);
-int launch_bump_counter(unsigned long long* ctr, cudaStream_t stream);
-int launch_exchange_publish(const float* triple, float* const* mailboxes_dev, int G, int rank, int stride, int n,
-                            const unsigned long long* step_ctr, cudaStream_t s);
+int softmax_partial_impl(const float* cost_dev, const float* noise_dev, int K, int T, int nu, float lambda_, float* triple_dev,
+                         float* weights_dev, void* workspace_dev, bool with_init, const ExchangePub& pub, cudaStream_t s);
+int launch_combine(const float* triples_dev, int G, int T, int nu, float lambda_, float u_scale, float* U_dev, float* action_dev,
+                   float* stats_dev, const StepTail& tl, cudaStream_t s);
 int launch_combine_exchange(float* mailbox, int G, int stride, int T, int nu, float lambda_, float u_scale, float* U, float* action,
-                            float* stats, unsigned long long* step_ctr, unsigned int* status, cudaStream_t s);
+                            float* stats, unsigned long long* step_ctr, unsigned int* status, const StepTail& tl, cudaStream_t s);
 bool encoder_is_tensor_core(nlc_model_t m, int B, int math_mode);
 int encode_history_overlapped(nlc_model_t m, const float* hist_dev, int K, int T, int B, float* p_dev, int math_mode,
                               unsigned int* ready, int max_ctas, cudaStream_t s);
@@ -124,6 +125,8 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   for (size_t i = 0; i < sizeof(slots) / sizeof(slots[0]); ++i) *slots[i] = base + offs[i];
   if (!d->keep_states) p->states = nullptr;
   p->softmax_ws = base + offs[17];
+  // stage 4's workspace header starts armed (min = +inf as all-ones, ticket = 0); every combine kernel re-arms it (StepTail)
+  if (cudaMemset(p->softmax_ws, 0xFF, 4) != cudaSuccess) { set_error("planner: memset failed"); return fail(NLC_ERR_CUDA); }
   if (cudaMallocHost(&p->h_in, sizeof(float) * (nx + B * nu)) != cudaSuccess || cudaMallocHost(&p->h_out, sizeof(float) * 4) != cudaSuccess) {
     cudaGetLastError(); set_error("planner: pinned allocation failed"); return fail(NLC_ERR_NOMEM);
   }
@@ -322,24 +325,24 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
   rc = perturb_launch(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, 0, p->call_ctr, action_buffer_dev, p->perturbed,
                       p->noise, p->hist, p->actions, p->pert_cost, stream);
   if (rc != NLC_OK) return rc;
-  rc = launch_bump_counter(p->call_ctr, s);  // the next control step draws fresh samples
-  if (rc != NLC_OK) return rc;
-  p->calls++;
+  p->calls++;  // (the device-side call index is bumped by the step's combine kernel)
   if (ev) NLC_CUDA_OK(cudaEventRecord(ev[1], s));
-  if (p->overlap && !ev) {
+  if (p->overlap) {
     // encoder || rollout: fork after stage 1, the encoder on this stream with all SMs but the rollout's, the rollout (one
     // 128-sample tile per CTA) on the side stream, join before stage 4.  The encoder is launched FIRST in host order: a
     // tool that serialises kernels then runs it to completion before the rollout starts polling.
     const int n_tiles = (mp.K + 127) / 128;
-    NLC_CUDA_OK(cudaMemsetAsync(p->ready, 0, sizeof(unsigned int) * (mp.T + 1), s));
+    // (the readiness counters were zeroed by the previous step's combine kernel)
     NLC_CUDA_OK(cudaEventRecord(p->ev_fork, s));
     NLC_CUDA_OK(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
     rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148 - n_tiles, s);
     if (rc != NLC_OK) return rc;
+    if (ev) NLC_CUDA_OK(cudaEventRecord(ev[2], s));  // profile: end of the encoder's own span
     rc = launch_rollout_overlapped(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,
                                    mp.nu, p->cost_total, p->states, p->d.math_mode, p->ready, 4u * (unsigned)n_tiles, p->ready + mp.T,
                                    p->side_stream);
     if (rc != NLC_OK) return rc;
+    if (ev) NLC_CUDA_OK(cudaEventRecord(ev[5], p->side_stream));  // profile: end of the rollout's span (it starts at ev[1])
     NLC_CUDA_OK(cudaEventRecord(p->ev_join, p->side_stream));
     NLC_CUDA_OK(cudaStreamWaitEvent(s, p->ev_join, 0));
   } else {
@@ -353,10 +356,10 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
     if (rc != NLC_OK) return rc;
   }
   if (ev) NLC_CUDA_OK(cudaEventRecord(ev[3], s));
-  rc = nlc_softmax_partial(p->cost_total, p->noise, mp.K, mp.T, mp.nu, mp.lambda_, p->triple, p->weights, p->softmax_ws, stream);
-  if (rc != NLC_OK || !p->xchg) return rc;
-  // connected shards: this shard's triple goes straight into every peer's mailbox over NVLink
-  return launch_exchange_publish(p->triple, p->mailboxes_dev, p->d.n_shards, p->d.shard_index, p->xstride, 2 + mp.T * mp.nu, p->xstep, s);
+  // connected shards: the last block of the sum kernel stores this shard's triple straight into every peer's mailbox over NVLink
+  const ExchangePub pub = p->xchg ? ExchangePub{p->mailboxes_dev, p->d.n_shards, p->d.shard_index, p->xstride, p->xstep}
+                                  : ExchangePub{nullptr, 0, 0, 0, nullptr};
+  return softmax_partial_impl(p->cost_total, p->noise, mp.K, mp.T, mp.nu, mp.lambda_, p->triple, p->weights, p->softmax_ws, false, pub, s);
 }
 
 extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int state_per_sample,
@@ -367,21 +370,28 @@ extern "C" int nlc_planner_rollout(nlc_planner_t p, const float* state_dev, int 
 
 // Measurement entry point: one control step on the planner's own input buffers as DIRECT launches (no graph) with CUDA
 // events at the stage boundaries, so the kernels are timed inside the step (warm L2, back to back) rather than alone.
-// ms_out[0..3] = perturb, history encoder, rollout + cost, softmax update (partial + combine).  Synchronises the stream.
+// ms_out[0..5] = perturb, history encoder, rollout + cost, softmax update (partial + combine), encoder-and-rollout section,
+// 1 if the two ran side by side (then [1] and [2] are their overlapping spans from the fork, [4] the section's wall time;
+// otherwise [4] = [1] + [2]).  Synchronises the stream.
 extern "C" int nlc_planner_step_profile(nlc_planner_t p, float* ms_out, void* stream) {
   NLC_REQUIRE(p && ms_out, NLC_ERR_ARG, "nlc_planner_step_profile: null argument");
   NLC_REQUIRE(p->d.n_shards == 1, NLC_ERR_UNSUPPORTED, "nlc_planner_step_profile is a single-shard entry point");
   NLC_CUDA_OK(cudaSetDevice(p->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaEvent_t ev[5];
+  cudaEvent_t ev[6];
   for (auto& e : ev) NLC_CUDA_OK(cudaEventCreate(&e));
   int rc = planner_rollout_impl(p, p->state_in, 0, p->abuf_in, nullptr, stream, ev);
   if (rc == NLC_OK) rc = nlc_planner_finish(p, stream);
   if (rc == NLC_OK && cudaEventRecord(ev[4], s) != cudaSuccess) rc = NLC_ERR_CUDA;
   if (rc == NLC_OK && cudaEventSynchronize(ev[4]) != cudaSuccess) rc = NLC_ERR_CUDA;
-  if (rc == NLC_OK)
-    for (int i = 0; i < 4; ++i)
-      if (cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]) != cudaSuccess) rc = NLC_ERR_CUDA;
+  if (rc == NLC_OK) {
+    bool ok = cudaEventElapsedTime(&ms_out[0], ev[0], ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms_out[1], ev[1], ev[2]) == cudaSuccess &&
+              cudaEventElapsedTime(&ms_out[3], ev[3], ev[4]) == cudaSuccess && cudaEventElapsedTime(&ms_out[4], ev[1], ev[3]) == cudaSuccess;
+    if (p->overlap) ok = ok && cudaEventElapsedTime(&ms_out[2], ev[1], ev[5]) == cudaSuccess;
+    else ok = ok && cudaEventElapsedTime(&ms_out[2], ev[2], ev[3]) == cudaSuccess;
+    ms_out[5] = p->overlap ? 1.0f : 0.0f;
+    if (!ok) rc = NLC_ERR_CUDA;
+  }
   for (auto& e : ev) cudaEventDestroy(e);
   if (rc == NLC_ERR_CUDA) { set_error("nlc_planner_step_profile: CUDA event error: %s", cudaGetErrorString(cudaGetLastError())); }
   return rc;
@@ -406,13 +416,14 @@ extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {
   const nlc_mppi_params& mp = p->d.mppi;
   NLC_CUDA_OK(cudaSetDevice(p->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // U <- rolled U (the update is applied to the rolled sequence, mppi_delay.py:199-216)
-  NLC_CUDA_OK(cudaMemcpyAsync(p->U, p->U_rolled, sizeof(float) * mp.T * mp.nu, cudaMemcpyDeviceToDevice, s));
+  // the update is applied to the rolled sequence (mppi_delay.py:199-216); the same kernel bumps the sampler's call index and
+  // re-arms stage 4's workspace and the encoder readiness counters for the next control step
+  const StepTail tl{p->U_rolled, p->call_ctr, p->softmax_ws, p->overlap ? p->ready : nullptr, mp.T};
   if (p->xchg)  // wait (on the device) for the G triples of this control step in the own mailbox, then combine
     return launch_combine_exchange(p->mailbox, p->d.n_shards, p->xstride, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats,
-                                   p->xstep, p->xstatus, s);
+                                   p->xstep, p->xstatus, tl, s);
   const float* triples = p->d.n_shards == 1 ? p->triple : p->all_triples;
-  return nlc_softmax_combine(triples, p->d.n_shards, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats, stream);
+  return launch_combine(triples, p->d.n_shards, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats, tl, s);
 }
 
 // One whole control step on the planner's own input buffers (state_in [nx], abuf_in [B][nu]), on-device sampler.
@@ -486,7 +497,7 @@ extern "C" int nlc_planner_step(nlc_planner_t p, void* stream) {
   if (p->graph_core) {
     NLC_CUDA_OK(cudaGraphLaunch(p->graph_core, static_cast<cudaStream_t>(stream)));
     p->calls++;
-    count_launch(8);
+    count_launch(p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE ? 6 : 5);
     return NLC_OK;
   }
   return planner_core_direct(p, stream);
@@ -495,7 +506,8 @@ extern "C" int nlc_planner_step(nlc_planner_t p, void* stream) {
 extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_host, const double* action_buffer_host,
                                         const float* noise_in_dev, double* action_host, void* stream) {
   NLC_REQUIRE(p && state_host && action_buffer_host && action_host, NLC_ERR_ARG, "nlc_planner_command_host: null argument");
-  NLC_REQUIRE(p->d.n_shards == 1, NLC_ERR_UNSUPPORTED, "nlc_planner_command_host is the single-shard entry point");
+  NLC_REQUIRE(p->d.n_shards == 1 || p->xchg, NLC_ERR_UNSUPPORTED,
+              "nlc_planner_command_host needs a single shard, or shards connected by nlc_planner_exchange_connect");
   const nlc_mppi_params& mp = p->d.mppi;
   const int nx = p->d.nx, nb = mp.B * mp.nu;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -507,7 +519,7 @@ extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_hos
   if (!noise_in_dev && p->graph_host) {  // the whole step, copies included, as one graph launch
     NLC_CUDA_OK(cudaGraphLaunch(p->graph_host, s));
     p->calls++;
-    count_launch(8);
+    count_launch(p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE ? 6 : 5);
   } else {
     NLC_CUDA_OK(cudaMemcpyAsync(p->state_in, p->h_in, sizeof(float) * nx, cudaMemcpyHostToDevice, s));
     NLC_CUDA_OK(cudaMemcpyAsync(p->abuf_in, p->h_in + nx, sizeof(float) * nb, cudaMemcpyHostToDevice, s));

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   {
     // weight images by TMA bulk copies (one issuing thread, counted on bar_w): only the MMA-issuing warps wait for them, so the
     // load runs under the TMEM allocation and the first operand's preparation - prologue latency is what small plans pay for
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {  // (elect.sync, not tid == 0: the copies' operands then stay in uniform registers)
       mbar_init(&s.bar_w, 1);
       mbar_init(&s.bar_w3, 1);
       mbar_fence_init();
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0));
 
   {
-    if (tid == 0) {  // weight images by TMA bulk copies; only the MMA warp waits for them (see rollout_tc2_kernel)
+    if (warp == 0 && elect_one()) {  // weight images by TMA bulk copies; only the MMA warp waits for them (see rollout_tc2_kernel)
       mbar_init(&s.bar_w, 1);
       mbar_fence_init();
       load_weight_images(a.m, w1_img, w2_img, w3_img, N3t, &s.bar_w);

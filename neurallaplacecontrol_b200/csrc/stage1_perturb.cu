@@ -111,14 +111,6 @@ __global__ void __launch_bounds__(256) perturb_kernel(PerturbArgs a) {
   }
 }
 
-__global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1ull; }
-
-int launch_bump_counter(unsigned long long* ctr, cudaStream_t stream) {
-  bump_counter_kernel<<<1, 1, 0, stream>>>(ctr);
-  NLC_LAUNCH_OK("bump_counter_kernel");
-  return NLC_OK;
-}
-
 // nlc_perturb with the call index optionally taken from device memory (call_index_dev != nullptr)
 int perturb_launch(const nlc_mppi_params* p, const float* U_prev_dev, float* U_dev, int roll, const float* noise_in_dev,
                    uint64_t seed, uint64_t call_index, const unsigned long long* call_index_dev, const float* action_buffer_dev,

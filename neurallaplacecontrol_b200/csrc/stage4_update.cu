@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) softmax_min_kernel(const float* __restric
 __global__ void __launch_bounds__(256) softmax_sum_kernel(const float* __restrict__ cost, const float* __restrict__ noise,
                                                           int K, int TN, float inv_lambda, SoftWs* ws,
                                                           float* partials /*[grid][1+TN]*/, float* triple,
-                                                          float* weights, int rows_per_block) {
+                                                          float* weights, int rows_per_block, ExchangePub pub) {
   __shared__ float red[8][257];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float beta = ord2f(ws->min_ord);
@@ -128,17 +128,43 @@ __global__ void __launch_bounds__(256) softmax_sum_kernel(const float* __restric
   __syncthreads();
   if (last) {  // fixed block order => run-to-run identical sums
     __threadfence();
+    const unsigned long long step = pub.G ? *pub.step_ctr : 0ull;
+    const int par = (int)(step & 1ull);
     for (int c = threadIdx.x; c < 1 + TN; c += blockDim.x) {
       float sacc = 0.0f;
       for (unsigned bb = 0; bb < gridDim.x; ++bb) sacc += partials[(size_t)bb * (1 + TN) + c];
       triple[1 + c] = sacc;
+      // connected shards (see the exchange notes below): the triple goes straight into every shard's mailbox over NVLink
+      for (int g = 0; g < pub.G; ++g) pub.mailboxes[g][((size_t)par * pub.G + pub.rank) * pub.stride + 1 + c] = sacc;
     }
-    if (threadIdx.x == 0) triple[0] = beta;
+    if (threadIdx.x == 0) {
+      triple[0] = beta;
+      for (int g = 0; g < pub.G; ++g) pub.mailboxes[g][((size_t)par * pub.G + pub.rank) * pub.stride] = beta;
+    }
+    if (pub.G) {
+      __threadfence_system();
+      __syncthreads();
+      if ((int)threadIdx.x < pub.G) {
+        unsigned int* seq = reinterpret_cast<unsigned int*>(pub.mailboxes[threadIdx.x] + (size_t)2 * pub.G * pub.stride) + par * pub.G + pub.rank;
+        const unsigned int id = (unsigned int)(step + 1ull);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(seq), "r"(id) : "memory");
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void step_tail(const StepTail& tl) {
+  // called after the combine's last use of the step's data by every thread of the (single) block
+  __syncthreads();
+  if (tl.ready) for (int i = threadIdx.x; i < tl.n_ready; i += blockDim.x) tl.ready[i] = 0u;
+  if (threadIdx.x == 0) {
+    if (tl.call_ctr) *tl.call_ctr += 1ull;
+    if (tl.softmax_ws) { SoftWs* ws = static_cast<SoftWs*>(tl.softmax_ws); ws->min_ord = 0xffffffffu; ws->ticket = 0u; }
   }
 }
 
 __global__ void softmax_combine_kernel(const float* __restrict__ triples, int G, int TN, int nu, float inv_lambda,
-                                       float u_scale, float* U, float* action, float* stats) {
+                                       float u_scale, float* U, float* action, float* stats, StepTail tl) {
   const int stride = 2 + TN;
   float beta = INFINITY;
   for (int g = 0; g < G; ++g) beta = fminf(beta, triples[g * stride]);
@@ -147,42 +173,26 @@ __global__ void softmax_combine_kernel(const float* __restrict__ triples, int G,
   for (int c = threadIdx.x; c < TN; c += blockDim.x) {
     float W = 0.0f;
     for (int g = 0; g < G; ++g) W = fmaf(triples[g * stride + 2 + c], exp_acc(-inv_lambda * (triples[g * stride] - beta)), W);
-    const float u = U[c] + W / eta;  // mppi_delay.py:214-216
+    const float u = (tl.U_src ? tl.U_src[c] : U[c]) + W / eta;  // mppi_delay.py:214-216
     U[c] = u;
     if (c < nu && action) action[c] = u * u_scale;  // :217-224
   }
   if (threadIdx.x == 0 && stats) { stats[0] = beta; stats[1] = eta; }
+  step_tail(tl);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Exchange of the per-shard triples WITHOUT a collective library (K sharded over the GPUs of one node): every shard owns
 // a "mailbox" in its own HBM,  float triples[2][G][stride]  followed by  unsigned seq[2][G];  peers map it through CUDA IPC.
-//   publish  each shard stores its triple into slot [parity][rank] of EVERY shard's mailbox over NVLink (plain peer
-//            stores), fences system-wide, then releases seq[parity][rank] = step id in each mailbox;
+//   publish  the last block of softmax_sum_kernel stores the shard's triple into slot [parity][rank] of EVERY shard's mailbox
+//            over NVLink (plain peer stores), fences system-wide, then releases seq[parity][rank] = step id in each mailbox;
 //   combine  polls its OWN mailbox until all G seq words carry the step id (acquire), then merges as softmax_combine_kernel.
 // Parity = step & 1: a shard can be at most one control step ahead of another (its next combine needs everybody's next
 // triple), so two slots are enough.  No host, no NCCL, no extra stream: the sharded control step is one CUDA graph.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) exchange_publish_kernel(const float* __restrict__ triple, float* const* __restrict__ mailboxes,
-                                                               int G, int rank, int stride, int n, const unsigned long long* step_ctr) {
-  const unsigned long long step = *step_ctr;
-  const int par = (int)(step & 1ull);
-  for (int g = 0; g < G; ++g) {
-    float* dst = mailboxes[g] + ((size_t)par * G + rank) * stride;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) dst[c] = triple[c];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < G) {
-    unsigned int* seq = reinterpret_cast<unsigned int*>(mailboxes[threadIdx.x] + (size_t)2 * G * stride) + par * G + rank;
-    const unsigned int id = (unsigned int)(step + 1ull);
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(seq), "r"(id) : "memory");
-  }
-}
-
 __global__ void __launch_bounds__(128) softmax_combine_exchange_kernel(float* mailbox, int G, int stride, int TN, int nu, float inv_lambda,
                                                                        float u_scale, float* U, float* action, float* stats,
-                                                                       unsigned long long* step_ctr, unsigned int* status) {
+                                                                       unsigned long long* step_ctr, unsigned int* status, StepTail tl) {
   const unsigned long long step = *step_ctr;
   const int par = (int)(step & 1ull);
   const unsigned int id = (unsigned int)(step + 1ull);
@@ -206,24 +216,20 @@ __global__ void __launch_bounds__(128) softmax_combine_exchange_kernel(float* ma
   for (int c = threadIdx.x; c < TN; c += blockDim.x) {
     float W = 0.0f;
     for (int g = 0; g < G; ++g) W = fmaf(triples[g * stride + 2 + c], exp_acc(-inv_lambda * (triples[g * stride] - beta)), W);
-    const float u = U[c] + W / eta;  // mppi_delay.py:214-216
+    const float u = (tl.U_src ? tl.U_src[c] : U[c]) + W / eta;  // mppi_delay.py:214-216
     U[c] = u;
     if (c < nu && action) action[c] = u * u_scale;  // :217-224
   }
   if (threadIdx.x == 0 && stats) { stats[0] = beta; stats[1] = eta; }
   __syncthreads();
   if (threadIdx.x == 0) *step_ctr = step + 1ull;
+  step_tail(tl);
 }
 
-int launch_exchange_publish(const float* triple, float* const* mailboxes_dev, int G, int rank, int stride, int n,
-                            const unsigned long long* step_ctr, cudaStream_t s) {
-  exchange_publish_kernel<<<1, 128, 0, s>>>(triple, mailboxes_dev, G, rank, stride, n, step_ctr);
-  NLC_LAUNCH_OK("exchange_publish_kernel");
-  return NLC_OK;
-}
 int launch_combine_exchange(float* mailbox, int G, int stride, int T, int nu, float lambda_, float u_scale, float* U, float* action,
-                            float* stats, unsigned long long* step_ctr, unsigned int* status, cudaStream_t s) {
-  softmax_combine_exchange_kernel<<<1, 128, 0, s>>>(mailbox, G, stride, T * nu, nu, 1.0f / lambda_, u_scale, U, action, stats, step_ctr, status);
+                            float* stats, unsigned long long* step_ctr, unsigned int* status, const StepTail& tl, cudaStream_t s) {
+  softmax_combine_exchange_kernel<<<1, 128, 0, s>>>(mailbox, G, stride, T * nu, nu, 1.0f / lambda_, u_scale, U, action, stats, step_ctr,
+                                                    status, tl);
   NLC_LAUNCH_OK("softmax_combine_exchange_kernel");
   return NLC_OK;
 }
@@ -243,19 +249,39 @@ extern "C" int64_t nlc_softmax_workspace_bytes(int K, int TN) {
   return 256 + (int64_t)sum_grid(K) * (1 + TN) * (int64_t)sizeof(float);
 }
 
+namespace nlc {
+// planner.cu: stage 4's shard-local half.  with_init = false: the workspace header was re-armed by the previous step's
+// combine kernel (StepTail); pub: publish the triple to connected shards from the sum kernel's last block.
+int softmax_partial_impl(const float* cost_dev, const float* noise_dev, int K, int T, int nu, float lambda_, float* triple_dev,
+                         float* weights_dev, void* workspace_dev, bool with_init, const ExchangePub& pub, cudaStream_t s);
+int launch_combine(const float* triples_dev, int G, int T, int nu, float lambda_, float u_scale, float* U_dev, float* action_dev,
+                   float* stats_dev, const StepTail& tl, cudaStream_t s) {
+  softmax_combine_kernel<<<1, 128, 0, s>>>(triples_dev, G, T * nu, nu, 1.0f / lambda_, u_scale, U_dev, action_dev, stats_dev, tl);
+  NLC_LAUNCH_OK("softmax_combine_kernel");
+  return NLC_OK;
+}
+}  // namespace nlc
+
 extern "C" int nlc_softmax_partial(const float* cost_dev, const float* noise_dev, int K, int T, int nu, float lambda_,
                                    float* triple_dev, float* weights_dev, void* workspace_dev, void* stream) {
+  return softmax_partial_impl(cost_dev, noise_dev, K, T, nu, lambda_, triple_dev, weights_dev, workspace_dev, true,
+                              ExchangePub{nullptr, 0, 0, 0, nullptr}, static_cast<cudaStream_t>(stream));
+}
+
+int nlc::softmax_partial_impl(const float* cost_dev, const float* noise_dev, int K, int T, int nu, float lambda_, float* triple_dev,
+                              float* weights_dev, void* workspace_dev, bool with_init, const ExchangePub& pub, cudaStream_t s) {
   NLC_REQUIRE(cost_dev && noise_dev && triple_dev && workspace_dev, NLC_ERR_ARG, "nlc_softmax_partial: null pointer");
   NLC_REQUIRE(K >= 1 && T >= 1 && nu >= 1, NLC_ERR_ARG, "nlc_softmax_partial: K, T, nu must be positive");
   const int TN = T * nu;
   NLC_REQUIRE(TN <= 256, NLC_ERR_SHAPE, "nlc_softmax_partial: T*nu = %d exceeds 256", TN);
   NLC_REQUIRE(lambda_ > 0.0f, NLC_ERR_ARG, "lambda must be positive");
   NLC_REQUIRE((reinterpret_cast<uintptr_t>(cost_dev) & 15) == 0, NLC_ERR_ARG, "cost_dev must be 16-byte aligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   SoftWs* ws = static_cast<SoftWs*>(workspace_dev);
   float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace_dev) + 256);
-  softmax_init_kernel<<<1, 1, 0, s>>>(ws);
-  NLC_LAUNCH_OK("softmax_init_kernel");
+  if (with_init) {
+    softmax_init_kernel<<<1, 1, 0, s>>>(ws);
+    NLC_LAUNCH_OK("softmax_init_kernel");
+  }
   int gmin = (K / 4 + 255) / 256;
   if (gmin > 148 * 2) gmin = 148 * 2;
   if (gmin < 1) gmin = 1;
@@ -264,7 +290,7 @@ extern "C" int nlc_softmax_partial(const float* cost_dev, const float* noise_dev
   const int grid = sum_grid(K);
   const int rows_per_block = (K + grid - 1) / grid;
   softmax_sum_kernel<<<grid, 256, 0, s>>>(cost_dev, noise_dev, K, TN, 1.0f / lambda_, ws, partials, triple_dev, weights_dev,
-                                          rows_per_block);
+                                          rows_per_block, pub);
   NLC_LAUNCH_OK("softmax_sum_kernel");
   return NLC_OK;
 }
@@ -274,7 +300,8 @@ extern "C" int nlc_softmax_combine(const float* triples_dev, int G, int T, int n
   NLC_REQUIRE(triples_dev && U_dev, NLC_ERR_ARG, "nlc_softmax_combine: null pointer");
   NLC_REQUIRE(G >= 1 && T >= 1 && nu >= 1 && lambda_ > 0.0f, NLC_ERR_ARG, "nlc_softmax_combine: bad sizes");
   softmax_combine_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(triples_dev, G, T * nu, nu, 1.0f / lambda_,
-                                                                           u_scale, U_dev, action_dev, stats_dev);
+                                                                           u_scale, U_dev, action_dev, stats_dev,
+                                                                           StepTail{nullptr, nullptr, nullptr, nullptr, 0});
   NLC_LAUNCH_OK("softmax_combine_kernel");
   return NLC_OK;
 }

@@ -412,7 +412,8 @@ class MPPIDelay:
         stream = _lib.current_stream_ptr()
         per_sample = state.dim() == 2 and state.shape[0] != 1
         with torch.cuda.device(self.d):
-            if not per_sample and noise is None and self.G == 1 and not state.is_cuda and not action_buffer.is_cuda:
+            if (not per_sample and noise is None and (self.G == 1 or (self._exchange and self.process_group is not None))
+                    and not state.is_cuda and not action_buffer.is_cuda):
                 # lowest-latency path: host buffers straight through the C ABI
                 sp, k1 = _lib.as_double_array(state.detach().reshape(-1).numpy())
                 bp, k2 = _lib.as_double_array(action_buffer.detach().reshape(-1).numpy())
@@ -443,6 +444,34 @@ class MPPIDelay:
             _lib.check(self._lib.nlc_planner_rollout(h, st.data_ptr(), int(per_sample), ab.data_ptr(), _lib.ptr(noise), stream),
                        "nlc_planner_rollout")
         return None
+
+    # ---- device-resident inputs: the control loop of a caller that keeps the state on the GPU ---------------------------------
+    def set_inputs(self, state, action_buffer):
+        """Copy ``state`` (nx) and ``action_buffer`` (B x nu, env units) into the planner's own device buffers; :meth:`step`
+        then plans on them.  (The batched closed loop and the benchmarks keep both on the device between control steps.)"""
+        action_buffer = torch.as_tensor(action_buffer)
+        if self.encode_obs_time:
+            action_buffer = action_buffer[:, :self.nu]
+        B = action_buffer.shape[0]
+        self._ensure(B)
+        self._push_U()
+        state = torch.as_tensor(np.asarray(state)) if not torch.is_tensor(state) else state
+        self.state = state.to(dtype=self.dtype)
+        self._buf(_lib.BUF_STATE, (self.K_local, self.nx))[0].copy_(state.reshape(-1).to(device=self.d, dtype=torch.float32))
+        self._buf(_lib.BUF_ACTION_BUFFER, (B, self.nu)).copy_(action_buffer.reshape(B, self.nu).to(device=self.d, dtype=torch.float32))
+
+    def step(self):
+        """One control step on the inputs resident in the planner's buffers (``set_inputs``), on-device sampler: ONE CUDA-graph
+        launch (``nlc_planner_step``), nothing else on the host.  Returns the planner's own device-resident action (fp32
+        view, valid until the next step).  Single shard, or shards connected by the device-side exchange."""
+        if self._handle is None:
+            raise RuntimeError("call set_inputs first")
+        if self.G > 1 and not self._exchange:
+            raise RuntimeError("step() needs a single shard or device-connected shards")
+        with torch.cuda.device(self.d):
+            _lib.check(self._lib.nlc_planner_step(self._handle, _lib.current_stream_ptr()), "nlc_planner_step")
+        self._calls += 1
+        return self._buf(_lib.BUF_ACTION, (self.nu,))
 
     def _finish(self):
         """Log-sum-exp combine of ``all_triples`` (G > 1) or of the own triple, ``U`` update, action."""
