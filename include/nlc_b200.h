@@ -136,7 +136,8 @@ typedef struct {
   int64_t k_total;      /* global K (for sample_null_action and the RNG counter)                     */
   float lambda_;
   float u_scale;
-  int32_t has_bounds;   float u_min, u_max;      /* scalar bounds (mppi_with_model.py:227-228)       */
+  int32_t has_bounds;                            /* bounds per action dimension (mppi_delay.py:143-150,347-356; the   */
+  float u_min[4], u_max[4];                      /* reference's callers pass scalars, mppi_with_model.py:227-228)     */
   int32_t sample_null_action;                    /* mppi_delay.py:322-323                            */
   int32_t noise_abs_cost;                        /* mppi_delay.py:329-333                            */
   float sigma_inv[16];  /* [nu][nu] row-major                                                        */

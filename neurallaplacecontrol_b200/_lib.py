@@ -45,7 +45,7 @@ class MppiParams(C.Structure):
         ("K", C.c_int32), ("T", C.c_int32), ("nu", C.c_int32), ("B", C.c_int32),
         ("k_offset", C.c_int64), ("k_total", C.c_int64),
         ("lambda_", C.c_float), ("u_scale", C.c_float),
-        ("has_bounds", C.c_int32), ("u_min", C.c_float), ("u_max", C.c_float),
+        ("has_bounds", C.c_int32), ("u_min", C.c_float * 4), ("u_max", C.c_float * 4),
         ("sample_null_action", C.c_int32), ("noise_abs_cost", C.c_int32),
         ("sigma_inv", C.c_float * 16), ("sigma_chol", C.c_float * 16), ("noise_mu", C.c_float * 4),
         ("u_init", C.c_float * 4),

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) perturb_kernel(PerturbArgs a) {
         float pa = __fadd_rn(Ut[u], nz[u]);                                   // :321
         if (a.p.sample_null_action && gk == a.p.k_total - 1) pa = 0.0f;      // :322-323
         float x = __fmul_rn(pa, u_scale);                                     // :325
-        if (a.p.has_bounds) x = fmaxf(fminf(x, a.p.u_max), a.p.u_min);        // :347-353
+        if (a.p.has_bounds) x = fmaxf(fminf(x, a.p.u_max[u]), a.p.u_min[u]);  // :347-353
         pert[u] = __fdiv_rn(x, u_scale);                                      // :326
         nb[u] = __fsub_rn(pert[u], Ut[u]);                                    // :328
         a.perturbed[e + u] = pert[u];

@@ -10,7 +10,7 @@ Differences a caller can see, all deliberate:
   ``cost_total_non_zero``, ``omega``, ``states``, ``actions``, ``U``) are fp32 CUDA tensors (zero-copy views of the
   planner's buffers); the returned action is cast to ``noise_sigma.dtype`` like the reference's.
 * Options the reference's callers never use and this path does not implement raise ``NotImplementedError``
-  instead of being silently ignored: ``terminal_state_cost``, ``step_dependent_dynamics``, ``rollout_samples > 1``
+  instead of being silently ignored: ``terminal_state_cost`` (an opaque callable), ``step_dependent_dynamics``, ``rollout_samples > 1``
   (legacy variance branch, ``:291-292,310``), planner-level ``encode_obs_time`` with a Neural Laplace model (a model built
   with ``encode_obs_time=True`` is supported: the closure-level time channel of ``mppi_with_model.py:110-119`` is
   synthesised inside the encoder kernels).
@@ -42,14 +42,18 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
-def _scalar_bound(x, name):
+def _bound_vector(x, nu, name):
+    """Bound per action dimension: a scalar (what the reference's callers pass, mppi_with_model.py:227-228) or ``nu`` values.
+    With a ``(nu,)`` tensor the reference's ``_bound_action`` (``mppi_delay.py:347-356``: slices of the T axis, ``torch.min``
+    broadcasting over the last axis) clamps every ``(k, t, u)`` entry to ``[u_min[u], u_max[u]]``."""
     if x is None:
         return None
     t = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
-    if not bool((t == t[0]).all()):
-        raise NotImplementedError(f"{name}: per-dimension bounds are not used by the reference's callers "
-                                  "(mppi_with_model.py:227-228) and are not implemented")
-    return float(t[0])
+    if t.numel() == 1:
+        t = t.repeat(nu)
+    if t.numel() != nu:
+        raise ValueError(f"{name} must be a scalar or have one entry per action dimension ({nu})")
+    return t
 
 
 class MPPIDelay:
@@ -75,8 +79,8 @@ class MPPIDelay:
             # only uses that with the analytic dynamics (mppi_dataset_collector.py:166-180), which ignore the channel.
             # A Neural Laplace model with encode_obs_time gets its channel from the closure instead (NLDynamics).
             raise NotImplementedError("planner-level encode_obs_time is implemented for AnalyticDelayDynamics only")
-        if u_per_command != 1:
-            raise NotImplementedError("u_per_command != 1 is not implemented")
+        if not 1 <= int(u_per_command) <= int(horizon):
+            raise ValueError("u_per_command must lie in [1, horizon]")
         dev = torch.device(device)
         if dev.type != "cuda":
             if not torch.cuda.is_available():
@@ -104,13 +108,15 @@ class MPPIDelay:
         self.u_scale = u_scale
         self.u_per_command = u_per_command
         # mppi_delay.py:143-150: if one bound is given the other is its negative
-        lo, hi = _scalar_bound(u_min, "u_min"), _scalar_bound(u_max, "u_max")
+        lo, hi = _bound_vector(u_min, self.nu, "u_min"), _bound_vector(u_max, self.nu, "u_max")
         if hi is not None and lo is None:
             lo = -hi
         if lo is not None and hi is None:
             hi = -lo
-        self.u_min = None if lo is None else torch.tensor(lo, device=self.d)
-        self.u_max = None if hi is None else torch.tensor(hi, device=self.d)
+        scalar = lo is not None and bool((lo == lo[0]).all()) and bool((hi == hi[0]).all())
+        self.u_min = None if lo is None else (lo[0] if scalar else lo).to(device=self.d, dtype=torch.float32)
+        self.u_max = None if hi is None else (hi[0] if scalar else hi).to(device=self.d, dtype=torch.float32)
+        self._bounds = None if lo is None else (lo.tolist(), hi.tolist())
         self.noise_mu = noise_mu
         self.noise_sigma = noise_sigma
         self.noise_sigma_inv = torch.inverse(noise_sigma)
@@ -178,8 +184,9 @@ class MPPIDelay:
         mp.k_offset, mp.k_total = k_offset, k_total
         mp.lambda_, mp.u_scale = float(self.lambda_), float(self.u_scale)
         mp.has_bounds = int(self.u_max is not None)
-        if self.u_max is not None:
-            mp.u_min, mp.u_max = float(self.u_min), float(self.u_max)
+        if self._bounds is not None:
+            for i in range(self.nu):
+                mp.u_min[i], mp.u_max[i] = self._bounds[0][i], self._bounds[1][i]
         mp.sample_null_action, mp.noise_abs_cost = int(self.sample_null_action), int(self.noise_abs_cost)
         sinv = self.noise_sigma_inv.to(torch.float64).reshape(self.nu, self.nu)
         chol = torch.linalg.cholesky(self.noise_sigma.to(torch.float64).reshape(self.nu, self.nu))
@@ -386,13 +393,21 @@ class MPPIDelay:
         :returns action: (nu) best action (``mppi_delay.py:193-224``)."""
         action = self._begin(state, action_buffer)
         if action is not None:  # single shard, host or planner-owned inputs: the whole step was one graph launch
-            return action
+            return self._first_actions(action)
         if self.G > 1 and not self._exchange:
             if self.process_group is None:
                 raise RuntimeError("a planner built with shard=(rank, G) has no process group to exchange the triples: "
                                    "drive it through _begin / all_triples / _finish")
             sharding.gather_triples(self.shard_triple, self.all_triples, group=self.process_group)
-        return self._finish()
+        return self._first_actions(self._finish())
+
+    def _first_actions(self, action):
+        """``U[:u_per_command] * u_scale`` (``mppi_delay.py:217-224``): the head action for ``u_per_command == 1``, else the first
+        ``u_per_command`` planned actions as a ``(u_per_command, nu)`` tensor."""
+        if self.u_per_command == 1:
+            return action
+        n = int(self.u_per_command)
+        return (self._buf(_lib.BUF_U, (self.T, self.nu))[:n] * float(self.u_scale)).to(self.dtype)
 
     # The control step of a shard in its two halves; the exchange of the triples sits between them (the parity tests
     # drive the G shards of one plan through these on a single GPU).

@@ -564,3 +564,31 @@ def test_device_side_exchange_equals_host_gather():
         res[mode] = outs
     for (Ua, aa), (Ub, ab) in zip(res["mailbox"], res["gather"]):
         assert torch.equal(Ua, Ub) and torch.equal(aa, ab)
+
+
+def test_per_dimension_bounds_and_u_per_command():
+    """Options the reference implements but its callers leave at their defaults: bounds given per action dimension
+    (``mppi_delay.py:143-150,347-356``) and ``u_per_command > 1`` (``:217-224``), against the oracle."""
+    from oracle import costs, mppi
+    from _util import START_STATE, injected_noise
+
+    nlc = _nlc()
+    env = "oderl-acrobot"
+    nx, nu = costs.ENV_DIMS[env]
+    K, T = 96, 6
+    m = make_model(env, calibrated=True)
+    lo, hi = torch.tensor([-1.0, -0.25]), torch.tensor([0.5, 2.0])
+    noise = injected_noise(K, T, nu, seed=12)
+    U0 = torch.zeros(T, nu, dtype=torch.float64)
+    p = nlc.MPPIDelay(nlc.NLDynamics(m, DT), nlc.EnvRunningCost(env), nx, nlc.noise_sigma_for(nu), num_samples=K, horizon=T,
+                      device="cuda:0", u_min=lo, u_max=hi, u_scale=2.0, U_init=U0, u_per_command=3, math_mode="fp32")
+    p.noise_dist.sample = lambda shape: noise
+    buf = torch.zeros(4, nu, dtype=torch.float64)
+    actions = p.command(np.array(START_STATE[env]), buf)
+    ref = mppi.command(U0.clone(), torch.tensor(START_STATE[env]), buf, noise, mppi.make_nl_dynamics(weights(env, calibrated=True), DT),
+                       costs.running_cost(env), noise_sigma=mppi.noise_sigma_for(nu), u_scale=2.0, u_min=lo.double(), u_max=hi.double())
+    assert actions.shape == (3, nu)
+    assert relerr(ref["perturbed_action"], p.perturbed_action) < 1e-6
+    assert float(p.perturbed_action[..., 0].max()) * 2.0 <= 0.5 + 1e-6 and float(p.perturbed_action[..., 1].min()) * 2.0 >= -0.25 - 1e-6
+    assert relerr(ref["cost_total"], p.cost_total) < TOL
+    assert relerr(ref["U"][:3] * 2.0, actions) < TOL

@@ -25,7 +25,9 @@ def _params(K, T, nu, B=4, k_offset=0, k_total=None, u_scale=2.0, bound=2.0, lam
     p = L.MppiParams()
     p.K, p.T, p.nu, p.B = K, T, nu, B
     p.k_offset, p.k_total = k_offset, K if k_total is None else k_total
-    p.lambda_, p.u_scale, p.has_bounds, p.u_min, p.u_max = lam, u_scale, 1, -bound, bound
+    p.lambda_, p.u_scale, p.has_bounds = lam, u_scale, 1
+    for i in range(nu):
+        p.u_min[i], p.u_max[i] = -bound, bound
     sig = mppi.noise_sigma_for(nu)
     sinv, chol = torch.inverse(sig), torch.linalg.cholesky(sig)
     for i in range(nu):
