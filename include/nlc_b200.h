@@ -114,9 +114,10 @@ int nlc_model_forward(nlc_model_t m, const float* obs_dev, const float* act_dev,
                       float* out_dev, float* p_action_dev, int math_mode, void* stream);
 
 /* Same with a per-sample prediction time ts_dev [K] (seconds), the irregular-time form used by
- * training/validation (train_utils.py:401-404): s-points are computed per sample in the kernel.   */
+ * training/validation (train_utils.py:401-404): s-points are computed per sample in the kernel.
+ * math_mode as in nlc_model_forward (the single-pass fp16 mode takes the fp32-class tensor-core form here). */
 int nlc_model_forward_ts(nlc_model_t m, const float* obs_dev, const float* act_dev, const float* ts_dev,
-                         int K, int B, float* out_dev, float* scratch_dev /* [K][132] floats */, void* stream);
+                         int K, int B, float* out_dev, float* scratch_dev /* [K][132] floats */, int math_mode, void* stream);
 
 /* ReverseGRUEncoder.forward (w_nl.py:25-29) over every window of a K x L action history:
  * hist_dev [K][L][gru_in] env units, windows [t, t+B) for t in [0, T), L = B-1+T.

@@ -72,7 +72,7 @@ SIGNATURES = {
     "nlc_model_destroy": (C.c_int, [C.c_void_p]),
     "nlc_model_set_prediction_time": (C.c_int, [C.c_void_p, C.c_double]),
     "nlc_model_forward": (C.c_int, [C.c_void_p, _fp, _fp, C.c_int, C.c_int, _fp, _fp, C.c_int, C.c_void_p]),
-    "nlc_model_forward_ts": (C.c_int, [C.c_void_p, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, C.c_void_p]),
+    "nlc_model_forward_ts": (C.c_int, [C.c_void_p, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, C.c_int, C.c_void_p]),
     "nlc_encode_history": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_void_p]),
     "nlc_perturb": (C.c_int, [C.POINTER(MppiParams), _fp, _fp, C.c_int, _fp, C.c_uint64, C.c_uint64, _fp, _fp, _fp,
                               _fp, _fp, _fp, C.c_void_p]),

@@ -269,7 +269,8 @@ int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K
 int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                        const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
                        float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream, const unsigned int* ready = nullptr,
-                       unsigned int ready_target = 0, unsigned int* status = nullptr);
+                       unsigned int ready_target = 0, unsigned int* status = nullptr, const float* row_b1 = nullptr,
+                       const float* row_tn = nullptr);
 bool rollout_has_tensor_core_form(const nlc_model_s* m);
 
 // planner.cu: can the rollout of this plan run BESIDE its history encoder (one-tile tcgen05 form on ceil(K/128) SMs, polling the
@@ -391,20 +392,34 @@ __global__ void __launch_bounds__(128) forward_ts_prep_kernel(ModelDev m, int S,
 }  // namespace nlc
 
 extern "C" int nlc_model_forward_ts(nlc_model_t m, const float* obs_dev, const float* act_dev, const float* ts_dev, int K,
-                                    int B, float* out_dev, float* scratch_dev, void* stream) {
+                                    int B, float* out_dev, float* scratch_dev, int math_mode, void* stream) {
   NLC_REQUIRE(m && obs_dev && act_dev && ts_dev && out_dev && scratch_dev, NLC_ERR_ARG, "nlc_model_forward_ts: null pointer");
   NLC_REQUIRE(K >= 1, NLC_ERR_ARG, "nlc_model_forward_ts: K must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* p_action = scratch_dev;                 // [K][2]
   float* row_tn = scratch_dev + 2 * (size_t)K;   // [K]
   float* row_b1 = scratch_dev + 4 * (size_t)K;   // [K][128]   (offset keeps 16-byte alignment)
-  int rc = encode_history_impl(m, act_dev, m->gin, K, 1, B, p_action, NLC_MATH_FP32, s);
+  NLC_REQUIRE(math_mode == NLC_MATH_FP32 || math_mode == NLC_MATH_TC_SPLIT3 || math_mode == NLC_MATH_TC_FP16, NLC_ERR_ARG,
+              "unknown math_mode %d", math_mode);
+  // the single-pass fp16 mode has no per-sample-time rollout instantiation: it takes the fp32-class tensor-core form
+  const int mm = math_mode == NLC_MATH_TC_FP16 ? NLC_MATH_TC_SPLIT3 : math_mode;
+  int rc = encode_history_impl(m, act_dev, m->gin, K, 1, B, p_action, mm, s);
   if (rc != NLC_OK) return rc;
   forward_ts_prep_kernel<<<K, 128, 0, s>>>(m->d, m->S, m->nx + 2, m->normalize && m->normalize_time, (float)m->dt, ts_dev, K, row_b1, row_tn);
   NLC_LAUNCH_OK("forward_ts_prep_kernel");
   nlc_rollout_opts o;
   o.env = m->nx == 3 ? NLC_ENV_PENDULUM : (m->nx == 5 ? NLC_ENV_CARTPOLE : NLC_ENV_ACROBOT);
   o.state_constraint = 0; o.goal_x = 0.0f; o.dynamics = NLC_DYN_NEURAL_LAPLACE; o.delay = 0; o.dt = (float)m->dt;
+  if (mm == NLC_MATH_TC_SPLIT3 && rollout_has_tensor_core_form(m)) {
+    // representation MLP on the tensor cores: per-sample first-layer bias added in the first epilogue, per-sample Fourier phases
+    // and weights in the last (rollout_tc2.cu, kPerRow)
+    rc = launch_rollout_tc2(m, &o, obs_dev, 1, p_action, act_dev, nullptr, K, 1, B, m->gin, nullptr, nullptr, out_dev, 1, 1, s, nullptr,
+                            0, nullptr, row_b1, row_tn);
+    if (rc != NLC_ERR_UNSUPPORTED) return rc;
+  }
+  if (mm != NLC_MATH_FP32 && K >= 4096)
+    warn_once(kWarnForwardTsFfma, "nlc_model_forward_ts: nx = %d, S = %d has no tcgen05 instantiation; %d samples run on the fp32 kernel",
+              m->nx, m->S, K);
   return launch_rollout_fp32(m, &o, obs_dev, 1, p_action, act_dev, nullptr, K, 1, B, m->gin, nullptr, nullptr, out_dev, s, row_b1,
                              row_tn);
 }

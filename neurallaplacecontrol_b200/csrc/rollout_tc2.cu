@@ -78,6 +78,10 @@ struct Args {
   const unsigned int* ready;
   unsigned int ready_target;
   unsigned int* status;
+  // per-sample prediction times (nlc_model_forward_ts, one-tile form with kPerRow): row_b1 [K][128] = first-layer bias with
+  // that sample's s-points folded in (natural units), row_tn [K] = its normalised time
+  const float* row_b1;
+  const float* row_tn;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -282,9 +286,11 @@ __device__ __forceinline__ void l3_two_pairs(f2_t th, f2_t ph, float phase0, flo
 
 // L3 epilogue of one 16-column chunk (8 pairs); kChunk = chunk index in the full N3t column space, kCol0 = first chunk
 // of the half that currently sits in the D region
-template <int NX, int S, int kChunk, int kCol0, bool kAccurate, int kRcp>
+// kPerRow: the sample has its own prediction time - phase_k = k pi t/T = k (pi/2 - rd) reduced to (-pi, pi] with the quarter turns
+// exact, weight_k = rs (k == 0 ? 1/2 : 1), rd = pi eps / T and rs = exp(gamma t) / T of that sample (oracle/ilt.py)
+template <int NX, int S, int kChunk, int kCol0, bool kAccurate, int kRcp, bool kPerRow = false>
 __device__ __forceinline__ void l3_chunk(uint32_t tD, const float* __restrict__ b3, const float* __restrict__ phase,
-                                         const float* __restrict__ weight, float (&delta)[NX]) {
+                                         const float* __restrict__ weight, float (&delta)[NX], float rd = 0.0f, float rs = 0.0f) {
   f2_t v[8];
   ldtm16p(tD + 16 * (kChunk - kCol0), v);
   tmem_ld_wait();
@@ -308,19 +314,27 @@ __device__ __forceinline__ void l3_chunk(uint32_t tD, const float* __restrict__ 
       const int ch0 = p0 / S, k0 = p0 - ch0 * S;
       const int ch1 = (p1 < NX * S) ? p1 / S : ch0, k1 = (p1 < NX * S) ? p1 - ch1 * S : k0;
       float t0, t1;
-      l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phase[k0], phase[k1], weight[k0], weight[k1], t0, t1);
+      if (kPerRow) {
+        const float q0 = (k0 & 3) == 0 ? 0.0f : ((k0 & 3) == 1 ? 1.57079632679489662f : ((k0 & 3) == 2 ? 3.14159265358979f : -1.57079632679489662f));
+        const float q1 = (k1 & 3) == 0 ? 0.0f : ((k1 & 3) == 1 ? 1.57079632679489662f : ((k1 & 3) == 2 ? 3.14159265358979f : -1.57079632679489662f));
+        l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), fmaf(-(float)k0, rd, q0), fmaf(-(float)k1, rd, q1),
+                                      k0 == 0 ? 0.5f * rs : rs, k1 == 0 ? 0.5f * rs : rs, t0, t1);
+      } else {
+        l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phase[k0], phase[k1], weight[k0], weight[k1], t0, t1);
+      }
       delta[ch0] += t0;
       if (p1 < NX * S) delta[ch1] += t1;
     }
   }
 }
 // chunks kChunk, kChunk + kStride, ... < kEnd (the column groups of a sample take chunks round-robin)
-template <int NX, int S, int kChunk, int kEnd, int kCol0, bool kAccurate, int kRcp, int kStride>
+template <int NX, int S, int kChunk, int kEnd, int kCol0, bool kAccurate, int kRcp, int kStride, bool kPerRow = false>
 struct L3Loop {
-  static __device__ __forceinline__ void run(uint32_t tD, const float* b3, const float* phase, const float* weight, float (&delta)[NX]) {
+  static __device__ __forceinline__ void run(uint32_t tD, const float* b3, const float* phase, const float* weight, float (&delta)[NX],
+                                             float rd = 0.0f, float rs = 0.0f) {
     if constexpr (kChunk < kEnd) {
-      l3_chunk<NX, S, kChunk, kCol0, kAccurate, kRcp>(tD, b3, phase, weight, delta);
-      L3Loop<NX, S, kChunk + kStride, kEnd, kCol0, kAccurate, kRcp, kStride>::run(tD, b3, phase, weight, delta);
+      l3_chunk<NX, S, kChunk, kCol0, kAccurate, kRcp, kPerRow>(tD, b3, phase, weight, delta, rd, rs);
+      L3Loop<NX, S, kChunk + kStride, kEnd, kCol0, kAccurate, kRcp, kStride, kPerRow>::run(tD, b3, phase, weight, delta, rd, rs);
     }
   }
 };
@@ -394,8 +408,9 @@ struct L3Units {
   }
 };
 
-template <int NX, int S, bool kSplit3, int kRcp, int kTiles>
+template <int NX, int S, bool kSplit3, int kRcp, int kTiles, bool kPerRow = false>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
+  static_assert(!kPerRow || kTiles == 1, "per-sample prediction times: one-tile form");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int Lp = NX + 2;
   constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
@@ -513,6 +528,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         in[NX] = pv.x; in[NX + 1] = pv.y;
       }
       float cost_acc = 0.0f;
+      float rd = 0.0f, rs = 0.0f;  // kPerRow: this sample's pi eps / T and exp(gamma t) / T (torchlaplace Fourier constants)
+      if (kPerRow) {
+        const float tn = a.row_tn[kk];
+        const float Tt = 2.0f * (tn + 1.0e-6f);
+        rd = 3.14159265358979f * 1.0e-6f / Tt;
+        rs = expf((1.0e-3f + 4.605170185988091f / Tt) * tn) / Tt;
+      }
 
       for (int t = 0; t < a.T; ++t) {
         float2 pnext = make_float2(0.f, 0.f);
@@ -523,8 +545,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
           f2_t v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float x0 = (2 * i < Lp) ? in[2 * i < Lp ? 2 * i : 0] : (2 * i == Lp ? 1.0f : 0.0f);
-            const float x1 = (2 * i + 1 < Lp) ? in[2 * i + 1 < Lp ? 2 * i + 1 : 0] : (2 * i + 1 == Lp ? 1.0f : 0.0f);
+            // the constant-1 column multiplies the folded first-layer bias; with per-sample times the bias comes in E1 instead
+            const float one = kPerRow ? 0.0f : 1.0f;
+            const float x0 = (2 * i < Lp) ? in[2 * i < Lp ? 2 * i : 0] : (2 * i == Lp ? one : 0.0f);
+            const float x1 = (2 * i + 1 < Lp) ? in[2 * i + 1 < Lp ? 2 * i + 1 : 0] : (2 * i + 1 == Lp ? one : 0.0f);
             v[i] = pk2(x0, x1);
           }
           uint32_t ph[8], pl[8];
@@ -544,6 +568,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
             f2_t v[8];
             ldtm16p(tD + n0, v);
             tmem_ld_wait();
+            if (kPerRow) {  // + (-2 log2 e) x this sample's first-layer bias (the accumulator carries the folded scale)
+              const float4* bp = reinterpret_cast<const float4*>(a.row_b1 + (size_t)kk * kH + n0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 b = __ldg(bp + i);
+                const f2_t c = pk2(-2.8853900817779268f, -2.8853900817779268f);
+                v[2 * i] = fma2(pk2(b.x, b.y), c, v[2 * i]);
+                v[2 * i + 1] = fma2(pk2(b.z, b.w), c, v[2 * i + 1]);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = tanh2_scaled<kSplit3, kRcp / 10>(v[i]);
             uint32_t ph[8], pl[8];
@@ -595,10 +629,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         // the first half's product has read the W3 buffer: the second half streams in under this epilogue
         if (kStream && wl == 0 && elect_one()) load_w3_rows(a.m, w3_img, N3a, N3b, N3t, N3buf, &s.bar_w3);
         if (active) {
-          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
-          else if (cg == 1) L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
-          else if (kCG == 4 && cg == 2) L3Loop<NX, S, 2, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
-          else if (kCG == 4) L3Loop<NX, S, 3, kChunksA, 0, kSplit3, kRcp % 10, kCG>::run(tD, s.b3, s.phase, s.weight, delta);
+          if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+          else if (cg == 1) L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+          else if (kCG == 4 && cg == 2) L3Loop<NX, S, 2, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+          else if (kCG == 4) L3Loop<NX, S, 3, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
         }
         if (N3b > 0) {
           mark(6);
@@ -609,10 +643,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
           if (kStream && wl == 0 && elect_one()) load_w3_rows(a.m, w3_img, 0, N3a, N3t, N3buf, &s.bar_w3);
           if (active) {
             if constexpr (kCG == 4) {  // four column groups take the second half's chunks round-robin
-              if (cg == 0) L3Loop<NX, S, kChunksA, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
-              else if (cg == 1) L3Loop<NX, S, kChunksA + 1, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
-              else if (cg == 2) L3Loop<NX, S, kChunksA + 2, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
-              else L3Loop<NX, S, kChunksA + 3, kChunks, kChunksA, kSplit3, kRcp % 10, 4>::run(tD, s.b3, s.phase, s.weight, delta);
+              if (cg == 0) L3Loop<NX, S, kChunksA, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+              else if (cg == 1) L3Loop<NX, S, kChunksA + 1, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+              else if (cg == 2) L3Loop<NX, S, kChunksA + 2, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+              else L3Loop<NX, S, kChunksA + 3, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
             } else {
               constexpr int kFirstB0 = kChunksA + (kChunksA & 1);        // first chunk >= kChunksA with even index
               constexpr int kFirstB1 = kChunksA + 1 - (kChunksA & 1);    // ... with odd index
@@ -1047,13 +1081,13 @@ static int launch_pp(const Args& a, cudaStream_t stream) {
   return NLC_OK;
 }
 
-template <int NX, int S, bool kSplit3, int kRcp, int kTiles>
+template <int NX, int S, bool kSplit3, int kRcp, int kTiles, bool kPerRow = false>
 static int launch_one_t(const Args& a, cudaStream_t stream) {
   constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
   constexpr int N3buf = (kTiles == 1 && N3t > 256) ? 16 * ((N3t / 16 + 1) / 2) : N3t;  // streamed W3: one half resident
   const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3buf * kH * 2 + sizeof(SmemTail) + 128;
   NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
-  auto kern = rollout_tc2_kernel<NX, S, kSplit3, kRcp, kTiles>;
+  auto kern = rollout_tc2_kernel<NX, S, kSplit3, kRcp, kTiles, kPerRow>;
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // one tile slot per 32..128 samples: enough CTAs to give every slot at least one warp of samples, at most one per SM
   int grid = (a.K + 32 * kTiles - 1) / (32 * kTiles);
@@ -1068,6 +1102,10 @@ static int launch_one_t(const Args& a, cudaStream_t stream) {
 // two tiles per CTA once the plan is more than one wave of 128-sample tiles, else one tile on all 16 warps
 template <int NX, int S, bool kSplit3, int kRcp>
 static int launch_one(const Args& a, int tiles, cudaStream_t stream) {
+  if (a.row_b1) {  // per-sample prediction times: the one-tile form's kPerRow instantiation (fp32-class arithmetic only)
+    if constexpr (kSplit3) return launch_one_t<NX, S, true, kRcp, 1, true>(a, stream);
+    else return NLC_ERR_UNSUPPORTED;
+  }
   if constexpr (2 * NX * S > 256) {
     // more (theta, phi) columns than two tiles' accumulators hold: the one-tile form with W3 streamed, whatever the plan size
     return launch_one_t<NX, S, kSplit3, kRcp, 1>(a, stream);
@@ -1090,9 +1128,11 @@ void set_rollout_trace(long long* p) { g_roll_trace = p; }
 int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p,
                        const float* hist, const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states,
                        float* delta_out, int split3, int tiles_per_cta, cudaStream_t stream, const unsigned int* ready,
-                       unsigned int ready_target, unsigned int* status) {
+                       unsigned int ready_target, unsigned int* status, const float* row_b1, const float* row_tn) {
   rt2::Args a;
   a.ready = ready; a.ready_target = ready_target; a.status = status;
+  a.row_b1 = row_b1; a.row_tn = row_tn;
+  NLC_REQUIRE(!row_b1 || (row_tn && split3 && !ready), NLC_ERR_ARG, "rollout: per-sample times need row_tn and the fp32-class tensor-core mode");
   if (2 * m->nx * m->S > 256) tiles_per_cta = 1;
   NLC_REQUIRE(!ready || (tiles_per_cta == 1 && (K + 127) / 128 <= 148 && status), NLC_ERR_ARG,
               "rollout: the overlapped form is the one-tile form of plans within one wave");

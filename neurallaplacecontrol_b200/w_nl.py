@@ -174,6 +174,7 @@ class NeuralLaplaceModel(nn.Module):
                 ts32 = ts.to(torch.float32).contiguous()
                 scratch = torch.empty((K, 132), dtype=torch.float32, device=dev)
                 _lib.check(lib.nlc_model_forward_ts(h, obs.data_ptr(), act.data_ptr(), ts32.data_ptr(), K, B, out.data_ptr(),
-                                                    scratch.data_ptr(), _lib.current_stream_ptr()), "nlc_model_forward_ts")
+                                                    scratch.data_ptr(), _lib.MATH_MODES[self.math_mode], _lib.current_stream_ptr()),
+                           "nlc_model_forward_ts")
                 self.last_p_action = scratch.view(-1)[:2 * K].view(K, 2)
         return torch.squeeze(out.to(out_dtype))
