@@ -305,8 +305,9 @@ def time_plan(ctx, env, K, H, group, steps, warmup):
 
     def e2e_step():
         a = planner.command(inp["state"], inp["buffer"])  # host buffers in
-        # one shard: the C entry point already synchronised and left the action on the host; sharded: read it back here
-        return planner.last_action_host if planner.G == 1 else a.cpu()
+        # one shard / device-connected shards: the C entry point already synchronised and left the action on the host;
+        # shards exchanging through NCCL: read it back here
+        return planner.last_action_host if planner.last_action_host is not None else a.cpu()
 
     _, ms_e2e, _ = ctx.timed(e2e_step, steps, warmup)
     return {"ms_dev": ms_dev, "ms_e2e": ms_e2e, "launches": launches, "inp": inp, "model": model, "planner": planner,

@@ -76,7 +76,25 @@ class NeuralLaplaceModel(nn.Module):
 
     # ---- device handle -------------------------------------------------------------------------------------------
     def _fingerprint(self):
-        return tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict(keep_vars=True).items())
+        """(version, address) of every parameter and buffer: changes on ``load_state_dict``, optimizer steps, ``.double()`` ...
+        The tensor list is cached (walking the module tree costs ~60 us, this runs once per control step) and dropped whenever
+        a tensor attribute is (re)assigned or ``_apply`` (``.to`` / ``.double`` / ``.cuda``) runs."""
+        ts = self.__dict__.get("_fp_tensors")
+        if ts is None:
+            ts = [v for _, v in self.state_dict(keep_vars=True).items()]
+            self.__dict__["_fp_tensors"] = ts
+        return tuple((v._version, v.data_ptr()) for v in ts)
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__["_fp_tensors"] = None
+        for m in self.modules():
+            m.__dict__["_fp_tensors"] = None
+        return super()._apply(fn, *a, **k)
+
+    def __setattr__(self, name, value):
+        if isinstance(value, (torch.Tensor, nn.Module)):
+            self.__dict__["_fp_tensors"] = None
+        super().__setattr__(name, value)
 
     def _device(self):
         if self._cuda_device is not None:
