@@ -385,7 +385,11 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        h0r[4 * c + i] = gru_pair<RZ, NN, true>(gr[i], gz[i], gn[i], gh[i], h0r[4 * c + i]);
+        // NN = 1 / 2: the n-gate reciprocal by Newton for one / two of the four pairs of a chunk, MUFU for the others.  The MUFU
+        // pipe (70 % busy) and the FMA pipe / issue slots are balanced at one in four: 2.18 ms at config 4 against 2.23 (none),
+        // 2.21 (two) and 2.29 ms (all four by Newton)
+        if ((NN == 1 && i == 0) || (NN == 2 && (i & 1) == 0)) h0r[4 * c + i] = gru_pair<RZ, 3, true>(gr[i], gz[i], gn[i], gh[i], h0r[4 * c + i]);
+        else h0r[4 * c + i] = gru_pair<RZ, (NN == 1 || NN == 2) ? 0 : NN, true>(gr[i], gz[i], gn[i], gh[i], h0r[4 * c + i]);
       }
       if (store) {
         if (c == 0 && wait_h0) { mbar_wait_sleep(&s.bar_h0, n_h0 & 1); ++n_h0; }
@@ -465,7 +469,8 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          h1r[4 * c + i] = gru_pair<RZ, NN, kClamp1>(gr[i], gz[i], gn[i], gh[i], h1r[4 * c + i]);
+          if ((NN == 1 && i == 0) || (NN == 2 && (i & 1) == 0)) h1r[4 * c + i] = gru_pair<RZ, 3, kClamp1>(gr[i], gz[i], gn[i], gh[i], h1r[4 * c + i]);
+          else h1r[4 * c + i] = gru_pair<RZ, (NN == 1 || NN == 2) ? 0 : NN, kClamp1>(gr[i], gz[i], gn[i], gh[i], h1r[4 * c + i]);
         }
         if (st + 1 < B) {  // MMA B(st), the last reader of the h1 image, has completed (bar_b above): store chunk by chunk
           const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h1r[4 * c]);
@@ -543,10 +548,10 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   a.m = m->d;
   a.trace = g_enc_trace;
   const int smem = (int)sizeof(Smem) + 128;
-  // fp32-class mode: Newton (3 steps) for the (r, z) reciprocal, MUFU for n  (pipe_bench "v3");
+  // fp32-class mode: Newton (3 steps) for the (r, z) reciprocal; for n, Newton for one pair in four and MUFU for the rest ("31");
   // single-pass fp16 mode: three tanh.approx per unit (that mode's accuracy class, 2e-2 bound).
-  // NLC_ENC_RCP=<rz><nn> (digits 0 or 3) overrides the fp32-class choice for measurements.
-  static const int rcp_sel = [] { const char* e = getenv("NLC_ENC_RCP"); return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 30; }();
+  // NLC_ENC_RCP=<rz><nn> (00, 30, 31, 32, 33) overrides the fp32-class choice for measurements.
+  static const int rcp_sel = [] { const char* e = getenv("NLC_ENC_RCP"); return (e && e[0] && e[1]) ? (e[0] - '0') * 10 + (e[1] - '0') : 31; }();
   void (*kern)(Args);
   // layer-1 (r, z) clamps are compiled out when the packed weights prove |pre-activation| * log2(e) < 60 (model.cu)
   const bool c1 = !m->enc_l1_bounded;
@@ -556,8 +561,10 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   if (!split3) kern = m->gin == 1 ? encode_tc2_kernel<false, 1, kGateTanhApprox, 0, true> : encode_tc2_kernel<false, 2, kGateTanhApprox, 0, true>;
   else if (rcp_sel == 0) kern = NLC_ENC_PICK(true, 0, 0, false);
   else if (rcp_sel == 33) kern = NLC_ENC_PICK(true, 3, 3, false);
-  else kern = NLC_ENC_PICK(true, 3, 0, false);
-  if (a.trace && split3) kern = NLC_ENC_PICK(true, 3, 0, true);
+  else if (rcp_sel == 30) kern = NLC_ENC_PICK(true, 3, 0, false);
+  else if (rcp_sel == 32) kern = NLC_ENC_PICK(true, 3, 2, false);
+  else kern = NLC_ENC_PICK(true, 3, 1, false);
+  if (a.trace && split3) kern = NLC_ENC_PICK(true, 3, 1, true);
 #undef NLC_ENC_PICK
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long n_tiles = ready ? (long long)a.tiles_per_t * T : (a.rows + kRows - 1) / kRows;
