@@ -1139,9 +1139,9 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
   a.trace = g_roll_trace;
-  // reciprocal flavour of the fp32-class epilogues: Newton on the FMA pipe for both the MLP tanh and the L3 pair ("33":
-  // 1.71 ms at config 4; MUFU.RCP "00": 1.85 ms - shorter chains, but the MUFU pipe is the scarcer one; measured with the
-  // two-group form, profiles/r1_rollout_sweep.md)
+  // reciprocal flavour of the fp32-class epilogues: Newton on the FMA pipe for both the MLP tanh and the L3 pair ("33").
+  // Ping-pong form at config 4: 1.412 ms; MUFU for the L3 pair ("30") 1.447, for the tanh ("03") 1.427, for both ("00") 1.466
+  // (round 2; round 1 measured 1.71 vs 1.85 ms with the two-group form, profiles/r1_rollout_sweep.md)
 #define NLC_RT2_CASE(NX_, S_)                                                                \
   if (m->nx == NX_ && m->S == S_) {                                                          \
     if (!split3) return rt2::launch_one<NX_, S_, false, 0>(a, tiles_per_cta, stream);        \
