@@ -36,6 +36,7 @@ struct nlc_planner_s {
   cudaStream_t side_stream;
   cudaEvent_t ev_fork, ev_join;
   unsigned int* ready;   // [T] finished encoder warps per rollout step, + 1 status word (1 = a poll timed out)
+  bool pending;          // nlc_planner_rollout ran and nlc_planner_finish has not yet: the phases must alternate
   // K sharded over the GPUs of one node: device-side exchange of the triples through peer-mapped mailboxes (stage4_update.cu)
   float* mailbox;               // own: [2][G][xstride] floats + [2][G] sequence words
   int xstride;
@@ -89,6 +90,7 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;
   p->call_ctr = nullptr; p->cap_stream = nullptr; p->graph_core = nullptr; p->graph_host = nullptr;
   p->graph_core_tried = p->graph_host_tried = false;
+  p->pending = false;
   p->overlap = false; p->side_stream = nullptr; p->ev_fork = p->ev_join = nullptr; p->ready = nullptr;
   p->mailbox = nullptr; p->xstride = 0; p->xchg = false; p->mailboxes_dev = nullptr; p->xstep = nullptr; p->xstatus = nullptr;
   memset(p->peer, 0, sizeof(p->peer)); memset(p->peer_ipc, 0, sizeof(p->peer_ipc));
@@ -321,6 +323,9 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
   NLC_CUDA_OK(cudaSetDevice(p->device));
   int rc = planner_check_model(p);
   if (rc != NLC_OK) return rc;
+  // nlc_planner_finish re-arms stage 4's workspace, the encoder readiness counters and the sampler for the next rollout
+  NLC_REQUIRE(!p->pending, NLC_ERR_ARG, "nlc_planner_rollout called twice without nlc_planner_finish in between");
+  p->pending = true;
   if (ev) NLC_CUDA_OK(cudaEventRecord(ev[0], s));
   rc = perturb_launch(&mp, p->U, p->U_rolled, 1, noise_in_dev, p->d.seed, 0, p->call_ctr, action_buffer_dev, p->perturbed,
                       p->noise, p->hist, p->actions, p->pert_cost, stream);
@@ -418,6 +423,8 @@ extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // the update is applied to the rolled sequence (mppi_delay.py:199-216); the same kernel bumps the sampler's call index and
   // re-arms stage 4's workspace and the encoder readiness counters for the next control step
+  NLC_REQUIRE(p->pending, NLC_ERR_ARG, "nlc_planner_finish without a preceding nlc_planner_rollout");
+  p->pending = false;
   const StepTail tl{p->U_rolled, p->call_ctr, p->softmax_ws, p->overlap ? p->ready : nullptr, mp.T};
   if (p->xchg)  // wait (on the device) for the G triples of this control step in the own mailbox, then combine
     return launch_combine_exchange(p->mailbox, p->d.n_shards, p->xstride, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats,
