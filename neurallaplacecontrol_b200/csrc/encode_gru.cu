@@ -19,8 +19,7 @@
 namespace nlc {
 
 constexpr int kEncRows = 64;
-constexpr int kHg = 64;
-constexpr int kG3 = 192;
+constexpr int kHg = 64;   // GRU width of the tensor-core encoder (hidden_units = 128); the fp32 kernel below is a template on it
 
 struct EncArgs {
   const float* hist;  // [K][L][gin] env units
@@ -31,31 +30,35 @@ struct EncArgs {
   ModelDev m;
 };
 
+template <int HG>
 struct EncSmem {
-  float w_hh0[kHg * kG3];
-  float w_ih1[kHg * kG3];
-  float w_hh1[kHg * kG3];
+  static constexpr int kG3 = 3 * HG;
+  float w_hh0[HG * kG3];
+  float w_ih1[HG * kG3];
+  float w_hh1[HG * kG3];
   float w_ih0[kG3 * kMaxNu];
   float b_ih0[kG3], b_hh0[kG3], b_ih1[kG3], b_hh1[kG3];
-  float w_out[2 * kHg];
-  alignas(16) float h0[2][kHg * kEncRows];
-  alignas(16) float h1[2][kHg * kEncRows];
+  float w_out[2 * HG];
+  alignas(16) float h0[2][HG * kEncRows];
+  alignas(16) float h1[2][HG * kEncRows];
   alignas(16) float act[kEncRows * 8 * kMaxNu];  // [row][B][gin], B <= 8
   float b_out[2];
   float act_mean[kMaxNu], act_inv_std[kMaxNu];
 };
-static_assert(offsetof(EncSmem, h0) % 16 == 0 && offsetof(EncSmem, h1) % 16 == 0 && offsetof(EncSmem, w_ih1) % 16 == 0, "float4 alignment");
+static_assert(offsetof(EncSmem<64>, h0) % 16 == 0 && offsetof(EncSmem<64>, h1) % 16 == 0 && offsetof(EncSmem<64>, w_ih1) % 16 == 0, "float4 alignment");
+static_assert(offsetof(EncSmem<32>, h0) % 16 == 0 && offsetof(EncSmem<32>, h1) % 16 == 0 && offsetof(EncSmem<32>, w_ih1) % 16 == 0, "float4 alignment");
 
-// acc[g][i][j] += sum_k aT[k][4rg+i] * WT[k][64g + 4ug + j]
+// acc[g][i][j] += sum_k aT[k][4rg+i] * WT[k][HG g + 4ug + j]
+template <int HG>
 __device__ __forceinline__ void gemm3(const float* __restrict__ WT, const float* __restrict__ aT, int rg, int ug,
                                       float acc[3][4][4]) {
 #pragma unroll 4
-  for (int k = 0; k < kHg; ++k) {
+  for (int k = 0; k < HG; ++k) {
     const float4 a = *reinterpret_cast<const float4*>(aT + k * kEncRows + 4 * rg);
     const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
-      const float4 w = *reinterpret_cast<const float4*>(WT + k * kG3 + 64 * g + 4 * ug);
+      const float4 w = *reinterpret_cast<const float4*>(WT + k * (3 * HG) + HG * g + 4 * ug);
       const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -76,13 +79,14 @@ __device__ __forceinline__ void zero3(float acc[3][4][4]) {
 
 // GRU gate equations (torch.nn.GRU, gate order r,z,n): gi/gh are the input/hidden pre-activations
 // WITHOUT bias for r,z,n; h_old may be null (zero state).
+template <int HG>
 __device__ __forceinline__ void gru_finish(const float gi[3][4][4], const float gh[3][4][4], const float* b_i,
                                            const float* b_h, const float* hT_old, float* hT_new, int rg, int ug) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int unit = 4 * ug + j;
-    const float bir = b_i[unit], biz = b_i[64 + unit], bin = b_i[128 + unit];
-    const float bhr = b_h[unit], bhz = b_h[64 + unit], bhn = b_h[128 + unit];
+    const float bir = b_i[unit], biz = b_i[HG + unit], bin = b_i[2 * HG + unit];
+    const float bhr = b_h[unit], bhz = b_h[HG + unit], bhn = b_h[2 * HG + unit];
     float4 ho = make_float4(0.f, 0.f, 0.f, 0.f);
     if (hT_old) ho = *reinterpret_cast<const float4*>(hT_old + unit * kEncRows + 4 * rg);
     const float hov[4] = {ho.x, ho.y, ho.z, ho.w};
@@ -98,14 +102,15 @@ __device__ __forceinline__ void gru_finish(const float gi[3][4][4], const float 
   }
 }
 
-// input projection of layer 0 (gin <= 4 inputs): gi[g][i][j] = sum_u w_ih0[64g+unit][u] * x[row][u]
-__device__ __forceinline__ void layer0_input(const EncSmem& s, int step_j, int B, int gin, int rg, int ug,
+// input projection of layer 0 (gin <= 4 inputs): gi[g][i][j] = sum_u w_ih0[HG g+unit][u] * x[row][u]
+template <int HG>
+__device__ __forceinline__ void layer0_input(const EncSmem<HG>& s, int step_j, int B, int gin, int rg, int ug,
                                              float gi[3][4][4]) {
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float* w = s.w_ih0 + (64 * g + 4 * ug + j) * gin;
+      const float* w = s.w_ih0 + (HG * g + 4 * ug + j) * gin;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float* x = s.act + ((4 * rg + i) * B + step_j) * gin;
@@ -116,9 +121,12 @@ __device__ __forceinline__ void layer0_input(const EncSmem& s, int step_j, int B
     }
 }
 
-__global__ void __launch_bounds__(256, 1) encode_gru_kernel(EncArgs a) {
+// HG = hidden_units / 2: 64 (config.py:37) or 32 (the reference class default hidden_units = 64, w_nl.py:71); 4 HG threads
+template <int HG>
+__global__ void __launch_bounds__(4 * HG, 1) encode_gru_kernel(EncArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  EncSmem& s = *reinterpret_cast<EncSmem*>(smem_raw);
+  constexpr int kG3 = 3 * HG, kNT = 4 * HG;
+  EncSmem<HG>& s = *reinterpret_cast<EncSmem<HG>*>(smem_raw);
   const int tid = threadIdx.x;
   const int rg = tid & 15, ug = tid >> 4;
   const int B = a.B, gin = a.gin;
@@ -128,12 +136,12 @@ __global__ void __launch_bounds__(256, 1) encode_gru_kernel(EncArgs a) {
                             reinterpret_cast<const float4*>(a.m.w_hh1_t)};
     float4* dst[3] = {reinterpret_cast<float4*>(s.w_hh0), reinterpret_cast<float4*>(s.w_ih1), reinterpret_cast<float4*>(s.w_hh1)};
     for (int w = 0; w < 3; ++w)
-      for (int i = tid; i < kHg * kG3 / 4; i += 256) dst[w][i] = __ldg(src[w] + i);
-    for (int i = tid; i < kG3 * gin; i += 256) s.w_ih0[i] = a.m.w_ih0[i];
-    for (int i = tid; i < kG3; i += 256) {
+      for (int i = tid; i < HG * kG3 / 4; i += kNT) dst[w][i] = __ldg(src[w] + i);
+    for (int i = tid; i < kG3 * gin; i += kNT) s.w_ih0[i] = a.m.w_ih0[i];
+    for (int i = tid; i < kG3; i += kNT) {
       s.b_ih0[i] = a.m.b_ih0[i]; s.b_hh0[i] = a.m.b_hh0[i]; s.b_ih1[i] = a.m.b_ih1[i]; s.b_hh1[i] = a.m.b_hh1[i];
     }
-    for (int i = tid; i < 2 * kHg; i += 256) s.w_out[i] = a.m.w_out[i];
+    for (int i = tid; i < 2 * HG; i += kNT) s.w_out[i] = a.m.w_out[i];
     if (tid < 2) s.b_out[tid] = a.m.b_out[tid];
     if (tid < gin) { s.act_mean[tid] = a.m.act_mean[tid]; s.act_inv_std[tid] = a.m.act_inv_std[tid]; }
   }
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(256, 1) encode_gru_kernel(EncArgs a) {
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * kEncRows;
     // normalised action windows of the tile (w_nl.py:121): act[row][j][u], j = 0 oldest
-    for (int i = tid; i < kEncRows * B * gin; i += 256) {
+    for (int i = tid; i < kEncRows * B * gin; i += kNT) {
       const int r = i / (B * gin), rem = i - r * (B * gin), j = rem / gin, u = rem - j * gin;
       long long row = row0 + r;
       if (row >= a.rows) row = a.rows - 1;
@@ -158,37 +166,49 @@ __global__ void __launch_bounds__(256, 1) encode_gru_kernel(EncArgs a) {
 
     float gi[3][4][4], gh[3][4][4];
     // layer 0, first cell: newest entry (reversed order, w_nl.py:27), zero state
-    layer0_input(s, B - 1, B, gin, rg, ug, gi);
+    layer0_input<HG>(s, B - 1, B, gin, rg, ug, gi);
     zero3(gh);
-    gru_finish(gi, gh, s.b_ih0, s.b_hh0, nullptr, s.h0[0], rg, ug);
+    gru_finish<HG>(gi, gh, s.b_ih0, s.b_hh0, nullptr, s.h0[0], rg, ug);
     __syncthreads();
     for (int st = 0; st < B; ++st) {
       const int cur = st & 1, prv = cur ^ 1;
       // layer 1 cell st: x = h0[cur], h = h1[prv] (zero at st == 0)
       zero3(gi);
-      gemm3(s.w_ih1, s.h0[cur], rg, ug, gi);
+      gemm3<HG>(s.w_ih1, s.h0[cur], rg, ug, gi);
       zero3(gh);
-      if (st > 0) gemm3(s.w_hh1, s.h1[prv], rg, ug, gh);
-      gru_finish(gi, gh, s.b_ih1, s.b_hh1, st > 0 ? s.h1[prv] : nullptr, s.h1[cur], rg, ug);
+      if (st > 0) gemm3<HG>(s.w_hh1, s.h1[prv], rg, ug, gh);
+      gru_finish<HG>(gi, gh, s.b_ih1, s.b_hh1, st > 0 ? s.h1[prv] : nullptr, s.h1[cur], rg, ug);
       if (st + 1 < B) {  // layer 0 cell st+1: x = window entry B-2-st, h = h0[cur]
-        layer0_input(s, B - 2 - st, B, gin, rg, ug, gi);
+        layer0_input<HG>(s, B - 2 - st, B, gin, rg, ug, gi);
         zero3(gh);
-        gemm3(s.w_hh0, s.h0[cur], rg, ug, gh);
-        gru_finish(gi, gh, s.b_ih0, s.b_hh0, s.h0[cur], s.h0[prv], rg, ug);
+        gemm3<HG>(s.w_hh0, s.h0[cur], rg, ug, gh);
+        gru_finish<HG>(gi, gh, s.b_ih0, s.b_hh0, s.h0[cur], s.h0[prv], rg, ug);
       }
       __syncthreads();
     }
     if (tid < 2 * kEncRows) {  // linear_out on the top layer's last state (w_nl.py:29)
-      const int r = tid & (kEncRows - 1), o = tid >> 6;
+      const int r = tid & (kEncRows - 1), o = tid >> 6;  // 2 x 64 outputs: the first 128 threads (4 HG >= 128)
       const float* hT = s.h1[(B - 1) & 1];
       float acc = s.b_out[o];
 #pragma unroll 8
-      for (int k = 0; k < kHg; ++k) acc = fmaf(s.w_out[o * kHg + k], hT[k * kEncRows + r], acc);
+      for (int k = 0; k < HG; ++k) acc = fmaf(s.w_out[o * HG + k], hT[k * kEncRows + r], acc);
       if (row0 + r < a.rows) a.p_out[(row0 + r) * 2 + o] = acc;
     }
     // no barrier needed here: the next tile's first writes (act, h0[0]) do not alias what the
     // output phase reads (h1), and h1 is next written only after the barrier that follows A(0).
   }
+}
+
+template <int HG>
+static int launch_encode_fp32_t(const EncArgs& a, cudaStream_t stream) {
+  const int smem = (int)sizeof(EncSmem<HG>);
+  // function attributes are per device: set on every launch, like every other kernel of the library
+  NLC_CUDA_OK(cudaFuncSetAttribute(encode_gru_kernel<HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  long long n_tiles = (a.rows + kEncRows - 1) / kEncRows;
+  int grid = (int)(n_tiles < 148 ? n_tiles : 148);
+  encode_gru_kernel<HG><<<grid, 4 * HG, smem, stream>>>(a);
+  NLC_LAUNCH_OK("encode_gru_kernel");
+  return NLC_OK;
 }
 
 int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, cudaStream_t stream) {
@@ -197,14 +217,7 @@ int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, in
   a.hist = hist; a.p_out = p; a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.gin = m->gin;
   a.rows = (long long)K * T;
   a.m = m->d;
-  const int smem = (int)sizeof(EncSmem);
-  // function attributes are per device: set on every launch, like every other kernel of the library
-  NLC_CUDA_OK(cudaFuncSetAttribute(encode_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  long long n_tiles = (a.rows + kEncRows - 1) / kEncRows;
-  int grid = (int)(n_tiles < 148 ? n_tiles : 148);
-  encode_gru_kernel<<<grid, 256, smem, stream>>>(a);
-  NLC_LAUNCH_OK("encode_gru_kernel");
-  return NLC_OK;
+  return m->Hg == 64 ? launch_encode_fp32_t<64>(a, stream) : launch_encode_fp32_t<32>(a, stream);
 }
 
 int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream,
@@ -217,13 +230,13 @@ int encode_history_impl(nlc_model_t m, const float* hist_dev, int hist_ch, int K
   NLC_REQUIRE(m && hist_dev && p_dev, NLC_ERR_ARG, "nlc_encode_history: null pointer");
   NLC_REQUIRE(K >= 1 && T >= 1, NLC_ERR_ARG, "nlc_encode_history: K and T must be positive");
   NLC_REQUIRE(B >= 1 && B <= 8, NLC_ERR_SHAPE, "nlc_encode_history: window length %d outside [1,8]", B);
-  NLC_REQUIRE(m->Hg == kHg, NLC_ERR_SHAPE, "encoder hidden size must be 64");
+  NLC_REQUIRE(m->Hg == 64 || m->Hg == 32, NLC_ERR_SHAPE, "encoder hidden size must be 64 or 32");
   switch (math_mode) {
     case NLC_MATH_FP32: return launch_encode_fp32(m, hist_dev, hist_ch, K, T, B, p_dev, s);
     case NLC_MATH_TC_SPLIT3:
     case NLC_MATH_TC_FP16:
       // shapes without a tensor-core instantiation run on the fp32 kernel
-      if (B < 2 || B * m->gin > 8 || m->gin > 2) {
+      if (B < 2 || B * m->gin > 8 || m->gin > 2 || m->Hg != kHg) {
         if ((long long)K * T >= 4096)
           warn_once(kWarnEncoderFfma, "encoder: window length %d x input width %d has no tcgen05 instantiation; %lld windows run on the "
                     "fp32 CUDA-core kernel", B, m->gin, (long long)K * T);

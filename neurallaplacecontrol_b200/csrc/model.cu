@@ -160,7 +160,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   const int gin = nu + (d->encode_obs_time ? 1 : 0);
   NLC_REQUIRE(nx >= 1 && nx <= kMaxNx, NLC_ERR_SHAPE, "state_dim %d outside [1,%d]", nx, kMaxNx);
   NLC_REQUIRE(nu >= 1 && gin <= kMaxNu, NLC_ERR_SHAPE, "GRU input width %d outside [1,%d]", gin, kMaxNu);
-  NLC_REQUIRE(Hm == 128, NLC_ERR_SHAPE, "hidden_units must be 128 (config.py:37); got %d", Hm);
+  NLC_REQUIRE(Hm == 128 || Hm == 64, NLC_ERR_SHAPE, "hidden_units must be 128 (config.py:37) or 64 (the class default, w_nl.py:71); got %d", Hm);
   NLC_REQUIRE(S >= 2 && S <= kMaxS, NLC_ERR_SHAPE, "s_terms %d outside [2,%d]", S, kMaxS);
   NLC_REQUIRE(d->action_std_len == 1 || d->action_std_len == nu, NLC_ERR_SHAPE, "action_std_len must be 1 or nu");
   const void* ptrs[] = {d->state_mean, d->state_std, d->action_mean, d->action_std, d->gru_w_ih_l0, d->gru_w_hh_l0,
@@ -258,7 +258,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
     put(o_amean, i, mean);
     put(o_ainv, i, 1.0 / stdv);
   }
-  {
+  if (Hm == 128) {  // (the tensor-core kernels are built for hidden_units = 128: other widths run on the fp32 kernels)
     // encode_tc2.cu operands: exponent scales folded (sigmoid(x) = 1/(1 + 2^(-log2e x)), tanh(x) = 2/(1 + 2^(-2 log2e x)) - 1)
     const double cR = -1.4426950408889634, cN = 2.0 * cR;
     auto gate_scale = [&](int row) { return row < 2 * Hg ? cR : cN; };
@@ -325,7 +325,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
     for (int i = 0; i < 2; ++i) put(o_enc2c, nlc::kE2Bout + i, d->enc_out_b[i]);
   }
 
-  if (N3t <= 416) {  // rollout_tc2.cu operands: -2 log2(e) folded
+  if (N3t <= 416 && Hm == 128) {  // rollout_tc2.cu operands: -2 log2(e) folded
     const double cN = -2.0 * 1.4426950408889634;
     std::vector<double> w2s((size_t)Hm * Hm);
     for (size_t i = 0; i < w2s.size(); ++i) w2s[i] = cN * d->mlp_w2[i];

@@ -41,13 +41,14 @@ struct RollArgs {
   int w3_smem;   // 0: W3 (128 x N3p floats) does not fit shared memory next to W2 (S = 33 with nx >= 5) and is read from L2
 };
 
+template <int H>
 __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ act, const float* __restrict__ WT, int ldw,
                                               int row0, int col0, float acc[kRT][4]) {
 #pragma unroll 2
-  for (int k4 = 0; k4 < kH / 4; ++k4) {
+  for (int k4 = 0; k4 < H / 4; ++k4) {
     float4 a[kRT];
 #pragma unroll
-    for (int i = 0; i < kRT; ++i) a[i] = *reinterpret_cast<const float4*>(act + (row0 + i) * kH + 4 * k4);
+    for (int i = 0; i < kRT; ++i) a[i] = *reinterpret_cast<const float4*>(act + (row0 + i) * H + 4 * k4);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float4 w = *reinterpret_cast<const float4*>(WT + (4 * k4 + kk) * ldw + col0);
@@ -63,7 +64,10 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ act, con
   }
 }
 
+// H = hidden_units: 128 (config.py:37) or 64 (the reference class default, w_nl.py:71)
+template <int H>
 __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
+  constexpr int kH = H;  // shadows the file-scope width of the default configuration
   extern __shared__ __align__(16) float smem[];
   const int nx = a.nx, S = a.S, N3p = a.N3p, R = a.R, Lp = nx + 2, nP = nx * S;
   float* w2 = smem;                       // [128][128]
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
     }
     // ---- L1: a1 = tanh(b1' + W1x . in) ----
     for (int i = tid; i < R * kH; i += 256) {
-      const int r = i >> 7, n = i & (kH - 1);
+      const int r = i / kH, n = i & (kH - 1);
       float acc = a.row_b1 ? a.row_b1[(size_t)min(k0 + r, a.K - 1) * kH + n] : b1[n];
       for (int j = 0; j < Lp; ++j) acc = fmaf(w1x[j * kH + n], in[r * Lp + j], acc);
       a1[r * ldt + n] = tanh_acc(acc);
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
     __syncthreads();
     // ---- L2: a2 = tanh(b2 + a1 . W2^T) ----
     for (int it = tid; it < RG * (kH / 4); it += 256) {
-      const int rg = it >> 5, cg = it & 31;
+      const int rg = it / (kH / 4), cg = it & (kH / 4 - 1);
       float acc[kRT][4];
 #pragma unroll
       for (int i = 0; i < kRT; ++i) { acc[i][0] = b2[4 * cg]; acc[i][1] = b2[4 * cg + 1]; acc[i][2] = b2[4 * cg + 2]; acc[i][3] = b2[4 * cg + 3]; }
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
       float acc[kRT][4];
 #pragma unroll
       for (int i = 0; i < kRT; ++i) { acc[i][0] = b3[4 * cg]; acc[i][1] = b3[4 * cg + 1]; acc[i][2] = b3[4 * cg + 2]; acc[i][3] = b3[4 * cg + 3]; }
-      tile_gemm_128(a2, w3r, N3p, rg * kRT, 4 * cg, acc);
+      tile_gemm_128<H>(a2, w3r, N3p, rg * kRT, 4 * cg, acc);
       const int pair0 = 2 * cg;  // pairs pair0, pair0+1 ; pair = c*S + k
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(256, 1) rollout_nl_kernel(RollArgs a) {
   }
 }
 
-static size_t rollout_smem_floats(int nx, int S, int N3p, int R, int termRows, bool w3_smem = true) {
+static size_t rollout_smem_floats(int kH, int nx, int S, int N3p, int R, int termRows, bool w3_smem = true) {
   const int Lp = nx + 2;
   return (size_t)kH * kH + (w3_smem ? (size_t)kH * N3p : 0) + (size_t)R * termRows + (size_t)R * kH + (size_t)Lp * kH + 2 * kH + N3p +
          2 * S + (size_t)R * Lp + (size_t)R * nx + 2 * nx + 2 * (size_t)R + 8;
@@ -242,24 +246,25 @@ int launch_rollout_fp32(nlc_model_s* m, const nlc_rollout_opts* o, const float* 
   a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.cost_total = cost; a.states = states;
   const int nP = m->nx * m->S;
-  a.termRows = ((nP > kH ? nP : kH) + 3) / 4 * 4;
+  a.termRows = ((nP > m->Hm ? nP : m->Hm) + 3) / 4 * 4;
   const size_t max_bytes = 227 * 1024;
   int R = 64;
   // W3 stays in shared memory when at least 16 rows fit beside it; else (S = 33 with nx >= 5) it is read through L2
-  bool w3s = rollout_smem_floats(m->nx, m->S, m->N3p, 16, a.termRows, true) * sizeof(float) <= max_bytes;
+  bool w3s = rollout_smem_floats(m->Hm, m->nx, m->S, m->N3p, 16, a.termRows, true) * sizeof(float) <= max_bytes;
   a.w3_smem = w3s ? 1 : 0;
-  while (R > 8 && rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float) > max_bytes) R -= 8;
-  NLC_REQUIRE(rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float) <= max_bytes, NLC_ERR_SHAPE,
+  while (R > 8 && rollout_smem_floats(m->Hm, m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float) > max_bytes) R -= 8;
+  NLC_REQUIRE(rollout_smem_floats(m->Hm, m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float) <= max_bytes, NLC_ERR_SHAPE,
               "rollout: model (nx=%d, S=%d) does not fit shared memory", m->nx, m->S);
   // spread small K over the SMs: the horizon is sequential, so latency is set by the rows one CTA owns
   int want = (K + 147) / 148;
   want = (want + 7) / 8 * 8;
   if (want < R) R = want;
   a.R = R;
-  const size_t smem = rollout_smem_floats(m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float);
-  NLC_CUDA_OK(cudaFuncSetAttribute(rollout_nl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes));
+  const size_t smem = rollout_smem_floats(m->Hm, m->nx, m->S, m->N3p, R, a.termRows, w3s) * sizeof(float);
+  auto kern = m->Hm == 128 ? rollout_nl_kernel<128> : rollout_nl_kernel<64>;
+  NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes));
   const int grid = (K + R - 1) / R;
-  rollout_nl_kernel<<<grid, 256, smem, stream>>>(a);
+  kern<<<grid, 256, smem, stream>>>(a);
   NLC_LAUNCH_OK("rollout_nl_kernel");
   return NLC_OK;
 }
@@ -367,7 +372,7 @@ extern "C" int nlc_model_forward(nlc_model_t m, const float* obs_dev, const floa
 // ---------------------------------------------------------------------------------------------------------------------
 namespace nlc {
 
-__global__ void __launch_bounds__(128) forward_ts_prep_kernel(ModelDev m, int S, int Lp, int norm_time, float dt, const float* __restrict__ ts,
+__global__ void __launch_bounds__(128) forward_ts_prep_kernel(ModelDev m, int kH, int S, int Lp, int norm_time, float dt, const float* __restrict__ ts,
                                                               int K, float* __restrict__ row_b1, float* __restrict__ row_tn) {
   __shared__ float th[kMaxS], ph[kMaxS];
   const int k = blockIdx.x, n = threadIdx.x;
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(128) forward_ts_prep_kernel(ModelDev m, int S,
   if (norm_time) tn = tn / (dt * 8.0f);  // w_nl.py:123
   const float T = 2.0f * (tn + 1.0e-6f);
   const float gamma = 1.0e-3f + 4.605170185988091f / T;
-  for (int j = n; j < S; j += 128) {  // oracle/ilt.py: fourier_s_points + complex_to_sphere
+  for (int j = n; j < S; j += kH) {  // oracle/ilt.py: fourier_s_points + complex_to_sphere
     const float im = 3.14159265358979f * (float)j / T;
     th[j] = atan2f(im, gamma);
     // phi = asin((r^2-1)/(r^2+1)) = 2 atan(r) - pi/2 (the asin form cancels for large r)
@@ -398,14 +403,14 @@ extern "C" int nlc_model_forward_ts(nlc_model_t m, const float* obs_dev, const f
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* p_action = scratch_dev;                 // [K][2]
   float* row_tn = scratch_dev + 2 * (size_t)K;   // [K]
-  float* row_b1 = scratch_dev + 4 * (size_t)K;   // [K][128]   (offset keeps 16-byte alignment)
+  float* row_b1 = scratch_dev + 4 * (size_t)K;   // [K][hidden_units]   (offset keeps 16-byte alignment)
   NLC_REQUIRE(math_mode == NLC_MATH_FP32 || math_mode == NLC_MATH_TC_SPLIT3 || math_mode == NLC_MATH_TC_FP16, NLC_ERR_ARG,
               "unknown math_mode %d", math_mode);
   // the single-pass fp16 mode has no per-sample-time rollout instantiation: it takes the fp32-class tensor-core form
   const int mm = math_mode == NLC_MATH_TC_FP16 ? NLC_MATH_TC_SPLIT3 : math_mode;
   int rc = encode_history_impl(m, act_dev, m->gin, K, 1, B, p_action, mm, s);
   if (rc != NLC_OK) return rc;
-  forward_ts_prep_kernel<<<K, 128, 0, s>>>(m->d, m->S, m->nx + 2, m->normalize && m->normalize_time, (float)m->dt, ts_dev, K, row_b1, row_tn);
+  forward_ts_prep_kernel<<<K, m->Hm, 0, s>>>(m->d, m->Hm, m->S, m->nx + 2, m->normalize && m->normalize_time, (float)m->dt, ts_dev, K, row_b1, row_tn);
   NLC_LAUNCH_OK("forward_ts_prep_kernel");
   nlc_rollout_opts o;
   o.env = m->nx == 3 ? NLC_ENV_PENDULUM : (m->nx == 5 ? NLC_ENV_CARTPOLE : NLC_ENV_ACROBOT);

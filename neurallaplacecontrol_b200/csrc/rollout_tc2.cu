@@ -1118,7 +1118,7 @@ static int launch_one(const Args& a, int tiles, cudaStream_t stream) {
 }  // namespace rt2
 
 bool rollout_has_tensor_core_form(const nlc_model_s* m) {
-  return (m->S == 17 || m->S == 33) && (m->nx == 3 || m->nx == 5 || m->nx == 6);
+  return m->Hm == 128 && (m->S == 17 || m->S == 33) && (m->nx == 3 || m->nx == 5 || m->nx == 6);
 }
 
 // returns NLC_ERR_UNSUPPORTED when the (nx, S) pair has no tensor-core instantiation (caller falls back)

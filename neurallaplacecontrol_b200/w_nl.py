@@ -51,8 +51,9 @@ class NeuralLaplaceModel(nn.Module):
         super().__init__()
         if ilt_algorithm != "fourier":
             raise NotImplementedError("only ilt_algorithm='fourier' is on this path (w_nl.py:86-88 'cme' is not)")
-        if hidden_units != 128:
-            raise NotImplementedError("the kernels are built for hidden_units=128 (config.py:37)")
+        if hidden_units not in (64, 128):
+            raise NotImplementedError("the kernels are built for hidden_units = 128 (config.py:37) and 64 (the class default, "
+                                      "w_nl.py:71; fp32 CUDA-core kernels only)")
         self.ilt_algorithm = ilt_algorithm
         self.latent_dim = latent_dim
         self.action_encoder = _EncoderParams(action_dim, 2, hidden_units // 2, encode_obs_time)
@@ -190,7 +191,7 @@ class NeuralLaplaceModel(nn.Module):
             else:
                 h = self.handle()
                 ts32 = ts.to(torch.float32).contiguous()
-                scratch = torch.empty((K, 132), dtype=torch.float32, device=dev)
+                scratch = torch.empty((K, 4 + self.hidden_units), dtype=torch.float32, device=dev)
                 _lib.check(lib.nlc_model_forward_ts(h, obs.data_ptr(), act.data_ptr(), ts32.data_ptr(), K, B, out.data_ptr(),
                                                     scratch.data_ptr(), _lib.MATH_MODES[self.math_mode], _lib.current_stream_ptr()),
                            "nlc_model_forward_ts")

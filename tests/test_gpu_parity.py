@@ -595,3 +595,42 @@ def test_per_dimension_bounds_and_u_per_command():
     assert float(p.perturbed_action[..., 0].max()) * 2.0 <= 0.5 + 1e-6 and float(p.perturbed_action[..., 1].min()) * 2.0 >= -0.25 - 1e-6
     assert relerr(ref["cost_total"], p.cost_total) < TOL
     assert relerr(ref["U"][:3] * 2.0, actions) < TOL
+
+
+def test_hidden_units_64_class_default():
+    """``hidden_units=64`` is the reference class default (``w_nl.py:71``; ``config.py:37`` uses 128): GRU width 32, MLP width 64.
+    Those widths run on the fp32 CUDA-core kernels whatever ``math_mode`` asks for: model forward (fixed and per-sample
+    times) and a small plan against the oracle."""
+    from oracle import costs, mppi, nl_model
+    from _util import START_STATE, injected_noise
+
+    nlc = _nlc()
+    env = "oderl-cartpole"
+    nx, nu = costs.ENV_DIMS[env]
+    torch.manual_seed(5)
+    m = nlc.NeuralLaplaceModel(nx, nu, nx, hidden_units=64, s_recon_terms=S_TERMS, state_mean=np.zeros(nx), state_std=np.ones(nx),
+                               action_mean=np.array([0.0] * nu), action_std=np.array([1.5]), normalize=True, normalize_time=True,
+                               dt=DT, device="cuda:0").double()
+    with torch.no_grad():  # trained-model operating range (cf. oracle/gen_golden.py calibrate_)
+        m.laplace_rep_func.linear_tanh_stack[4].bias[nx * S_TERMS:].sub_(4.0)
+    sd = {k: v.detach().clone().double() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    K = 70
+    obs = torch.randn(K, nx, generator=g, dtype=torch.float64)
+    act = (torch.rand(K, 4, nu, generator=g, dtype=torch.float64) * 2 - 1) * 3.0
+    for ts in (torch.full((K, 1), DT, dtype=torch.float64), 0.01 + 0.3 * torch.rand(K, 1, generator=g, dtype=torch.float64)):
+        ref = nl_model.nl_forward(sd, obs, act, ts)
+        out = m(obs.cuda(), act.cuda(), ts.cuda())
+        assert relerr(ref, out) < TOL, relerr(ref, out)
+    K, T = 200, 8
+    noise = injected_noise(K, T, nu, seed=13)
+    U0 = torch.zeros(T, nu, dtype=torch.float64)
+    p = nlc.MPPIDelay(nlc.NLDynamics(m, DT), nlc.EnvRunningCost(env), nx, nlc.noise_sigma_for(nu), num_samples=K, horizon=T,
+                      device="cuda:0", u_min=torch.tensor(-3.0), u_max=torch.tensor(3.0), u_scale=3.0, U_init=U0)
+    p.noise_dist.sample = lambda shape: noise
+    buf = torch.zeros(4, nu, dtype=torch.float64)
+    action = p.command(np.array(START_STATE[env]), buf)
+    ref = mppi.command(U0.clone(), torch.tensor(START_STATE[env]), buf, noise, mppi.make_nl_dynamics(sd, DT), costs.running_cost(env),
+                       noise_sigma=mppi.noise_sigma_for(nu), u_scale=3.0, u_min=-3.0, u_max=3.0)
+    assert relerr(ref["cost_total"], p.cost_total) < TOL and relerr(ref["states"], p.states) < TOL
+    assert action_relerr(ref["action"], action, ref["U"], 3.0) < TOL
