@@ -268,8 +268,10 @@ int nlc_planner_exchange_status(nlc_planner_t p, int* connected, int* status);
 
 /* MPPIDelay.command (mppi_delay.py:193-224) end to end with HOST buffers, single shard: copies the
  * state [nx] and action_buffer [B][nu] (fp64, as the reference's callers hold them) to the device,
- * runs both phases, copies the action [nu] back and synchronises the stream.  Without injected noise the whole step,
- * copies included, is one CUDA-graph launch.                                                        */
+ * runs both phases and returns with the action [nu] on the host.  The inputs and the action travel through MAPPED pinned
+ * host memory: the step's first kernel reads the staged inputs, its last kernel writes the action and bumps a sequence word
+ * the host spins on - no copy nodes and no stream synchronisation on the critical path (later work on the stream is ordered
+ * after the step as usual).  Without injected noise the whole step is one CUDA-graph launch.          */
 int nlc_planner_command_host(nlc_planner_t p, const double* state_host, const double* action_buffer_host,
                              const float* noise_in_dev, double* action_host, void* stream);
 

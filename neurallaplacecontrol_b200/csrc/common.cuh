@@ -61,6 +61,12 @@ struct StepTail {
   void* softmax_ws;              // stage 4 workspace header: re-armed for the next step (min = +inf, ticket = 0)
   unsigned int* ready;           // encoder readiness counters of the overlapped step: zeroed for the next step
   int n_ready;
+  // host entry point (nlc_planner_command_host): the action and a sequence word go straight into MAPPED pinned host memory -
+  // the host spins on the word instead of paying a D2H copy node and a stream synchronisation
+  float* host_action;            // [nu] mapped host memory (nullptr: none)
+  unsigned int* host_seq;        // mapped host word, incremented after the action is visible system-wide
+  const float* action_src;       // the planner's device-resident action (written earlier in the same kernel)
+  int nu;
 };
 
 constexpr int kMaxNx = 8;

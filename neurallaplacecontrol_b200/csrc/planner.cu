@@ -20,9 +20,11 @@ struct nlc_planner_s {
   float *U, *U_rolled, *noise, *perturbed, *hist, *actions, *pert_cost, *p, *cost_total, *weights, *states;
   float *triple, *all_triples, *action, *stats, *state_in, *abuf_in;
   void* softmax_ws;
-  // pinned host staging for the host-buffer entry point
+  // MAPPED pinned host staging of the host-buffer entry point: the first kernel of the step reads h_in, the last writes the
+  // action and bumps a sequence word in h_out; the host spins on that word (no copy nodes, no stream synchronisation)
   float* h_in;   // [nx + B*nu]
-  float* h_out;  // [nu]
+  float* h_out;  // [4] action, then the sequence word at float index 4
+  bool to_host;  // the control step being issued belongs to nlc_planner_command_host: its combine kernel reports to h_out
   // sampler call index in device memory (read by the perturb kernel, bumped right after it) so that a whole control step
   // is a fixed sequence of launches with fixed arguments: captured once into CUDA graphs, replayed with one launch
   unsigned long long* call_ctr;
@@ -56,6 +58,7 @@ int softmax_partial_impl(const float* cost_dev, const float* noise_dev, int K, i
                          float* weights_dev, void* workspace_dev, bool with_init, const ExchangePub& pub, cudaStream_t s);
 int launch_combine(const float* triples_dev, int G, int T, int nu, float lambda_, float u_scale, float* U_dev, float* action_dev,
                    float* stats_dev, const StepTail& tl, cudaStream_t s);
+int launch_ingest(const float* h_in, float* state_in, float* abuf_in, int nx, int nb, cudaStream_t s);
 int launch_combine_exchange(float* mailbox, int G, int stride, int T, int nu, float lambda_, float u_scale, float* U, float* action,
                             float* stats, unsigned long long* step_ctr, unsigned int* status, const StepTail& tl, cudaStream_t s);
 bool encoder_is_tensor_core(nlc_model_t m, int B, int math_mode);
@@ -90,7 +93,7 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;
   p->call_ctr = nullptr; p->cap_stream = nullptr; p->graph_core = nullptr; p->graph_host = nullptr;
   p->graph_core_tried = p->graph_host_tried = false;
-  p->pending = false;
+  p->pending = false; p->to_host = false;
   p->overlap = false; p->side_stream = nullptr; p->ev_fork = p->ev_join = nullptr; p->ready = nullptr;
   p->mailbox = nullptr; p->xstride = 0; p->xchg = false; p->mailboxes_dev = nullptr; p->xstep = nullptr; p->xstatus = nullptr;
   memset(p->peer, 0, sizeof(p->peer)); memset(p->peer_ipc, 0, sizeof(p->peer_ipc));
@@ -129,9 +132,12 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->softmax_ws = base + offs[17];
   // stage 4's workspace header starts armed (min = +inf as all-ones, ticket = 0); every combine kernel re-arms it (StepTail)
   if (cudaMemset(p->softmax_ws, 0xFF, 4) != cudaSuccess) { set_error("planner: memset failed"); return fail(NLC_ERR_CUDA); }
-  if (cudaMallocHost(&p->h_in, sizeof(float) * (nx + B * nu)) != cudaSuccess || cudaMallocHost(&p->h_out, sizeof(float) * 4) != cudaSuccess) {
+  if (cudaHostAlloc(&p->h_in, sizeof(float) * 64, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostAlloc(&p->h_out, sizeof(float) * 8, cudaHostAllocMapped) != cudaSuccess) {
     cudaGetLastError(); set_error("planner: pinned allocation failed"); return fail(NLC_ERR_NOMEM);
   }
+  memset(p->h_in, 0, sizeof(float) * 64);
+  memset(p->h_out, 0, sizeof(float) * 8);
   if (d->rollout.dynamics == NLC_DYN_NEURAL_LAPLACE && encoder_is_tensor_core(model, mp.B, d->math_mode) &&
       rollout_can_overlap(model, mp.K, mp.T, d->math_mode) && d->rollout.env >= 0) {
     if (cudaMalloc(&p->ready, sizeof(unsigned int) * (T + 1)) != cudaSuccess || cudaMemset(p->ready, 0, sizeof(unsigned int) * (T + 1)) != cudaSuccess ||
@@ -425,7 +431,8 @@ extern "C" int nlc_planner_finish(nlc_planner_t p, void* stream) {
   // re-arms stage 4's workspace and the encoder readiness counters for the next control step
   NLC_REQUIRE(p->pending, NLC_ERR_ARG, "nlc_planner_finish without a preceding nlc_planner_rollout");
   p->pending = false;
-  const StepTail tl{p->U_rolled, p->call_ctr, p->softmax_ws, p->overlap ? p->ready : nullptr, mp.T};
+  StepTail tl{p->U_rolled, p->call_ctr, p->softmax_ws, p->overlap ? p->ready : nullptr, mp.T, nullptr, nullptr, nullptr, 0};
+  if (p->to_host) { tl.host_action = p->h_out; tl.host_seq = reinterpret_cast<unsigned int*>(p->h_out + 4); tl.action_src = p->action; tl.nu = mp.nu; }
   if (p->xchg)  // wait (on the device) for the G triples of this control step in the own mailbox, then combine
     return launch_combine_exchange(p->mailbox, p->d.n_shards, p->xstride, mp.T, mp.nu, mp.lambda_, mp.u_scale, p->U, p->action, p->stats,
                                    p->xstep, p->xstatus, tl, s);
@@ -463,12 +470,11 @@ static cudaGraphExec_t planner_capture(nlc_planner_t p, bool with_host_copies) {
   cudaGraphExec_t exec = nullptr;
   if (cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   bool ok = true;
-  if (with_host_copies) {
-    ok = ok && cudaMemcpyAsync(p->state_in, p->h_in, sizeof(float) * nx, cudaMemcpyHostToDevice, p->cap_stream) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(p->abuf_in, p->h_in + nx, sizeof(float) * nb, cudaMemcpyHostToDevice, p->cap_stream) == cudaSuccess;
-  }
+  (void)mp;
+  if (with_host_copies) ok = ok && launch_ingest(p->h_in, p->state_in, p->abuf_in, nx, nb, p->cap_stream) == NLC_OK;
+  p->to_host = with_host_copies;
   ok = ok && planner_core_direct(p, p->cap_stream) == NLC_OK;
-  if (with_host_copies) ok = ok && cudaMemcpyAsync(p->h_out, p->action, sizeof(float) * mp.nu, cudaMemcpyDeviceToHost, p->cap_stream) == cudaSuccess;
+  p->to_host = false;
   const cudaError_t ee = cudaStreamEndCapture(p->cap_stream, &graph);
   p->calls = calls0;  // launches recorded during capture did not run
   if (!ok || ee != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return nullptr; }
@@ -521,22 +527,44 @@ extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_hos
   NLC_CUDA_OK(cudaSetDevice(p->device));
   { int rc = planner_check_model(p); if (rc != NLC_OK) return rc; }
   if (!noise_in_dev && !p->graph_host_tried) { p->graph_host_tried = true; p->graph_host = planner_capture_preserving_state(p, true); }
+  NLC_REQUIRE(nx + nb <= 64, NLC_ERR_SHAPE, "nlc_planner_command_host: state + action buffer exceed the 64-float staging area");
   for (int i = 0; i < nx; ++i) p->h_in[i] = (float)state_host[i];
   for (int i = 0; i < nb; ++i) p->h_in[nx + i] = (float)action_buffer_host[i];
-  if (!noise_in_dev && p->graph_host) {  // the whole step, copies included, as one graph launch
+  volatile unsigned int* seq = reinterpret_cast<volatile unsigned int*>(p->h_out + 4);
+  const unsigned int seq0 = *seq;
+  __sync_synchronize();  // the staged inputs are in memory before the launch that reads them
+  if (!noise_in_dev && p->graph_host) {  // the whole step as one graph launch: ingest kernel, 5-6 kernels, the last reports to h_out
     NLC_CUDA_OK(cudaGraphLaunch(p->graph_host, s));
     p->calls++;
-    count_launch(p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE ? 6 : 5);
+    count_launch(p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE ? 7 : 6);
   } else {
-    NLC_CUDA_OK(cudaMemcpyAsync(p->state_in, p->h_in, sizeof(float) * nx, cudaMemcpyHostToDevice, s));
-    NLC_CUDA_OK(cudaMemcpyAsync(p->abuf_in, p->h_in + nx, sizeof(float) * nb, cudaMemcpyHostToDevice, s));
-    int rc = nlc_planner_rollout(p, p->state_in, 0, p->abuf_in, noise_in_dev, stream);
+    int rc = launch_ingest(p->h_in, p->state_in, p->abuf_in, nx, nb, s);
     if (rc != NLC_OK) return rc;
+    rc = nlc_planner_rollout(p, p->state_in, 0, p->abuf_in, noise_in_dev, stream);
+    if (rc != NLC_OK) return rc;
+    p->to_host = true;
     rc = nlc_planner_finish(p, stream);
+    p->to_host = false;
     if (rc != NLC_OK) return rc;
-    NLC_CUDA_OK(cudaMemcpyAsync(p->h_out, p->action, sizeof(float) * mp.nu, cudaMemcpyDeviceToHost, s));
   }
-  NLC_CUDA_OK(cudaStreamSynchronize(s));
+  // Spin on the sequence word the combine kernel bumps after the action is visible system-wide.  Checked against the stream
+  // every ~2 ms of spinning, so that a failed launch or a device error surfaces instead of spinning for ever.
+  {
+    unsigned long long spins = 0;
+    while (*seq == seq0) {
+      __builtin_ia32_pause();
+      if ((++spins & 0xFFFFull) == 0) {
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q == cudaSuccess) break;  // the step has retired (the word is visible by now, or the step failed before its end)
+        if (q != cudaErrorNotReady) { set_error("nlc_planner_command_host: %s", cudaGetErrorString(q)); return NLC_ERR_CUDA; }
+      }
+    }
+    __sync_synchronize();
+    if (*seq == seq0) {
+      NLC_CUDA_OK(cudaStreamSynchronize(s));
+      NLC_REQUIRE(*seq != seq0, NLC_ERR_CUDA, "nlc_planner_command_host: the control step retired without reporting its action");
+    }
+  }
   for (int i = 0; i < mp.nu; ++i) action_host[i] = p->h_out[i];
   return NLC_OK;
 }

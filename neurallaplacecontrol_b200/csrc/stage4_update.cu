@@ -160,7 +160,26 @@ __device__ __forceinline__ void step_tail(const StepTail& tl) {
   if (threadIdx.x == 0) {
     if (tl.call_ctr) *tl.call_ctr += 1ull;
     if (tl.softmax_ws) { SoftWs* ws = static_cast<SoftWs*>(tl.softmax_ws); ws->min_ord = 0xffffffffu; ws->ticket = 0u; }
+    if (tl.host_seq) {  // everything of the step is done: hand the action to the spinning host thread
+      for (int i = 0; i < tl.nu; ++i) tl.host_action[i] = tl.action_src[i];
+      __threadfence_system();
+      const unsigned int v = *reinterpret_cast<volatile unsigned int*>(tl.host_seq) + 1u;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(tl.host_seq), "r"(v) : "memory");
+    }
   }
+}
+
+// host entry point: state [nx] and action buffer [nb] from mapped pinned host memory into the planner's device buffers (one
+// tiny kernel node instead of two H2D copy nodes)
+__global__ void ingest_kernel(const float* __restrict__ h_in, float* __restrict__ state_in, float* __restrict__ abuf_in, int nx, int nb) {
+  const int i = threadIdx.x;
+  if (i < nx) state_in[i] = h_in[i];
+  else if (i < nx + nb) abuf_in[i - nx] = h_in[i];
+}
+int launch_ingest(const float* h_in, float* state_in, float* abuf_in, int nx, int nb, cudaStream_t s) {
+  ingest_kernel<<<1, 64, 0, s>>>(h_in, state_in, abuf_in, nx, nb);
+  NLC_LAUNCH_OK("ingest_kernel");
+  return NLC_OK;
 }
 
 __global__ void softmax_combine_kernel(const float* __restrict__ triples, int G, int TN, int nu, float inv_lambda,
@@ -301,7 +320,7 @@ extern "C" int nlc_softmax_combine(const float* triples_dev, int G, int T, int n
   NLC_REQUIRE(G >= 1 && T >= 1 && nu >= 1 && lambda_ > 0.0f, NLC_ERR_ARG, "nlc_softmax_combine: bad sizes");
   softmax_combine_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(triples_dev, G, T * nu, nu, 1.0f / lambda_,
                                                                            u_scale, U_dev, action_dev, stats_dev,
-                                                                           StepTail{nullptr, nullptr, nullptr, nullptr, 0});
+                                                                           StepTail{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0});
   NLC_LAUNCH_OK("softmax_combine_kernel");
   return NLC_OK;
 }
