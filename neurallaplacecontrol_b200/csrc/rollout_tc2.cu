@@ -429,6 +429,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   constexpr int kChunksA = ((kTiles == 1 && !kStream) || N3t <= 128) ? kChunks : (kChunks + 1) / 2;  // chunks in the first column half
   constexpr int N3a = 16 * kChunksA, N3b = N3t - N3a;
   constexpr int N3buf = kStream ? N3a : N3t;                          // rows of W3 resident at a time
+  // kSplitD (one tile, resident W3): the L3 product is issued as TWO products into disjoint column ranges of the accumulator,
+  // each with its own completion barrier, so the epilogue of the first half's columns runs while the second half is still
+  // on the tensor pipe - in this form nothing else covers the products (strict chain per sample)
+  constexpr bool kSplitD = kTiles == 1 && !kStream && kChunks >= 8;
+  constexpr int kChunksH = kSplitD ? (kChunks + 1) / 2 : kChunks;     // chunks of the first product
+  constexpr int N3h = 16 * kChunksH;
   static_assert((kTiles == 1 ? (N3a <= 256 && N3b <= 256) : (N3a <= 128 && N3b <= 128 && N3t <= 256)) && N3t <= kMaxN3 && Lp + 1 <= 16, "tile shape");
   unsigned char* w1_img = smem_raw;                                   // [hi | lo] 128 x 16 halves = 4 KB each
   unsigned char* w2_img = w1_img + 2 * kH * 16 * 2;                   // [hi | lo] 32 KB each
@@ -482,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
     const uint32_t w2_hi = smem_u32(w2_img), w2_lo = w2_hi + kH * kH * 2;
     const uint32_t w3_hi = smem_u32(w3_img), w3_lo = w3_hi + (uint32_t)N3buf * kH * 2;
     const uint32_t w3b_off = kStream ? 0u : (uint32_t)(N3a / 8) * kSbo;
-    uint32_t n = 0, n_w3 = 0;  // products waited for; W3 halves waited for (issuing warp only)
+    uint32_t n = 0, n_w3 = 0, n_b = 0;  // products waited for; W3 halves waited for (issuing warp only); second L3 halves (kSplitD)
     int tstep = 0;
     auto mark = [&](int ev) {
       if (a.trace && blockIdx.x == 0 && lane == 0 && tstep < 104) a.trace[(tstep * 16 + warp) * 8 + ev] = clock64();
@@ -500,9 +506,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         fence_after_sync();
         if (ev == 0) issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w1_hi, w1_lo, kH, 1, kSbo16);
         else if (ev == 1) issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w2_hi, w2_lo, kH, kH / 16, kSbo);
+        else if (ev == 2 && kSplitD) {
+          issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w3_hi, w3_lo, N3h, kH / 16, kSbo);
+          mma_commit(done);  // first half: the epilogue starts on it while the second half computes
+          issue_gemm_ts<kSplit3>(tg + kColD + N3h, tg + kColA, w3_hi + (uint32_t)(N3h / 8) * kSbo, w3_lo + (uint32_t)(N3h / 8) * kSbo,
+                                 N3t - N3h, kH / 16, kSbo);
+          mma_commit(&s.done[1]);
+        }
         else if (ev == 2) issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w3_hi, w3_lo, N3a, kH / 16, kSbo);
         else issue_gemm_ts<kSplit3>(tg + kColD, tg + kColA, w3_hi + w3b_off, w3_lo + w3b_off, N3b, kH / 16, kSbo);
-        mma_commit(done);
+        if (!(ev == 2 && kSplitD)) mma_commit(done);
       }
       __syncwarp();
     };
@@ -628,7 +641,25 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         mark(5);
         // the first half's product has read the W3 buffer: the second half streams in under this epilogue
         if (kStream && wl == 0 && elect_one()) load_w3_rows(a.m, w3_img, N3a, N3b, N3t, N3buf, &s.bar_w3);
-        if (active) {
+        if constexpr (kSplitD) {
+          // this thread's chunks of the first product, then (after the second product's own barrier) of the second: the same
+          // chunks in the same order as the single-product form, so the sums are bit-identical
+          constexpr int kM = kChunksH % 4;
+          if (active) {
+            if (cg == 0) L3Loop<NX, S, 0, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+            else if (cg == 1) L3Loop<NX, S, 1, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+            else if (cg == 2) L3Loop<NX, S, 2, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+            else L3Loop<NX, S, 3, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+          }
+          mbar_wait_sleep(&s.done[1], n_b & 1); ++n_b;
+          fence_after_sync();
+          if (active) {
+            if (cg == 0) L3Loop<NX, S, kChunksH + (4 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+            else if (cg == 1) L3Loop<NX, S, kChunksH + (5 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+            else if (cg == 2) L3Loop<NX, S, kChunksH + (6 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+            else L3Loop<NX, S, kChunksH + (7 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+          }
+        } else if (active) {
           if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
           else if (cg == 1) L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
           else if (kCG == 4 && cg == 2) L3Loop<NX, S, 2, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);

@@ -634,3 +634,35 @@ def test_hidden_units_64_class_default():
                        noise_sigma=mppi.noise_sigma_for(nu), u_scale=3.0, u_min=-3.0, u_max=3.0)
     assert relerr(ref["cost_total"], p.cost_total) < TOL and relerr(ref["states"], p.states) < TOL
     assert action_relerr(ref["action"], action, ref["U"], 3.0) < TOL
+
+
+def test_resident_step_equals_command():
+    """``set_inputs`` + ``step`` (inputs resident in the planner's buffers, one graph launch) plans exactly what ``command`` does,
+    from host buffers (mapped-memory entry point) and from device tensors."""
+    from oracle import costs
+    from _util import START_STATE
+
+    env = "oderl-cartpole"
+    nx, nu = costs.ENV_DIMS[env]
+    K, T = 1024, 12
+    state = np.array(START_STATE[env]) + 0.01
+    buf = torch.tensor([[0.3], [-0.2], [0.1], [0.5]], dtype=torch.float64)
+    outs = []
+    for how in ("host", "device", "step"):
+        m = make_model(env, calibrated=True, math_mode="tc_split3")
+        p = make_planner(env, m, K, T, np.zeros((T, nu)), math_mode="tc_split3", seed=21)
+        acts = []
+        for it in range(3):
+            if how == "host":
+                a = p.command(state, buf)
+                assert np.allclose(p.last_action_host, a.cpu().numpy())
+            elif how == "device":
+                a = p.command(torch.from_numpy(state).cuda(), buf.cuda())
+            else:
+                p.set_inputs(state, buf)
+                a = p.step().double()
+            acts.append(a.clone())
+        outs.append((torch.stack(acts), p.U.clone(), p.cost_total.clone()))
+    for o in outs[1:]:
+        for x, y in zip(outs[0], o):
+            assert torch.equal(x, y)
