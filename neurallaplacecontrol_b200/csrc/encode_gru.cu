@@ -221,7 +221,7 @@ int launch_encode_fp32(nlc_model_s* m, const float* hist, int hist_ch, int K, in
 }
 
 int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream,
-                      unsigned int* ready = nullptr, int max_ctas = 0);
+                      unsigned int* ready = nullptr, int max_ctas = 0, long long tile_begin = 0, long long tile_end = 0);
 
 // hist_ch: channels stored per history entry (model gin for nlc_model_forward, whose caller supplies the time channel
 // like the reference's forward; action_dim on the planner path, where encode_obs_time's channel is synthesised)
@@ -256,8 +256,8 @@ bool encoder_is_tensor_core(nlc_model_t m, int B, int math_mode) {
 // The planner's overlapped form: step-major tile order, ready[t] counts finished warps of step t (4 per tile), at most
 // max_ctas CTAs so that the rollout kernel keeps its SMs.
 int encode_history_overlapped(nlc_model_t m, const float* hist_dev, int K, int T, int B, float* p_dev, int math_mode,
-                              unsigned int* ready, int max_ctas, cudaStream_t s) {
-  return launch_encode_tc2(m, hist_dev, m->nu, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s, ready, max_ctas);
+                              unsigned int* ready, int max_ctas, long long tile_begin, long long tile_end, cudaStream_t s) {
+  return launch_encode_tc2(m, hist_dev, m->nu, K, T, B, p_dev, math_mode == NLC_MATH_TC_SPLIT3, s, ready, max_ctas, tile_begin, tile_end);
 }
 
 }  // namespace nlc

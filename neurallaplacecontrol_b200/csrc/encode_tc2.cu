@@ -61,6 +61,7 @@ struct Args {
   // plain sample-major order (window index = k * T + t).
   int tiles_per_t;
   unsigned int* ready;
+  long long tile_begin;  // first tile of this launch (step-major order only: the planner may split the encoder in two launches)
   long long* trace;  // measurement only: clock64 timeline of CTA 0, [step][warp][8 events]
   ModelDev m;
 };
@@ -248,7 +249,8 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   const uint32_t w_ih1_hi = smem_u32(s.w[1][0]), w_ih1_lo = smem_u32(s.w[1][1]);
   const uint32_t w_hh1_hi = smem_u32(s.w[2][0]), w_hh1_lo = smem_u32(s.w[2][1]);
   const uint32_t w_x0 = smem_u32(s.wx[0]), w_x1 = smem_u32(s.wx[1]);
-  const long long n_tiles = (a.rows + kRows - 1) / kRows;
+  const long long n_tiles = (a.rows + kRows - 1) / kRows;   // one past the last tile of this launch
+  const long long tile_first = a.tile_begin + blockIdx.x;
 
   if (warp == 16) {
     // =====================================  MMA warp  =====================================
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       }
       __syncwarp();
     };
-    if ((long long)blockIdx.x < n_tiles) {
+    if (tile_first < n_tiles) {
       mbar_wait(&s.bar_w, 0);
       wait_ready(kBarH0);  // [x(0) | 1]
       issue_a(false);
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
       wait_ready(kBarH1);
       issue_b(false);
     }
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long tile = tile_first; tile < n_tiles; tile += gridDim.x) {
       const bool has_next = tile + gridDim.x < n_tiles;
       for (int st = 0; st < B; ++st) {
         if (st + 1 < B || has_next) {
@@ -414,8 +416,8 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
   };
 
   // ---- head of the first tile: layer-0 cell 0 (zero state: the [x | 1] product alone), then A(1) and the input part of B(0) ----
-  if ((long long)blockIdx.x < n_tiles) {
-    base_cur = window_base(blockIdx.x);
+  if (tile_first < n_tiles) {
+    base_cur = window_base(tile_first);
     fetch_x(false, 0);
     publish_h0(true);
     fetch_x(false, 1);
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     publish_h0(true);
     publish_h1(false);  // nothing of layer 1 exists yet: the input part of B(0) can go
   }
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (long long tile = tile_first; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * kRows;
     const long long next_tile = tile + gridDim.x;
     const bool has_next = next_tile < n_tiles;
@@ -535,7 +537,7 @@ static long long* g_enc_trace = nullptr;
 void set_encoder_trace(long long* p) { g_enc_trace = p; }
 
 int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int T, int B, float* p, int split3, cudaStream_t stream,
-                      unsigned int* ready, int max_ctas) {
+                      unsigned int* ready, int max_ctas, long long tile_begin, long long tile_end) {
   using namespace enc2;
   NLC_REQUIRE(B * m->gin <= 8, NLC_ERR_SHAPE, "tcgen05 encoder: window_length * input_width = %d exceeds 8", B * m->gin);
   NLC_REQUIRE(B >= 2, NLC_ERR_SHAPE, "tcgen05 encoder: window_length must be >= 2");
@@ -545,6 +547,7 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   a.rows = (long long)K * T;
   a.tiles_per_t = ready ? (K + kRows - 1) / kRows : 0;
   a.ready = ready;
+  a.tile_begin = 0;
   a.m = m->d;
   a.trace = g_enc_trace;
   const int smem = (int)sizeof(Smem) + 128;
@@ -567,10 +570,17 @@ int launch_encode_tc2(nlc_model_s* m, const float* hist, int hist_ch, int K, int
   if (a.trace && split3) kern = NLC_ENC_PICK(true, 3, 1, true);
 #undef NLC_ENC_PICK
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const long long n_tiles = ready ? (long long)a.tiles_per_t * T : (a.rows + kRows - 1) / kRows;
-  if (ready) a.rows = n_tiles * kRows;  // step-major: every tile is walked; rows beyond K are masked at the output
+  long long n_tiles = ready ? (long long)a.tiles_per_t * T : (a.rows + kRows - 1) / kRows;
+  if (ready) {
+    // step-major: every tile is walked (rows beyond K are masked at the output); [tile_begin, tile_end) of them in this launch
+    if (tile_end > 0 && tile_end < n_tiles) n_tiles = tile_end;
+    a.tile_begin = tile_begin > 0 ? tile_begin : 0;
+    a.rows = n_tiles * kRows;
+    if (a.tile_begin >= n_tiles) return NLC_OK;
+  }
   const int cap = max_ctas > 0 && max_ctas < 148 ? max_ctas : 148;
-  const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+  const long long mine = n_tiles - a.tile_begin;
+  const int grid = (int)(mine < cap ? mine : cap);
   kern<<<grid, kThreadsAll, smem, stream>>>(a);
   NLC_LAUNCH_OK("encode_tc2_kernel");
   return NLC_OK;

@@ -25,6 +25,7 @@ struct nlc_planner_s {
   float* h_in;   // [nx + B*nu]
   float* h_out;  // [4] action, then the sequence word at float index 4
   bool to_host;  // the control step being issued belongs to nlc_planner_command_host: its combine kernel reports to h_out
+  int kernels_per_step;  // kernels one control step launches (counted during the capture warm-up; for nlc_launch_count)
   // sampler call index in device memory (read by the perturb kernel, bumped right after it) so that a whole control step
   // is a fixed sequence of launches with fixed arguments: captured once into CUDA graphs, replayed with one launch
   unsigned long long* call_ctr;
@@ -63,7 +64,7 @@ int launch_combine_exchange(float* mailbox, int G, int stride, int T, int nu, fl
                             float* stats, unsigned long long* step_ctr, unsigned int* status, const StepTail& tl, cudaStream_t s);
 bool encoder_is_tensor_core(nlc_model_t m, int B, int math_mode);
 int encode_history_overlapped(nlc_model_t m, const float* hist_dev, int K, int T, int B, float* p_dev, int math_mode,
-                              unsigned int* ready, int max_ctas, cudaStream_t s);
+                              unsigned int* ready, int max_ctas, long long tile_begin, long long tile_end, cudaStream_t s);
 bool rollout_can_overlap(const nlc_model_s* m, int K, int T, int math_mode);
 int launch_rollout_overlapped(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p, const float* hist,
                               const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states, int math_mode,
@@ -93,7 +94,7 @@ extern "C" int nlc_planner_create(nlc_planner_t* out, nlc_model_t model, const n
   p->device = device; p->model = model; p->d = *d; p->calls = 0; p->arena = nullptr; p->h_in = nullptr; p->h_out = nullptr;
   p->call_ctr = nullptr; p->cap_stream = nullptr; p->graph_core = nullptr; p->graph_host = nullptr;
   p->graph_core_tried = p->graph_host_tried = false;
-  p->pending = false; p->to_host = false;
+  p->pending = false; p->to_host = false; p->kernels_per_step = 6;
   p->overlap = false; p->side_stream = nullptr; p->ev_fork = p->ev_join = nullptr; p->ready = nullptr;
   p->mailbox = nullptr; p->xstride = 0; p->xchg = false; p->mailboxes_dev = nullptr; p->xstep = nullptr; p->xstatus = nullptr;
   memset(p->peer, 0, sizeof(p->peer)); memset(p->peer_ipc, 0, sizeof(p->peer_ipc));
@@ -344,9 +345,22 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
     // tool that serialises kernels then runs it to completion before the rollout starts polling.
     const int n_tiles = (mp.K + 127) / 128;
     // (the readiness counters were zeroed by the previous step's combine kernel)
+    // Beyond half a wave of tiles the rollout leaves the encoder too few SMs to keep ahead of it for the whole horizon: the
+    // first steps' windows are encoded on all SMs BEFORE the fork, and only as many of the last steps as the spare SMs can
+    // encode during the rollout (12.6 us per tile and SM, ~9.5 us per rollout step: measured at config 4 / its shards; a
+    // wrong estimate only makes the rollout poll a little longer) run beside it.
+    long long split = 0;  // first tile of the part that runs beside the rollout
+    if (n_tiles > 74) {
+      const double spare_tiles = 0.85 * (148 - n_tiles) * (mp.T * 9.5) / 12.6;
+      long long beside_steps = (long long)(spare_tiles / n_tiles);
+      if (beside_steps > mp.T - 1) beside_steps = mp.T - 1;
+      split = (long long)(mp.T - beside_steps) * n_tiles;
+      rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148, 0, split, s);
+      if (rc != NLC_OK) return rc;
+    }
     NLC_CUDA_OK(cudaEventRecord(p->ev_fork, s));
     NLC_CUDA_OK(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
-    rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148 - n_tiles, s);
+    rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148 - n_tiles, split, 0, s);
     if (rc != NLC_OK) return rc;
     if (ev) NLC_CUDA_OK(cudaEventRecord(ev[2], s));  // profile: end of the encoder's own span
     rc = launch_rollout_overlapped(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,
@@ -456,7 +470,9 @@ static cudaGraphExec_t planner_capture(nlc_planner_t p, bool with_host_copies) {
   if (!p->cap_stream && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   // first use of every kernel outside capture: one-time function attributes and lazy module loading must not be captured
   const uint64_t calls0 = p->calls;
+  const uint64_t launches0 = nlc_launch_count();
   if (planner_core_direct(p, p->cap_stream) != NLC_OK || cudaStreamSynchronize(p->cap_stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  p->kernels_per_step = (int)(nlc_launch_count() - launches0);
   // undo the warm-up's side effects on the control sequence and the sampler: U <- U before the roll is not recoverable
   // from U_rolled alone, so the warm-up ran on a scratch copy (see caller); the counter is rewound here
   if (cudaMemsetAsync(p->call_ctr, 0, sizeof(unsigned long long), p->cap_stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -510,7 +526,7 @@ extern "C" int nlc_planner_step(nlc_planner_t p, void* stream) {
   if (p->graph_core) {
     NLC_CUDA_OK(cudaGraphLaunch(p->graph_core, static_cast<cudaStream_t>(stream)));
     p->calls++;
-    count_launch(p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE ? 6 : 5);
+    count_launch(p->kernels_per_step);
     return NLC_OK;
   }
   return planner_core_direct(p, stream);
@@ -536,7 +552,7 @@ extern "C" int nlc_planner_command_host(nlc_planner_t p, const double* state_hos
   if (!noise_in_dev && p->graph_host) {  // the whole step as one graph launch: ingest kernel, 5-6 kernels, the last reports to h_out
     NLC_CUDA_OK(cudaGraphLaunch(p->graph_host, s));
     p->calls++;
-    count_launch(p->d.rollout.dynamics == NLC_DYN_NEURAL_LAPLACE ? 7 : 6);
+    count_launch(p->kernels_per_step + 1);  // + the ingest kernel
   } else {
     int rc = launch_ingest(p->h_in, p->state_in, p->abuf_in, nx, nb, s);
     if (rc != NLC_OK) return rc;

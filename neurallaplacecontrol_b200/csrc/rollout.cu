@@ -279,11 +279,13 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
 bool rollout_has_tensor_core_form(const nlc_model_s* m);
 
 // planner.cu: can the rollout of this plan run BESIDE its history encoder (one-tile tcgen05 form on ceil(K/128) SMs, polling the
-// encoder's per-step readiness counters)?  Plans of at most half a wave of tiles: the encoder keeps at least half the SMs.
+// encoder's per-step readiness counters)?
 bool rollout_can_overlap(const nlc_model_s* m, int K, int T, int math_mode) {
   static const bool off = [] { const char* e = getenv("NLC_NO_OVERLAP"); return e && e[0] == '1'; }();
   const char* f = getenv("NLC_ROLLOUT_TILES");  // a forced kernel form (parity tests) keeps the plain sequence
-  return !off && !(f && f[0]) && math_mode != NLC_MATH_FP32 && rollout_has_tensor_core_form(m) && T >= 2 && (K + 127) / 128 <= 74;
+  // up to 74 tiles the encoder keeps at least half the SMs for the whole step; up to 140 the planner runs most of the encoder
+  // first and only its tail beside the rollout (planner.cu)
+  return !off && !(f && f[0]) && math_mode != NLC_MATH_FP32 && rollout_has_tensor_core_form(m) && T >= 2 && (K + 127) / 128 <= 140;
 }
 int launch_rollout_overlapped(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p, const float* hist,
                               const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states, int math_mode,

@@ -504,10 +504,12 @@ def test_non_finite_weights_are_rejected():
         m.handle()
 
 
-@pytest.mark.parametrize("env,K,T", [("oderl-cartpole", 8192, 30), ("oderl-pendulum", 1000, 20), ("oderl-acrobot", 8192, 50), ("oderl-acrobot", 333, 7)])
+@pytest.mark.parametrize("env,K,T", [("oderl-cartpole", 8192, 30), ("oderl-pendulum", 1000, 20), ("oderl-acrobot", 8192, 50), ("oderl-acrobot", 333, 7),
+                                     ("oderl-acrobot", 16384, 50), ("oderl-cartpole", 12001, 9), ("oderl-pendulum", 17900, 3)])
 def test_overlapped_step_equals_sequential_step(env, K, T, monkeypatch):
-    """Plans within half a wave of tiles run the encoder beside the rollout (step-major encoder order, per-step readiness
-    counters): same kernels, same per-sample arithmetic - bit-identical costs, states and U as the plain sequence
+    """Plans within one wave of tiles run the encoder beside the rollout (step-major encoder order, per-step readiness
+    counters; beyond half a wave only the encoder's tail runs beside it - the last three cases): same kernels, same
+    per-sample arithmetic - bit-identical costs, states and U as the plain sequence
     (NLC_NO_OVERLAP is latched per process, so the plain sequence is reached by forcing the one-tile rollout form, which the
     overlap logic treats as a request for the plain launch order)."""
     from oracle import costs
