@@ -367,10 +367,8 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
     for (int i = 0; i < 4; ++i) { const __half2 p2 = __halves2half2(hv[2 * i], hv[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&p2); }
     *reinterpret_cast<uint4*>(s.h0_hi + (uint32_t)(row >> 3) * kSboX + 8 * kLbo + (uint32_t)(row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   };
-  // layer-0 cell: complete pre-activations come out of D0 = [r | z | hn | in].  With `store`, each 8-unit chunk goes into the
-  // layer-0 state image as soon as its gates are done (the conversion and the stores overlap the next chunk's MUFU work);
-  // the image is free once the part of the previous MMA B that reads it has completed (bar_h0), which `wait_h0` waits for
-  // before the first store.
+  // layer-0 cell: complete pre-activations come out of D0 = [r | z | hn | in]; with `store` the new state goes into the layer-0
+  // state image (after `wait_h0`: see below).
   auto cell_a = [&](bool from_zero, bool store, bool wait_h0) {
     if (from_zero) {  // cell 0 of a window: h = 0 (one uniform branch instead of a select per use)
 #pragma unroll
@@ -393,10 +391,16 @@ __global__ void __launch_bounds__(kThreadsAll, 1) encode_tc2_kernel(Args a) {
         if ((NN == 1 && i == 0) || (NN == 2 && (i & 1) == 0)) h0r[4 * c + i] = gru_pair<RZ, 3, true>(gr[i], gz[i], gn[i], gh[i], h0r[4 * c + i]);
         else h0r[4 * c + i] = gru_pair<RZ, (NN == 1 || NN == 2) ? 0 : NN, true>(gr[i], gz[i], gn[i], gh[i], h0r[4 * c + i]);
       }
-      if (store) {
-        if (c == 0 && wait_h0) { mbar_wait_sleep(&s.bar_h0, n_h0 & 1); ++n_h0; }
+    }
+    if (store) {
+      // The state image is free once the part of the previous MMA B that reads it has completed (bar_h0: half a product
+      // earlier than bar_b).  Waited for AFTER both chunks' gate math: that part completes ~1.8 k clocks after it was
+      // issued, later than one chunk's math (waiting after the first chunk showed up as 8.8 % of all stall samples).
+      if (wait_h0) { mbar_wait_sleep(&s.bar_h0, n_h0 & 1); ++n_h0; }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         const f2_t (&hc)[4] = *reinterpret_cast<const f2_t(*)[4]>(&h0r[4 * c]);
-        store_operand8<kSplit3>(s.h0_hi, kSboX, s.h0_lo, kSbo, row, u0, hc);
+        store_operand8<kSplit3>(s.h0_hi, kSboX, s.h0_lo, kSbo, row, ubase + 8 * c, hc);
       }
     }
   };
