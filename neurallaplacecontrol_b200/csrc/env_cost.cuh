@@ -50,9 +50,23 @@ __device__ __forceinline__ float env_running_cost(const nlc_rollout_opts& o, con
 // (ctacrobot.py:153-166,233-255) sat on the critical path of every step: cos(atan2(s, c)) = c / sqrt(c^2 + s^2), so the
 // angles are never formed - an algebraic identity (difference ~1 ulp of fp32), pendulum and cartpole unchanged.
 __device__ __forceinline__ float env_running_cost_fast(const nlc_rollout_opts& o, const float* s, const float* u, int nu) {
-  if (o.env != NLC_ENV_ACROBOT) return env_running_cost(o, s, u, nu);
+  // (pendulum and cartpole restated here rather than calling env_running_cost: its acrobot branch - atan2f and two sincosf
+  // with their slow paths, ~480 instructions - would be compiled into every call site of the rollout's step loop)
   float ac = 0.0f;
   for (int i = 0; i < nu; ++i) ac = fmaf(u[i], u[i], ac);
+  if (o.env == NLC_ENV_PENDULUM) {
+    const float om = 1.0f - s[0];
+    const float state_reward = -(om * om + s[1] * s[1]);
+    return -(state_reward + 0.01f * (-(s[2] * s[2])) + (-0.01f * ac));
+  }
+  if (o.env == NLC_ENV_CARTPOLE) {
+    const float ex = (s[0] + s[3]) - o.goal_x, ey = s[2] - 1.0f;
+    float state_reward;
+    if (o.state_constraint) state_reward = -((ex * ex + expf(ex * 10.0f + 7.0f)) + ey * ey);
+    else state_reward = -(ex * ex + ey * ey);
+    const float vel = -(s[1] * s[1]) - s[4] * s[4];
+    return -(state_reward + 0.01f * vel + (-0.01f * ac));
+  }
   const float r1 = rsqrtf(fmaf(s[0], s[0], s[1] * s[1])), r2 = rsqrtf(fmaf(s[2], s[2], s[3] * s[3]));
   const float c1 = s[0] * r1, s1 = s[1] * r1, c2 = s[2] * r2, s2 = s[3] * r2;
   const float c12 = fmaf(c1, c2, -(s1 * s2)), s12 = fmaf(s1, c2, c1 * s2);

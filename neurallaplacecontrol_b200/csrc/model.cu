@@ -213,6 +213,12 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   size_t o_enc2w = A.add(tc_halves / 2), o_enc2c = A.add(nlc::kE2Count), o_enc2x = A.add(2 * 256 * 8 / 2);
   size_t o_m2w1 = A.add((size_t)2 * Hm * 16 / 2), o_m2w2 = A.add((size_t)2 * Hm * Hm / 2), o_m2w3 = A.add((size_t)2 * N3t * Hm / 2);
   size_t o_m2c = A.add(128 + 416);  // b2 | b3 (up to 416 (theta, phi) columns: rollout_tc2.cu kMaxN3)
+  // group-uniform W3 image of the ping-pong rollout: 32 columns per unit, NX (S-1)/16 regular units + 1 unit of last terms
+  const int gu_upc = (S - 1) % 16 == 0 ? (S - 1) / 16 : 0;
+  const int gu_units = gu_upc ? nx * gu_upc + 1 : 0;
+  const int N3u = (Hm == 128 && gu_units >= 1 && gu_units <= 8) ? 32 * gu_units : 0;
+  m->N3u = N3u;
+  size_t o_m2w3u = A.add((size_t)2 * (N3u ? N3u : 16) * Hm / 2), o_m2cu = A.add(N3u ? N3u : 16);
 
   for (int i = 0; i < G3 * gin; ++i) put(o_w_ih0, i, d->gru_w_ih_l0[i]);
   for (int i = 0; i < G3; ++i) {
@@ -341,6 +347,22 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
         }
     uint16_t* w3i = reinterpret_cast<uint16_t*>(A.data.data() + o_m2w3);
     nlc::tc_pack_weight_split(w3p.data(), N3t, Hm, w3i, w3i + (size_t)N3t * Hm);
+    if (N3u) {  // the same rows in the group-uniform order (see ModelDev::mlp2_w3u)
+      std::vector<double> w3u((size_t)N3u * Hm, 0.0);
+      const int kJ = nx * gu_upc;
+      for (int col = 0; col < N3u; ++col) {
+        const int j = col / 32, cgp = (col % 32) / 8, i = (col % 8) / 2, part = col % 2;
+        int c, k;
+        if (j < kJ) { c = j / gu_upc; k = 16 * (j % gu_upc) + cgp + 4 * i; }
+        else { c = cgp + 4 * i; k = S - 1; }
+        if (c >= nx) continue;  // no such channel: zero weights and bias (its Fourier weight is zeroed in the kernel too)
+        const int src = (part * nx + c) * S + k;
+        for (int h = 0; h < Hm; ++h) w3u[(size_t)col * Hm + h] = cN * d->mlp_w4[(size_t)src * Hm + h];
+        put(o_m2cu, col, cN * d->mlp_b4[src]);
+      }
+      uint16_t* w3ui = reinterpret_cast<uint16_t*>(A.data.data() + o_m2w3u);
+      nlc::tc_pack_weight_split(w3u.data(), N3u, Hm, w3ui, w3ui + (size_t)N3u * Hm);
+    }
     for (int n = 0; n < Hm; ++n) put(o_m2c, n, cN * d->mlp_b2[n]);
   }
 
@@ -364,6 +386,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   m->d.b_ih1 = base + o_b_ih1; m->d.b_hh1 = base + o_b_hh1; m->d.w_out = base + o_wout; m->d.b_out = base + o_bout;
   m->d.enc2_w = base + o_enc2w; m->d.enc2_c = base + o_enc2c; m->d.enc2_x = base + o_enc2x;
   m->d.mlp2_w1 = base + o_m2w1; m->d.mlp2_w2 = base + o_m2w2; m->d.mlp2_w3 = base + o_m2w3; m->d.mlp2_c = base + o_m2c;
+  m->d.mlp2_w3u = base + o_m2w3u; m->d.mlp2_cu = base + o_m2cu;
   m->d.w1_full_t = base + o_w1full; m->d.b1_raw = base + o_b1raw; m->d.w1x_t = base + o_w1x; m->d.b1_fold = base + o_b1f;
   m->d.w2_t = base + o_w2; m->d.b2 = base + o_b2; m->d.w3_t = base + o_w3; m->d.b3 = base + o_b3;
   m->d.ilt_phase = base + o_phase; m->d.ilt_weight = base + o_weight;

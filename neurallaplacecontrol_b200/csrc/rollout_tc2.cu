@@ -107,14 +107,15 @@ __device__ __forceinline__ void wait_windows_ready(const Args& a, int t, int lan
 // W1 (2 x 4 KB), W2 (2 x 32 KB), W3 (2 x N3t x 256 B) -> shared memory; bulk copies of at most 32 KB each.  with_w3 = false:
 // W3 is streamed half by half instead (load_w3_rows)
 __device__ __forceinline__ void load_weight_images(const ModelDev& m, unsigned char* w1_img, unsigned char* w2_img, unsigned char* w3_img,
-                                                   int N3t, uint64_t* bar, bool with_w3 = true) {
+                                                   int N3t, uint64_t* bar, bool with_w3 = true, const void* w3_src = nullptr) {
+  if (!w3_src) w3_src = m.mlp2_w3;
   const uint32_t b1 = 2 * kH * 16 * 2, b2 = 2 * kH * kH * 2, b3 = with_w3 ? 2u * (uint32_t)N3t * kH * 2 : 0u;
   mbar_expect_tx(bar, b1 + b2 + b3);
   bulk_g2s(w1_img, m.mlp2_w1, b1, bar);
   for (uint32_t o = 0; o < b2; o += 32768) bulk_g2s(w2_img + o, static_cast<const unsigned char*>(m.mlp2_w2) + o, 32768, bar);
   for (uint32_t o = 0; o < b3; o += 32768) {
     const uint32_t n = b3 - o < 32768 ? b3 - o : 32768;
-    bulk_g2s(w3_img + o, static_cast<const unsigned char*>(m.mlp2_w3) + o, n, bar);
+    bulk_g2s(w3_img + o, static_cast<const unsigned char*>(w3_src) + o, n, bar);
   }
 }
 // Rows [row0, row0 + nrows) of W3 (output columns of the third layer; multiples of 8, so whole 8-row groups of the K-major
@@ -339,10 +340,8 @@ struct L3Loop {
   }
 };
 
-// Ping-pong form: the (theta, phi) columns are dealt in UNITS of 8 columns (4 pairs) - 13 chunks over 4 column groups leave
-// one group with 4 chunks and three with 3, 26 units give 7, 7, 6, 6 - and all of a thread's units of a phase are loaded
-// before the first is used (one TMEM round trip per phase instead of one per chunk).  Unit u = columns 8u .. 8u+7 of the
-// full column space, pairs 4u .. 4u+3; kBase = first unit of the half that currently sits in the D region.
+// Ping-pong form: the (theta, phi) columns are dealt in UNITS of 8 columns (4 pairs), and all of a thread's units of a phase
+// are loaded before the first is used (one TMEM round trip per phase instead of one per chunk).
 __device__ __forceinline__ void ldtm8q(uint32_t taddr, f2_t (&v)[4]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -352,61 +351,48 @@ __device__ __forceinline__ void ldtm8q(uint32_t taddr, f2_t (&v)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = pk2u(r[2 * i], r[2 * i + 1]);
 }
-template <int NX, int S, int kUnit, bool kAccurate, int kRcp>
-__device__ __forceinline__ void l3_unit(const f2_t (&v)[4], const float* __restrict__ b3, const float* __restrict__ phase,
-                                        const float* __restrict__ weight, float (&delta)[NX]) {
-  f2_t bb[4];
+// GROUP-UNIFORM units (ping-pong form, ModelDev::mlp2_w3u): unit j = 32 columns, 8 per column group, so that the four column
+// groups of a sample run the SAME instructions on different addresses - the four warps of an SM sub-partition are the four
+// column groups of one row quarter, and with a code variant per group each sub-partition walked four copies of the unrolled
+// epilogue (47 KB; a tenth of the warp stalls were instruction fetches).  Regular unit j < NX upc (upc = (S-1)/16): channel
+// j / upc (compile time), terms 16 (j % upc) + cg + 4 i; the last unit holds the terms k = S-1 of channels cg and cg + 4.
+// tDcg, b3cg, phasecg, weightcg: the D region / bias / Fourier tables offset by this thread's column group (8 cg, 8 cg, cg, cg).
+template <int NX, int S, int kJ0, int kJ1, bool kAccurate, int kRcp>
+__device__ __forceinline__ void l3_units_gu(uint32_t tDcg, const float* __restrict__ b3cg, const float* __restrict__ phasecg,
+                                            const float* __restrict__ weightcg, int cg, float (&delta)[NX]) {
+  constexpr int kUpc = (S - 1) / 16, kJ = NX * kUpc, kCount = kJ1 - kJ0;
+  static_assert((S - 1) % 16 == 0 && kCount >= 1 && kCount <= 4 && kJ1 <= kJ + 1, "group-uniform units");
+  f2_t v[kCount][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float4 t = *reinterpret_cast<const float4*>(b3 + 8 * kUnit + 4 * i);
-    bb[2 * i] = pk2(t.x, t.y);
-    bb[2 * i + 1] = pk2(t.z, t.w);
-  }
+  for (int u = 0; u < kCount; ++u) ldtm8q(tDcg + 32 * u, v[u]);
+  tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 4; i += 2) {
-    const int p0 = 4 * kUnit + i, p1 = p0 + 1;
-    if (p0 < NX * S) {
-      const f2_t s0 = add2(v[i], bb[i]), s1 = add2(v[i + 1], bb[i + 1]);
+  for (int u = 0; u < kCount; ++u) {
+    const int j = kJ0 + u;
+    const float4 ba = *reinterpret_cast<const float4*>(b3cg + 32 * j), bb = *reinterpret_cast<const float4*>(b3cg + 32 * j + 4);
+    const f2_t bias[4] = {pk2(ba.x, ba.y), pk2(ba.z, ba.w), pk2(bb.x, bb.y), pk2(bb.z, bb.w)};
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      if (j == kJ && i == 2) break;  // the last unit: two pairs (channels cg and cg + 4), the other four columns are padding
+      const f2_t s0 = add2(v[u][i], bias[i]), s1 = add2(v[u][i + 1], bias[i + 1]);
       float th0, ph0, th1, ph1;
       upk2(s0, th0, ph0);
       upk2(s1, th1, ph1);
-      const int ch0 = p0 / S, k0 = p0 - ch0 * S;
-      const int ch1 = (p1 < NX * S) ? p1 / S : ch0, k1 = (p1 < NX * S) ? p1 - ch1 * S : k0;
       float t0, t1;
-      l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phase[k0], phase[k1], weight[k0], weight[k1], t0, t1);
-      delta[ch0] += t0;
-      if (p1 < NX * S) delta[ch1] += t1;
+      if (j < kJ) {
+        const int kb = 16 * (j % kUpc) + 4 * i;  // + cg: in the table pointers
+        l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phasecg[kb], phasecg[kb + 4], weightcg[kb], weightcg[kb + 4], t0, t1);
+        delta[j / kUpc] += t0;
+        delta[j / kUpc] += t1;
+      } else {
+        const float phl = phasecg[S - 1 - cg], wl = weightcg[S - 1 - cg];
+        l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phl, phl, wl, wl, t0, t1);
+#pragma unroll
+        for (int c = 0; c < NX; ++c) delta[c] += (c == cg) ? t0 : ((c == cg + 4) ? t1 : 0.0f);
+      }
     }
   }
 }
-// units kFirst, kFirst + 4, ... < kEnd of one column group: at most kMaxUnits of them
-template <int NX, int S, int kFirst, int kEnd, int kBase, bool kAccurate, int kRcp>
-struct L3Units {
-  static constexpr int kCount = kFirst < kEnd ? (kEnd - kFirst + 3) / 4 : 0;
-  template <int I>
-  static __device__ __forceinline__ void load(uint32_t tD, f2_t (&v)[kCount > 0 ? kCount : 1][4]) {
-    if constexpr (I < kCount) {
-      ldtm8q(tD + 8 * (kFirst + 4 * I - kBase), v[I]);
-      load<I + 1>(tD, v);
-    }
-  }
-  template <int I>
-  static __device__ __forceinline__ void compute(const f2_t (&v)[kCount > 0 ? kCount : 1][4], const float* b3, const float* phase,
-                                                 const float* weight, float (&delta)[NX]) {
-    if constexpr (I < kCount) {
-      l3_unit<NX, S, kFirst + 4 * I, kAccurate, kRcp>(v[I], b3, phase, weight, delta);
-      compute<I + 1>(v, b3, phase, weight, delta);
-    }
-  }
-  static __device__ __forceinline__ void run(uint32_t tD, const float* b3, const float* phase, const float* weight, float (&delta)[NX]) {
-    if constexpr (kCount > 0) {
-      f2_t v[kCount][4];
-      load<0>(tD, v);
-      tmem_ld_wait();
-      compute<0>(v, b3, phase, weight, delta);
-    }
-  }
-};
 
 template <int NX, int S, bool kSplit3, int kRcp, int kTiles, bool kPerRow = false>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
@@ -754,16 +740,20 @@ struct SmemTailPP {
   alignas(8) uint64_t done[2];
   uint32_t tmem_base;
 };
+template <int NX, int S>
+struct PPShape {  // columns of the group-uniform W3 image: model.cu packs N3u = 32 (NX (S-1)/16 + 1)
+  static constexpr int kUnits = NX * ((S - 1) / 16) + 1, N3u = 32 * kUnits;
+};
 constexpr int kThreadsPP = kThreads + 128;    // 16 epilogue warps + the MMA warp's group (setmaxnreg works on groups of 4 warps)
 
 template <int NX, int S, bool kSplit3, int kRcp>
 __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int Lp = NX + 2;
-  constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
-  constexpr int kChunks = N3t / 16;
-  constexpr int kChunksA = kChunks < 8 ? kChunks : 8;
-  constexpr int N3a = 16 * kChunksA, N3b = N3t - N3a;
+  // the (theta, phi) columns in the group-uniform order (l3_units_gu): units of 32 columns, the first four in the first half
+  constexpr int kUnits = PPShape<NX, S>::kUnits, N3t = PPShape<NX, S>::N3u;
+  constexpr int kUnitsA = kUnits < 4 ? kUnits : 4;
+  constexpr int N3a = 32 * kUnitsA, N3b = N3t - N3a;
   static_assert(N3b <= 128 && N3t <= 256 && Lp + 1 <= 16, "tile shape");
   unsigned char* w1_img = smem_raw;                                   // [hi | lo] 128 x 16 halves = 4 KB each
   unsigned char* w2_img = w1_img + 2 * kH * 16 * 2;                   // [hi | lo] 32 KB each
@@ -779,10 +769,10 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
     if (warp == 0 && elect_one()) {  // weight images by TMA bulk copies; only the MMA warp waits for them (see rollout_tc2_kernel)
       mbar_init(&s.bar_w, 1);
       mbar_fence_init();
-      load_weight_images(a.m, w1_img, w2_img, w3_img, N3t, &s.bar_w);
+      load_weight_images(a.m, w1_img, w2_img, w3_img, N3t, &s.bar_w, true, a.m.mlp2_w3u);
     }
     for (int i = tid; i < kH; i += kThreadsPP) s.b2[i] = a.m.mlp2_c[i];
-    for (int i = tid; i < 256; i += kThreadsPP) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
+    for (int i = tid; i < 256; i += kThreadsPP) s.b3[i] = i < N3t ? a.m.mlp2_cu[i] : 0.0f;
     for (int i = tid; i < S; i += kThreadsPP) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
     if (tid < NX) { s.smean[tid] = a.m.state_mean[tid]; s.sinv[tid] = a.m.state_inv_std[tid]; }
     for (int i = tid; i < 2 * 2 * kRows * 2; i += kThreadsPP) (&s.stage_u[0][0][0][0])[i] = 0.0f;
@@ -953,18 +943,14 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
     // first (kHalf == 0) or second half of the (theta, phi) columns: this thread's units -> partial sums in shared memory
     auto l3_half = [&](int x, auto half_tag) {
       constexpr int kHalf = decltype(half_tag)::value;
-      constexpr int kBeg = kHalf == 0 ? 0 : kChunksA, kEnd = kHalf == 0 ? kChunksA : kChunks;
+      constexpr int kBeg = kHalf == 0 ? 0 : kUnitsA, kEnd = kHalf == 0 ? kUnitsA : kUnits;
       const uint32_t tD = tlane + kGroupCols * x + kColD;
       float delta[NX];
 #pragma unroll
       for (int c = 0; c < NX; ++c) delta[c] = 0.0f;
-      if ((amask >> x) & 1) {
-        // unit u of this half belongs to column group (u - first unit of the half) mod 4
-        constexpr int kU0 = 2 * kBeg, kU1 = 2 * kEnd;
-        if (cg == 0) L3Units<NX, S, kU0 + 0, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
-        else if (cg == 1) L3Units<NX, S, kU0 + 1, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
-        else if (cg == 2) L3Units<NX, S, kU0 + 2, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
-        else L3Units<NX, S, kU0 + 3, kU1, kU0, kSplit3, kRcp % 10>::run(tD, s.b3, s.phase, s.weight, delta);
+      if constexpr (kBeg < kEnd) {
+        if ((amask >> x) & 1)
+          l3_units_gu<NX, S, kBeg, kEnd, kSplit3, kRcp % 10>(tD + 8 * cg, s.b3 + 8 * cg, s.phase + cg, s.weight + cg, cg, delta);
       }
       float* e = &s.exch[x][cg][row];
 #pragma unroll
@@ -973,8 +959,8 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
 
     // duties of step tt's END state that nothing waits for - its row of `states` (column group 2) and its running cost
     // (column group 3; mppi_delay.py:288-290: the post-step state with the action just applied) - are carried out one
-    // step later, behind these groups' units of the last L3 phase: they have one unit less there than groups 0 and 1 and
-    // would otherwise idle at the exchange barrier, while after the state update they would delay the next step's M1
+    // step later, behind these groups' units of the last L3 phase: after the state update they would delay the next step's M1
+    // (measured at config 4 with the group-uniform units: here 1.325 ms, before the E2 wait 1.333, before the E1 wait 1.378)
     auto deferred = [&](int x, int tt) {
       const int kx = x ? kk1 : kk0;
       if (!((lmask >> x) & 1)) return;
@@ -1100,7 +1086,7 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
 
 template <int NX, int S, bool kSplit3, int kRcp>
 static int launch_pp(const Args& a, cudaStream_t stream) {
-  constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
+  constexpr int N3t = PPShape<NX, S>::N3u;
   const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3t * kH * 2 + sizeof(SmemTailPP<NX>) + 128;
   NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
   auto kern = rollout_pp_kernel<NX, S, kSplit3, kRcp>;
@@ -1165,6 +1151,8 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   a.row_b1 = row_b1; a.row_tn = row_tn;
   NLC_REQUIRE(!row_b1 || (row_tn && split3 && !ready), NLC_ERR_ARG, "rollout: per-sample times need row_tn and the fp32-class tensor-core mode");
   if (2 * m->nx * m->S > 256) tiles_per_cta = 1;
+  NLC_REQUIRE(tiles_per_cta != 3 || m->N3u == 32 * (m->nx * ((m->S - 1) / 16) + 1), NLC_ERR_SHAPE,
+              "tcgen05 rollout: the model holds no group-uniform W3 image for nx=%d S=%d", m->nx, m->S);
   NLC_REQUIRE(!ready || (tiles_per_cta == 1 && (K + 127) / 128 <= 148 && status), NLC_ERR_ARG,
               "rollout: the overlapped form is the one-tile form of plans within one wave");
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;

@@ -26,6 +26,7 @@ def sass():
     if out.returncode != 0:
         pytest.skip("cuobjdump could not read the library")
     stats = collections.defaultdict(lambda: {"instr": 0, "mma": 0, "waterfall": 0})
+    bodies = collections.defaultdict(list)
     name = None
     for line in out.stdout.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -36,10 +37,19 @@ def sass():
             continue
         st = stats[name]
         st["instr"] += 1
+        body = bodies[name]
+        body.append(line)
         if "UTCHMMA" in line:
             st["mma"] += 1
-        if "BRA.U.ANY" in line:
-            st["waterfall"] += 1
+        m = re.search(r"BRA\.U\.ANY\s+0x([0-9a-f]+)", line)
+        if m:
+            # a divergence ("waterfall") loop: ptxas wraps an instruction whose uniform operand it could not prove uniform.
+            # Around the one-off TMEM allocate / free (UTCATOMSWS) at the kernel's ends it is harmless; around an MMA or
+            # a bulk copy it serialises the issue
+            target = int(m.group(1), 16)
+            loop = [b for b in body if int(re.match(r"\s+/\*([0-9a-f]+)\*/", b).group(1), 16) >= target]
+            if any(op in b for b in loop for op in ("UTCHMMA", "UTCQMMA", "UBLKCP", "UTMALDG")):
+                st["waterfall"] += 1
     return stats
 
 
@@ -55,4 +65,4 @@ def test_ping_pong_rollout_fits_the_instruction_cache(sass):
     pp = {n: s for n, s in sass.items() if "rollout_pp_kernel" in n}
     assert pp
     for n, s in pp.items():
-        assert s["instr"] * 16 <= 120 * 1024, (n, s["instr"] * 16 // 1024)
+        assert s["instr"] * 16 <= 80 * 1024, (n, s["instr"] * 16 // 1024)  # 62 KB with the group-uniform L3 units (round 2)
