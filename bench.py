@@ -249,6 +249,13 @@ class Ctx:
         """(device ms per step, wall ms per step, launches) - L2 flushed before every timed step (outside its span), barrier +
         synchronize on both sides, max over ranks."""
         torch = self.torch
+        idle = float(getattr(self.args, "idle", 0.0) or 0.0)
+        if idle > 0:
+            # every timed region starts from the same power state: on this pool's power-capped B200s a region measured right
+            # after another runs ~10 % slower (tools/diag_e2e.py: the same call 3.55 ms first, 3.93 ms after three other loops,
+            # 3.49 ms again after 2 s of idle), which otherwise shows up as a difference BETWEEN the numbers of one line
+            torch.cuda.synchronize()
+            time.sleep(idle)
         for _ in range(warmup):
             fn()
         self.barrier() if collective else torch.cuda.synchronize()
@@ -608,7 +615,8 @@ def run_gpu(args, env, K, H, desc):
                        "parallelism": f"K-sharded x{world}", "K_per_gpu": Kl, "tiles_per_gpu": (Kl + 127) // 128,
                        "sm_fill": min(1.0, ((Kl + 127) // 128) / N_SM),
                        "rollout_form": "ping-pong, 2 tiles per CTA" if pp else "1 tile per CTA", "math": args.math,
-                       "noise": "on-device Philox4x32-10", "l2": "flushed between timed steps (256 MiB fill)", "keep_states": True},
+                       "noise": "on-device Philox4x32-10", "l2": "flushed between timed steps (256 MiB fill)", "keep_states": True,
+                       "idle_before_each_timed_region_s": args.idle},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": head["ms_e2e"], "h2d_bytes_per_step": 4 * (nx + 4 * nu) * world,
                     "d2h_bytes_per_step": 4 * nu * world},
@@ -651,6 +659,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="strong (default): the named K sharded N ways - north_star's config 4; weak: every GPU plans the named K")
     ap.add_argument("--cpu-samples", type=int, default=8192, help="samples per CPU step when the whole K does not fit the time box")
+    ap.add_argument("--idle", type=float, default=1.0, help="seconds of idle before every timed region (equal power state for every number of the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config 1/2/3/5 extras (N = 1)")
     args = ap.parse_args()

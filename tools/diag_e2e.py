@@ -50,6 +50,14 @@ def main():
     st = _lib.current_stream_ptr()
     print("nlc_planner_command_host wall ms", wall(lambda: lib.nlc_planner_command_host(h, sp, bp, None, op, st)))
     print("nlc_planner_step         wall ms", wall(lambda: lib.nlc_planner_step(h, st)))
+    # the same measurements again in the opposite order: a difference between the rounds is the box (power cap, clocks), not the path
+    print("nlc_planner_command_host wall ms", wall(lambda: lib.nlc_planner_command_host(h, sp, bp, None, op, st)))
+    print("command(host buffers)   wall ms", wall(lambda: planner.command(inp["state"], inp["buffer"]).cpu()))
+    print("command(device tensors) wall ms", wall(lambda: planner.command(state_dev, buf_dev)))
+    time.sleep(2.0)
+    print("after 2 s idle: nlc_planner_step wall ms", wall(lambda: lib.nlc_planner_step(h, st)))
+    time.sleep(2.0)
+    print("after 2 s idle: command(host)    wall ms", wall(lambda: planner.command(inp["state"], inp["buffer"]).cpu()))
     t0 = time.perf_counter()
     for _ in range(200):
         planner._ensure(4)
