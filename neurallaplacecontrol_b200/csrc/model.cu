@@ -216,7 +216,7 @@ extern "C" int nlc_model_create(nlc_model_t* out, const nlc_model_desc* d, int d
   // group-uniform W3 image of the ping-pong rollout: 32 columns per unit, NX (S-1)/16 regular units + 1 unit of last terms
   const int gu_upc = (S - 1) % 16 == 0 ? (S - 1) / 16 : 0;
   const int gu_units = gu_upc ? nx * gu_upc + 1 : 0;
-  const int N3u = (Hm == 128 && gu_units >= 1 && gu_units <= 8) ? 32 * gu_units : 0;
+  const int N3u = (Hm == 128 && gu_units >= 1 && gu_units <= 13) ? 32 * gu_units : 0;  // <= 416 columns (rollout_tc2.cu kMaxN3)
   m->N3u = N3u;
   size_t o_m2w3u = A.add((size_t)2 * (N3u ? N3u : 16) * Hm / 2), o_m2cu = A.add(N3u ? N3u : 16);
 

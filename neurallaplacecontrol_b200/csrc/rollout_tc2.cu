@@ -119,12 +119,13 @@ __device__ __forceinline__ void load_weight_images(const ModelDev& m, unsigned c
   }
 }
 // Rows [row0, row0 + nrows) of W3 (output columns of the third layer; multiples of 8, so whole 8-row groups of the K-major
-// image = contiguous bytes), hi and lo image, into a buffer that holds n_buf rows of each.  Issued by one thread.
+// image = contiguous bytes), hi and lo image, into a buffer that holds n_buf rows of each.  Issued by one thread.  (The
+// streamed form is a one-tile form: the group-uniform image.)
 __device__ __forceinline__ void load_w3_rows(const ModelDev& m, unsigned char* w3_buf, int row0, int nrows, int N3t, int n_buf, uint64_t* bar) {
   const uint32_t bytes = (uint32_t)nrows * kH * 2;
   mbar_expect_tx(bar, 2 * bytes);
   for (int img = 0; img < 2; ++img) {
-    const unsigned char* src = static_cast<const unsigned char*>(m.mlp2_w3) + ((size_t)img * N3t + row0) * kH * 2;
+    const unsigned char* src = static_cast<const unsigned char*>(m.mlp2_w3u) + ((size_t)img * N3t + row0) * kH * 2;
     unsigned char* dst = w3_buf + (size_t)img * n_buf * kH * 2;
     for (uint32_t o = 0; o < bytes; o += 32768) bulk_g2s(dst + o, src + o, bytes - o < 32768 ? bytes - o : 32768, bar);
   }
@@ -389,9 +390,12 @@ __device__ __forceinline__ void ldtm8q(uint32_t taddr, f2_t (&v)[4]) {
 // epilogue (47 KB; a tenth of the warp stalls were instruction fetches).  Regular unit j < NX upc (upc = (S-1)/16): channel
 // j / upc (compile time), terms 16 (j % upc) + cg + 4 i; the last unit holds the terms k = S-1 of channels cg and cg + 4.
 // tDcg, b3cg, phasecg, weightcg: the D region / bias / Fourier tables offset by this thread's column group (8 cg, 8 cg, cg, cg).
-template <int NX, int S, int kJ0, int kJ1, bool kAccurate, int kRcp>
+// kPerRow: the sample's own prediction time (see l3_chunk) - k & 3 = cg for the regular units (their terms are cg + a multiple
+// of 4), 0 for the last (S - 1 is a multiple of 16).
+template <int NX, int S, int kJ0, int kJ1, bool kAccurate, int kRcp, bool kPerRow = false>
 __device__ __forceinline__ void l3_units_gu(uint32_t tDcg, const float* __restrict__ b3cg, const float* __restrict__ phasecg,
-                                            const float* __restrict__ weightcg, int cg, float (&delta)[NX]) {
+                                            const float* __restrict__ weightcg, int cg, float (&delta)[NX], float rd = 0.0f,
+                                            float rs = 0.0f) {
   constexpr int kUpc = (S - 1) / 16, kJ = NX * kUpc, kCount = kJ1 - kJ0;
   static_assert((S - 1) % 16 == 0 && kCount >= 1 && kCount <= 4 && kJ1 <= kJ + 1, "group-uniform units");
   f2_t v[kCount][4];
@@ -413,11 +417,18 @@ __device__ __forceinline__ void l3_units_gu(uint32_t tDcg, const float* __restri
       float t0, t1;
       if (j < kJ) {
         const int kb = 16 * (j % kUpc) + 4 * i;  // + cg: in the table pointers
-        l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phasecg[kb], phasecg[kb + 4], weightcg[kb], weightcg[kb + 4], t0, t1);
+        if constexpr (kPerRow) {
+          const float qcg = cg == 0 ? 0.0f : (cg == 1 ? 1.57079632679489662f : (cg == 2 ? 3.14159265358979f : -1.57079632679489662f));
+          const float kf = (float)(kb + cg);
+          l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), fmaf(-kf, rd, qcg), fmaf(-(kf + 4.0f), rd, qcg),
+                                        (kb == 0 && cg == 0) ? 0.5f * rs : rs, rs, t0, t1);
+        } else {
+          l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phasecg[kb], phasecg[kb + 4], weightcg[kb], weightcg[kb + 4], t0, t1);
+        }
         delta[j / kUpc] += t0;
         delta[j / kUpc] += t1;
       } else {
-        const float phl = phasecg[S - 1 - cg], wl = weightcg[S - 1 - cg];
+        const float phl = kPerRow ? -(float)(S - 1) * rd : phasecg[S - 1 - cg], wl = kPerRow ? rs : weightcg[S - 1 - cg];
         l3_two_pairs<kAccurate, kRcp>(pk2(th0, th1), pk2(ph0, ph1), phl, phl, wl, wl, t0, t1);
 #pragma unroll
         for (int c = 0; c < NX; ++c) delta[c] += (c == cg) ? t0 : ((c == cg + 4) ? t1 : 0.0f);
@@ -426,12 +437,34 @@ __device__ __forceinline__ void l3_units_gu(uint32_t tDcg, const float* __restri
   }
 }
 
+// units kJ0 .. kJ1 - 1, four at a time (32 accumulator registers in flight); kBase = the unit in column 0 of the D region
+template <int NX, int S, int kJ0, int kJ1, int kBase, bool kAccurate, int kRcp, bool kPerRow>
+struct L3GU {
+  static __device__ __forceinline__ void run(uint32_t tDcg, const float* b3cg, const float* phasecg, const float* weightcg, int cg,
+                                             float (&delta)[NX], float rd, float rs) {
+    if constexpr (kJ0 < kJ1) {
+      constexpr int kJm = kJ0 + 4 < kJ1 ? kJ0 + 4 : kJ1;
+      l3_units_gu<NX, S, kJ0, kJm, kAccurate, kRcp, kPerRow>(tDcg + 32 * (kJ0 - kBase), b3cg, phasecg, weightcg, cg, delta, rd, rs);
+      L3GU<NX, S, kJm, kJ1, kBase, kAccurate, kRcp, kPerRow>::run(tDcg, b3cg, phasecg, weightcg, cg, delta, rd, rs);
+    }
+  }
+};
+
+template <int NX, int S>
+struct PPShape {  // columns of the group-uniform W3 image: model.cu packs N3u = 32 (NX (S-1)/16 + 1)
+  static constexpr int kUnits = NX * ((S - 1) / 16) + 1, N3u = 32 * kUnits;
+};
+
 template <int NX, int S, bool kSplit3, int kRcp, int kTiles, bool kPerRow = false>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   static_assert(!kPerRow || kTiles == 1, "per-sample prediction times: one-tile form");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int Lp = NX + 2;
-  constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
+  // kGU (one tile): the (theta, phi) columns in the GROUP-UNIFORM order (l3_units_gu: one L3 epilogue code for all four column
+  // groups), counted in "chunks" of 16 columns like the natural order of the two-tile form - a unit is two chunks
+  constexpr bool kGU = kTiles == 1;
+  constexpr int kUnits = PPShape<NX, S>::kUnits;
+  constexpr int N3t = kGU ? PPShape<NX, S>::N3u : (2 * NX * S + 15) / 16 * 16;
   constexpr int kChunks = N3t / 16;
   // kTiles == 2: two 128-sample tiles per CTA, 8 warps and 256 TMEM columns each, two column groups per tile, L3 in two
   // column halves.  kTiles == 1 (plans of at most one wave of tiles, where the step latency is all that matters): one
@@ -444,14 +477,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   // buffer of N3a rows, reloaded by TMA bulk copies (L2-resident source) as soon as the product that read it has completed,
   // each load hidden under the epilogue that follows.
   constexpr bool kStream = kTiles == 1 && N3t > 256;
-  constexpr int kChunksA = ((kTiles == 1 && !kStream) || N3t <= 128) ? kChunks : (kChunks + 1) / 2;  // chunks in the first column half
+  constexpr int kUnitsA = kStream ? (kUnits + 1) / 2 : kUnits;        // (kGU) units in the first column half
+  constexpr int kChunksA = kGU ? 2 * kUnitsA : (N3t <= 128 ? kChunks : (kChunks + 1) / 2);  // chunks in the first column half
   constexpr int N3a = 16 * kChunksA, N3b = N3t - N3a;
   constexpr int N3buf = kStream ? N3a : N3t;                          // rows of W3 resident at a time
   // kSplitD (one tile, resident W3): the L3 product is issued as TWO products into disjoint column ranges of the accumulator,
   // each with its own completion barrier, so the epilogue of the first half's columns runs while the second half is still
   // on the tensor pipe - in this form nothing else covers the products (strict chain per sample)
   constexpr bool kSplitD = kTiles == 1 && !kStream && kChunks >= 8;
-  constexpr int kChunksH = kSplitD ? (kChunks + 1) / 2 : kChunks;     // chunks of the first product
+  constexpr int kUnitsH = kSplitD ? (kUnits + 1) / 2 : kUnits;        // (kGU) units of the first product
+  constexpr int kChunksH = kGU ? 2 * kUnitsH : kChunks;               // chunks of the first product
   constexpr int N3h = 16 * kChunksH;
   static_assert((kTiles == 1 ? (N3a <= 256 && N3b <= 256) : (N3a <= 128 && N3b <= 128 && N3t <= 256)) && N3t <= kMaxN3 && Lp + 1 <= 16, "tile shape");
   unsigned char* w1_img = smem_raw;                                   // [hi | lo] 128 x 16 halves = 4 KB each
@@ -467,11 +502,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
       mbar_init(&s.bar_w, 1);
       mbar_init(&s.bar_w3, 1);
       mbar_fence_init();
-      load_weight_images(a.m, w1_img, w2_img, w3_img, N3t, &s.bar_w, !kStream);
+      load_weight_images(a.m, w1_img, w2_img, w3_img, N3t, &s.bar_w, !kStream, kGU ? a.m.mlp2_w3u : a.m.mlp2_w3);
       if (kStream) load_w3_rows(a.m, w3_img, 0, N3a, N3t, N3buf, &s.bar_w3);
     }
     for (int i = tid; i < kH; i += kThreads) s.b2[i] = a.m.mlp2_c[i];
-    for (int i = tid; i < kMaxN3; i += kThreads) s.b3[i] = i < N3t ? a.m.mlp2_c[128 + i] : 0.0f;
+    for (int i = tid; i < kMaxN3; i += kThreads) s.b3[i] = i < N3t ? (kGU ? a.m.mlp2_cu[i] : a.m.mlp2_c[128 + i]) : 0.0f;
     for (int i = tid; i < S; i += kThreads) { s.phase[i] = a.m.ilt_phase[i]; s.weight[i] = a.m.ilt_weight[i]; }
     if (tid < NX) { s.smean[tid] = a.m.state_mean[tid]; s.sinv[tid] = a.m.state_inv_std[tid]; }
     if (tid == 0) {
@@ -659,29 +694,19 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         mark(5);
         // the first half's product has read the W3 buffer: the second half streams in under this epilogue
         if (kStream && wl == 0 && elect_one()) load_w3_rows(a.m, w3_img, N3a, N3b, N3t, N3buf, &s.bar_w3);
+        const uint32_t tDcg = tD + 8 * cg;
+        const float *b3cg = s.b3 + 8 * cg, *phcg = s.phase + cg, *wtcg = s.weight + cg;
         if constexpr (kSplitD) {
-          // this thread's chunks of the first product, then (after the second product's own barrier) of the second: the same
-          // chunks in the same order as the single-product form, so the sums are bit-identical
-          constexpr int kM = kChunksH % 4;
-          if (active) {
-            if (cg == 0) L3Loop<NX, S, 0, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-            else if (cg == 1) L3Loop<NX, S, 1, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-            else if (cg == 2) L3Loop<NX, S, 2, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-            else L3Loop<NX, S, 3, kChunksH, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-          }
+          // this thread's units of the first product, then (after the second product's own barrier) of the second
+          if (active) L3GU<NX, S, 0, kUnitsH, 0, kSplit3, kRcp % 10, kPerRow>::run(tDcg, b3cg, phcg, wtcg, cg, delta, rd, rs);
           mbar_wait_sleep(&s.done[1], n_b & 1); ++n_b;
           fence_after_sync();
-          if (active) {
-            if (cg == 0) L3Loop<NX, S, kChunksH + (4 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-            else if (cg == 1) L3Loop<NX, S, kChunksH + (5 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-            else if (cg == 2) L3Loop<NX, S, kChunksH + (6 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-            else L3Loop<NX, S, kChunksH + (7 - kM) % 4, kChunks, 0, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-          }
+          if (active) L3GU<NX, S, kUnitsH, kUnits, 0, kSplit3, kRcp % 10, kPerRow>::run(tDcg, b3cg, phcg, wtcg, cg, delta, rd, rs);
+        } else if constexpr (kGU) {
+          if (active) L3GU<NX, S, 0, kUnitsA, 0, kSplit3, kRcp % 10, kPerRow>::run(tDcg, b3cg, phcg, wtcg, cg, delta, rd, rs);
         } else if (active) {
           if (cg == 0) L3Loop<NX, S, 0, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-          else if (cg == 1) L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-          else if (kCG == 4 && cg == 2) L3Loop<NX, S, 2, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-          else if (kCG == 4) L3Loop<NX, S, 3, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+          else L3Loop<NX, S, 1, kChunksA, 0, kSplit3, kRcp % 10, kCG, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
         }
         if (N3b > 0) {
           mark(6);
@@ -691,11 +716,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
           // ... and the first half again for the next step (or the next tile), under this epilogue and the next step's E1 / E2
           if (kStream && wl == 0 && elect_one()) load_w3_rows(a.m, w3_img, 0, N3a, N3t, N3buf, &s.bar_w3);
           if (active) {
-            if constexpr (kCG == 4) {  // four column groups take the second half's chunks round-robin
-              if (cg == 0) L3Loop<NX, S, kChunksA, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-              else if (cg == 1) L3Loop<NX, S, kChunksA + 1, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-              else if (cg == 2) L3Loop<NX, S, kChunksA + 2, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
-              else L3Loop<NX, S, kChunksA + 3, kChunks, kChunksA, kSplit3, kRcp % 10, 4, kPerRow>::run(tD, s.b3, s.phase, s.weight, delta, rd, rs);
+            if constexpr (kGU) {  // (streamed W3) the second half's units, now in column 0.. of the D region
+              L3GU<NX, S, kUnitsA, kUnits, kUnitsA, kSplit3, kRcp % 10, kPerRow>::run(tDcg, b3cg, phcg, wtcg, cg, delta, rd, rs);
             } else {
               constexpr int kFirstB0 = kChunksA + (kChunksA & 1);        // first chunk >= kChunksA with even index
               constexpr int kFirstB1 = kChunksA + 1 - (kChunksA & 1);    // ... with odd index
@@ -771,10 +793,6 @@ struct SmemTailPP {
   alignas(8) float stage_u[2][2][kRows][2];  // ... and the action this step applies (running cost): [step parity][tile][sample]
   alignas(8) uint64_t done[2];
   uint32_t tmem_base;
-};
-template <int NX, int S>
-struct PPShape {  // columns of the group-uniform W3 image: model.cu packs N3u = 32 (NX (S-1)/16 + 1)
-  static constexpr int kUnits = NX * ((S - 1) / 16) + 1, N3u = 32 * kUnits;
 };
 constexpr int kThreadsPP = kThreads + 128;    // 16 epilogue warps + the MMA warp's group (setmaxnreg works on groups of 4 warps)
 
@@ -1131,8 +1149,9 @@ static int launch_pp(const Args& a, cudaStream_t stream) {
 
 template <int NX, int S, bool kSplit3, int kRcp, int kTiles, bool kPerRow = false>
 static int launch_one_t(const Args& a, cudaStream_t stream) {
-  constexpr int N3t = (2 * NX * S + 15) / 16 * 16;
-  constexpr int N3buf = (kTiles == 1 && N3t > 256) ? 16 * ((N3t / 16 + 1) / 2) : N3t;  // streamed W3: one half resident
+  constexpr int kUnits = PPShape<NX, S>::kUnits;
+  constexpr int N3t = kTiles == 1 ? PPShape<NX, S>::N3u : (2 * NX * S + 15) / 16 * 16;
+  constexpr int N3buf = (kTiles == 1 && N3t > 256) ? 32 * ((kUnits + 1) / 2) : N3t;  // streamed W3: one half resident
   const size_t smem = 2 * (size_t)kH * 16 * 2 + 2 * (size_t)kH * kH * 2 + 2 * (size_t)N3buf * kH * 2 + sizeof(SmemTail) + 128;
   NLC_REQUIRE(smem <= 227 * 1024, NLC_ERR_SHAPE, "tcgen05 rollout: %zu bytes of shared memory needed", smem);
   auto kern = rollout_tc2_kernel<NX, S, kSplit3, kRcp, kTiles, kPerRow>;
@@ -1182,7 +1201,7 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   a.row_b1 = row_b1; a.row_tn = row_tn;
   NLC_REQUIRE(!row_b1 || (row_tn && split3 && !ready), NLC_ERR_ARG, "rollout: per-sample times need row_tn and the fp32-class tensor-core mode");
   if (2 * m->nx * m->S > 256) tiles_per_cta = 1;
-  NLC_REQUIRE(tiles_per_cta != 3 || m->N3u == 32 * (m->nx * ((m->S - 1) / 16) + 1), NLC_ERR_SHAPE,
+  NLC_REQUIRE(tiles_per_cta == 2 || m->N3u == 32 * (m->nx * ((m->S - 1) / 16) + 1), NLC_ERR_SHAPE,
               "tcgen05 rollout: the model holds no group-uniform W3 image for nx=%d S=%d", m->nx, m->S);
   NLC_REQUIRE(!ready || (tiles_per_cta == 1 && (K + 127) / 128 <= 148 && status), NLC_ERR_ARG,
               "rollout: the overlapped form is the one-tile form of plans within one wave");
