@@ -66,6 +66,7 @@ bool encoder_is_tensor_core(nlc_model_t m, int B, int math_mode);
 int encode_history_overlapped(nlc_model_t m, const float* hist_dev, int K, int T, int B, float* p_dev, int math_mode,
                               unsigned int* ready, int max_ctas, long long tile_begin, long long tile_end, cudaStream_t s);
 bool rollout_can_overlap(const nlc_model_s* m, int K, int T, int math_mode);
+bool rollout_overlap_is_ping_pong(const nlc_model_s* m, int K);
 int launch_rollout_overlapped(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p, const float* hist,
                               const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states, int math_mode,
                               const unsigned int* ready, unsigned int ready_target, unsigned int* status, cudaStream_t stream);
@@ -345,22 +346,29 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
     // tool that serialises kernels then runs it to completion before the rollout starts polling.
     const int n_tiles = (mp.K + 127) / 128;
     // (the readiness counters were zeroed by the previous step's combine kernel)
-    // Beyond half a wave of tiles the rollout leaves the encoder too few SMs to keep ahead of it for the whole horizon: the
-    // first steps' windows are encoded on all SMs BEFORE the fork, and only as many of the last steps as the spare SMs can
-    // encode during the rollout (12.6 us per tile and SM, ~9.5 us per rollout step: measured at config 4 / its shards; a
-    // wrong estimate only makes the rollout poll a little longer) run beside it.
+    // The rollout takes n_tiles SMs (one tile per CTA, ~9.5 us per step) or, from 89 tiles, n_tiles / 2 (ping-pong form, ~13.3 us
+    // per step): the encoder has the other SMs for the rollout's duration.  What those cannot encode in that time (12.6 us per
+    // tile and SM: measured at config 4 / its shards; a wrong estimate only makes the rollout poll a little longer) is encoded
+    // on all SMs BEFORE the fork - the windows of the first steps, the encoder walking its tiles in step-major order.
+    const bool pp = rollout_overlap_is_ping_pong(p->model, mp.K);
+    const int roll_sms = pp ? (n_tiles + 1) / 2 : n_tiles;
     long long split = 0;  // first tile of the part that runs beside the rollout
-    if (n_tiles > 74) {
-      const double spare_tiles = 0.85 * (148 - n_tiles) * (mp.T * 9.5) / 12.6;
-      long long beside_steps = (long long)(spare_tiles / n_tiles);
-      if (beside_steps > mp.T - 1) beside_steps = mp.T - 1;
+    {
+      static const double factor = [] { const char* e = getenv("NLC_OVERLAP_FACTOR"); return e && e[0] ? atof(e) : 0.9; }();  // measurements
+      const double beside_tiles = factor * (148 - roll_sms) * (mp.T * (pp ? 13.3 : 9.5)) / 12.6;
+      long long beside_steps = (long long)(beside_tiles / n_tiles);
+      if (beside_steps > mp.T) beside_steps = mp.T;
+      if (n_tiles <= 74) beside_steps = mp.T;  // at least half the SMs for the whole step: everything beside the rollout
+      if (beside_steps < 1) beside_steps = 1;
       split = (long long)(mp.T - beside_steps) * n_tiles;
+    }
+    if (split > 0) {
       rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148, 0, split, s);
       if (rc != NLC_OK) return rc;
     }
     NLC_CUDA_OK(cudaEventRecord(p->ev_fork, s));
     NLC_CUDA_OK(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
-    rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148 - n_tiles, split, 0, s);
+    rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148 - roll_sms, split, 0, s);
     if (rc != NLC_OK) return rc;
     if (ev) NLC_CUDA_OK(cudaEventRecord(ev[2], s));  // profile: end of the encoder's own span
     rc = launch_rollout_overlapped(p->model, &p->d.rollout, state_dev, state_per_sample, p->p, p->hist, p->pert_cost, mp.K, mp.T, mp.B,

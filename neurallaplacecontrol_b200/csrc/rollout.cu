@@ -283,15 +283,29 @@ bool rollout_has_tensor_core_form(const nlc_model_s* m);
 bool rollout_can_overlap(const nlc_model_s* m, int K, int T, int math_mode) {
   static const bool off = [] { const char* e = getenv("NLC_NO_OVERLAP"); return e && e[0] == '1'; }();
   const char* f = getenv("NLC_ROLLOUT_TILES");  // a forced kernel form (parity tests) keeps the plain sequence
-  // up to 74 tiles the encoder keeps at least half the SMs for the whole step; up to 140 the planner runs most of the encoder
-  // first and only its tail beside the rollout (planner.cu)
-  return !off && !(f && f[0]) && math_mode != NLC_MATH_FP32 && rollout_has_tensor_core_form(m) && T >= 2 && (K + 127) / 128 <= 140;
+  // up to 74 tiles the encoder keeps at least half the SMs for the whole step; beyond, the planner runs the first part of the
+  // encoder alone and the rest beside the rollout (planner.cu); beyond 280 tiles the ping-pong rollout leaves it < 8 SMs
+  const int n_tiles = (K + 127) / 128;
+  const bool pp_form = 2 * m->nx * m->S <= 256;  // shapes with a ping-pong instantiation (rollout_tc2.cu launch_one)
+  return !off && !(f && f[0]) && math_mode != NLC_MATH_FP32 && rollout_has_tensor_core_form(m) && T >= 2 &&
+         n_tiles <= (pp_form ? 280 : 140);
+}
+// The overlapped rollout's form: one tile per CTA on n_tiles SMs (9.5 us per step), or - from 89 tiles - the ping-pong form on
+// n_tiles / 2 SMs (13.3 us per step of a tile pair), which leaves the encoder 148 - n_tiles / 2 SMs for the whole rollout.
+// Model (12.6 us per encoder tile and SM, T = 50): 128 tiles 0.96 -> 0.83 ms, 100 tiles 0.75 -> 0.66 ms, 75 tiles 0.56 (one tile).
+bool rollout_overlap_is_ping_pong(const nlc_model_s* m, int K) {
+  const int n_tiles = (K + 127) / 128;
+  static const int forced = [] { const char* e = getenv("NLC_OVERLAP_FORM"); return e && e[0] ? e[0] - '0' : 0; }();  // measurements
+  if (2 * m->nx * m->S > 256) return false;
+  if (forced == 1 && n_tiles <= 140) return false;
+  if (forced == 3) return true;
+  return n_tiles >= 89;
 }
 int launch_rollout_overlapped(nlc_model_s* m, const nlc_rollout_opts* o, const float* state, int sps, const float* p, const float* hist,
                               const float* pert_cost, int K, int T, int B, int nu, float* cost, float* states, int math_mode,
                               const unsigned int* ready, unsigned int ready_target, unsigned int* status, cudaStream_t stream) {
-  return launch_rollout_tc2(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, nullptr, math_mode == NLC_MATH_TC_SPLIT3, 1,
-                            stream, ready, ready_target, status);
+  return launch_rollout_tc2(m, o, state, sps, p, hist, pert_cost, K, T, B, nu, cost, states, nullptr, math_mode == NLC_MATH_TC_SPLIT3,
+                            rollout_overlap_is_ping_pong(m, K) ? 3 : 1, stream, ready, ready_target, status);
 }
 
 // math_mode dispatch: the tensor-core kernel when it has an instantiation for (nx, S), else the FFMA kernel

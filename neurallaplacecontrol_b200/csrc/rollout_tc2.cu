@@ -936,7 +936,11 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
 #pragma unroll
       for (int c = 0; c < NX; ++c) { if (x == 0) st0[c] = sp[c]; else st1[c] = sp[c]; }
       if (x == 0) kk0 = k; else kk1 = k;
-      if (cg == 2) *reinterpret_cast<float2*>(&s.stage_p[x][row][0]) = *reinterpret_cast<const float2*>(a.p + ((size_t)k * a.T) * 2);
+      if (cg == 2) {
+        // (overlapped step: p is being written by the encoder beside this kernel - wait for step 0's windows, read through L2)
+        if (a.ready) wait_windows_ready(a, 0, lane);
+        *reinterpret_cast<float2*>(&s.stage_p[x][row][0]) = __ldcg(reinterpret_cast<const float2*>(a.p + ((size_t)k * a.T) * 2));
+      }
     }
     // A1 = [obs_n | p_action | 1 | 0..] as the K = 16 operand of the first layer (one thread per sample: column group 2);
     // p_action comes from this thread's own stage_p slot
@@ -1036,10 +1040,19 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
       // the running cost (column group 3) - start their way now as cp.async copies into per-sample shared-memory slots:
       // no registers held across the step (held in registers they were spilled right after the load, and the spill
       // store stalled the warp on the load at the top of every step)
+      // Overlapped step (a.ready: the encoder runs beside this kernel and publishes its windows step by step): the 128-byte line
+      // of p(k, t+1) also holds later steps that are not written yet, so it must not pass through L1 - ld.global.cg into two
+      // registers per tile once step t+1 is published, stored into the landing slot before the exchange barrier below.
+      float2 pn0 = make_float2(0.f, 0.f), pn1 = make_float2(0.f, 0.f);
+      if (a.ready && cg == 2 && t + 1 < a.T) {
+        wait_windows_ready(a, t + 1, lane);
+        pn0 = __ldcg(reinterpret_cast<const float2*>(a.p + ((size_t)kk0 * a.T + t + 1) * 2));
+        pn1 = __ldcg(reinterpret_cast<const float2*>(a.p + ((size_t)kk1 * a.T + t + 1) * 2));
+      }
 #pragma unroll 1
       for (int x = 0; x < 2; ++x) {
         const int kx = x ? kk1 : kk0;
-        if (cg == 2 && t + 1 < a.T)
+        if (!a.ready && cg == 2 && t + 1 < a.T)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s.stage_p[x][row][0])), "l"(a.p + ((size_t)kx * a.T + t + 1) * 2) : "memory");
         if (cg == 3 && ((lmask >> x) & 1) && a.cost_total) {
           const float* up = a.hist + ((size_t)kx * a.L + t + a.B - 1) * a.nu;
@@ -1084,6 +1097,10 @@ __global__ void __launch_bounds__(kThreadsPP, 1) rollout_pp_kernel(Args a) {
         ++nphase;
       }
       mark(15);
+      if (a.ready && cg == 2 && t + 1 < a.T) {
+        *reinterpret_cast<float2*>(&s.stage_p[0][row][0]) = pn0;
+        *reinterpret_cast<float2*>(&s.stage_p[1][row][0]) = pn1;
+      }
       asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's own copies: it reads only its own slots
       // ONE barrier among the four warps of a row quarter covers the partial sums of both tiles (tile 1's were written last)
       asm volatile("bar.sync %0, %1;" ::"r"(5 + q), "n"(128) : "memory");
@@ -1142,6 +1159,8 @@ static int launch_pp(const Args& a, cudaStream_t stream) {
   NLC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (a.K + 63) / 64;   // at least one warp of samples per tile slot, at most one CTA per SM
   if (grid > 148) grid = 148;
+  // overlapped planner step: whole 128-sample tiles, two per CTA, on as few SMs as possible - the encoder runs on the others
+  if (a.ready) grid = ((a.K + kRows - 1) / kRows + 1) / 2;
   kern<<<grid, kThreadsPP, smem, stream>>>(a);
   NLC_LAUNCH_OK("rollout_pp_kernel");
   return NLC_OK;
@@ -1203,8 +1222,8 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   if (2 * m->nx * m->S > 256) tiles_per_cta = 1;
   NLC_REQUIRE(tiles_per_cta == 2 || m->N3u == 32 * (m->nx * ((m->S - 1) / 16) + 1), NLC_ERR_SHAPE,
               "tcgen05 rollout: the model holds no group-uniform W3 image for nx=%d S=%d", m->nx, m->S);
-  NLC_REQUIRE(!ready || (tiles_per_cta == 1 && (K + 127) / 128 <= 148 && status), NLC_ERR_ARG,
-              "rollout: the overlapped form is the one-tile form of plans within one wave");
+  NLC_REQUIRE(!ready || (status && ((tiles_per_cta == 1 && (K + 127) / 128 <= 148) || (tiles_per_cta == 3 && (K + 127) / 128 <= 296))), NLC_ERR_ARG,
+              "rollout: the overlapped forms are the one-tile form of plans within one wave and the ping-pong form within two");
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
   a.trace = g_roll_trace;

@@ -505,13 +505,15 @@ def test_non_finite_weights_are_rejected():
 
 
 @pytest.mark.parametrize("env,K,T", [("oderl-cartpole", 8192, 30), ("oderl-pendulum", 1000, 20), ("oderl-acrobot", 8192, 50), ("oderl-acrobot", 333, 7),
-                                     ("oderl-acrobot", 16384, 50), ("oderl-cartpole", 12001, 9), ("oderl-pendulum", 17900, 3)])
+                                     ("oderl-acrobot", 11000, 12), ("oderl-acrobot", 16384, 50), ("oderl-cartpole", 12001, 9),
+                                     ("oderl-pendulum", 17900, 3), ("oderl-acrobot", 32768, 50), ("oderl-cartpole", 20011, 6)])
 def test_overlapped_step_equals_sequential_step(env, K, T, monkeypatch):
-    """Plans within one wave of tiles run the encoder beside the rollout (step-major encoder order, per-step readiness
-    counters; beyond half a wave only the encoder's tail runs beside it - the last three cases): same kernels, same
-    per-sample arithmetic - bit-identical costs, states and U as the plain sequence
-    (NLC_NO_OVERLAP is latched per process, so the plain sequence is reached by forcing the one-tile rollout form, which the
-    overlap logic treats as a request for the plain launch order)."""
+    """Plans within two waves of tiles run the encoder beside the rollout (step-major encoder order, per-step readiness
+    counters): up to 74 tiles all of it, beyond that the first steps' windows are encoded on all SMs first (cases 5-10); from
+    89 tiles the rollout is the ping-pong form on half as many SMs (cases 6-10, the last two beyond one wave).  Same
+    kernels, same per-sample arithmetic - bit-identical costs, states and U as the plain sequence (NLC_NO_OVERLAP is latched
+    per process, so the plain sequence is reached by forcing the rollout form the overlapped step uses, which the overlap
+    logic treats as a request for the plain launch order)."""
     from oracle import costs
     from _util import START_STATE
 
@@ -519,7 +521,7 @@ def test_overlapped_step_equals_sequential_step(env, K, T, monkeypatch):
     res = {}
     for name in ("overlap", "plain"):
         if name == "plain":
-            monkeypatch.setenv("NLC_ROLLOUT_TILES", "1")
+            monkeypatch.setenv("NLC_ROLLOUT_TILES", "3" if (K + 127) // 128 >= 89 else "1")
         m = make_model(env, calibrated=True, math_mode="tc_split3")
         p = make_planner(env, m, K, T, np.zeros((T, nu)), math_mode="tc_split3", seed=5)
         acts = []
