@@ -442,7 +442,7 @@ def sharded_vs_unsharded(ctx, env, K, H):
         # the whole plan through the same rollout kernel form as the shards (a 65536-sample plan would pick the ping-pong
         # form on its own: same arithmetic, other summation order), so that per-sample costs are bit-identical and the
         # comparison isolates what sharding changes: the order of stage 4's sums
-        pp_shard = (sharded.K_local + 127) // 128 > N_SM
+        pp_shard = (sharded.K_local + 127) // 128 >= 89  # (the overlapped step's own choice: rollout.cu rollout_overlap_is_ping_pong)
         os.environ["NLC_ROLLOUT_TILES"] = "3" if pp_shard else "1"
         _, _, whole = make_planner(ctx, env, K, H, group=None, seed=99)
         a1 = whole.command(state_dev, buf_dev).double()
