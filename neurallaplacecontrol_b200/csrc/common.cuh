@@ -138,6 +138,12 @@ constexpr int kE2Wout = 512 + 3 * kMaxNu * 64;  // [2][64]
 constexpr int kE2Bout = kE2Wout + 128;          // [2]
 constexpr int kE2Count = kE2Bout + 8;
 
+// Overlapped planner step, ping-pong rollout (rollout_tc2.cu, planner.cu): CTAs and passes ("iterations" of two tiles per CTA) for
+// n_tiles whole 128-sample tiles - as many passes as 148 CTAs would need, on as few CTAs as that number of passes allows;
+// the encoder runs on the other SMs for the rollout's duration.
+inline int pp_overlap_iters(int n_tiles) { return (n_tiles + 295) / 296; }
+inline int pp_overlap_grid(int n_tiles) { const int it = pp_overlap_iters(n_tiles); return (n_tiles + 2 * it - 1) / (2 * it); }
+
 struct ModelHost {  // fp64 copies kept for re-folding at another prediction time
   double* w0 = nullptr;  // [Hm][2S+nx+2]
   double* b0 = nullptr;  // [Hm]

@@ -351,11 +351,11 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
     // tile and SM: measured at config 4 / its shards; a wrong estimate only makes the rollout poll a little longer) is encoded
     // on all SMs BEFORE the fork - the windows of the first steps, the encoder walking its tiles in step-major order.
     const bool pp = rollout_overlap_is_ping_pong(p->model, mp.K);
-    const int roll_sms = pp ? (n_tiles + 1) / 2 : n_tiles;
+    const int roll_sms = pp ? pp_overlap_grid(n_tiles) : n_tiles;
     long long split = 0;  // first tile of the part that runs beside the rollout
     {
       static const double factor = [] { const char* e = getenv("NLC_OVERLAP_FACTOR"); return e && e[0] ? atof(e) : 0.9; }();  // measurements
-      const double beside_tiles = factor * (148 - roll_sms) * (mp.T * (pp ? 13.3 : 9.5)) / 12.6;
+      const double beside_tiles = factor * (148 - roll_sms) * (mp.T * (pp ? 13.3 * pp_overlap_iters(n_tiles) : 9.5)) / 12.6;
       long long beside_steps = (long long)(beside_tiles / n_tiles);
       if (beside_steps > mp.T) beside_steps = mp.T;
       if (n_tiles <= 74) beside_steps = mp.T;  // at least half the SMs for the whole step: everything beside the rollout

@@ -1160,7 +1160,7 @@ static int launch_pp(const Args& a, cudaStream_t stream) {
   int grid = (a.K + 63) / 64;   // at least one warp of samples per tile slot, at most one CTA per SM
   if (grid > 148) grid = 148;
   // overlapped planner step: whole 128-sample tiles, two per CTA, on as few SMs as possible - the encoder runs on the others
-  if (a.ready) grid = ((a.K + kRows - 1) / kRows + 1) / 2;
+  if (a.ready) grid = pp_overlap_grid((a.K + kRows - 1) / kRows);
   kern<<<grid, kThreadsPP, smem, stream>>>(a);
   NLC_LAUNCH_OK("rollout_pp_kernel");
   return NLC_OK;
@@ -1222,8 +1222,8 @@ int launch_rollout_tc2(nlc_model_s* m, const nlc_rollout_opts* o, const float* s
   if (2 * m->nx * m->S > 256) tiles_per_cta = 1;
   NLC_REQUIRE(tiles_per_cta == 2 || m->N3u == 32 * (m->nx * ((m->S - 1) / 16) + 1), NLC_ERR_SHAPE,
               "tcgen05 rollout: the model holds no group-uniform W3 image for nx=%d S=%d", m->nx, m->S);
-  NLC_REQUIRE(!ready || (status && ((tiles_per_cta == 1 && (K + 127) / 128 <= 148) || (tiles_per_cta == 3 && (K + 127) / 128 <= 296))), NLC_ERR_ARG,
-              "rollout: the overlapped forms are the one-tile form of plans within one wave and the ping-pong form within two");
+  NLC_REQUIRE(!ready || (status && ((tiles_per_cta == 1 && (K + 127) / 128 <= 148) || tiles_per_cta == 3)), NLC_ERR_ARG,
+              "rollout: the overlapped forms are the one-tile form of plans within one wave and the ping-pong form");
   a.m = m->d; a.o = *o; a.state0 = state; a.state_per_sample = sps; a.p = p; a.hist = hist; a.pert_cost = pert_cost;
   a.K = K; a.T = T; a.B = B; a.L = B - 1 + T; a.nu = nu; a.cost_total = cost; a.states = states; a.delta_out = delta_out;
   a.trace = g_roll_trace;
