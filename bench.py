@@ -307,10 +307,10 @@ def make_planner(ctx, env, K, H, group=None, seed=1234, math=None, S=None, **kw)
     return inp, model, planner
 
 
-def time_plan(ctx, env, K, H, group, steps, warmup, S=None):
+def time_plan(ctx, env, K, H, group, steps, warmup, S=None, math=None):
     """Device-timed and end-to-end control step of one workload; returns a dict and the live objects."""
     torch = ctx.torch
-    inp, model, planner = make_planner(ctx, env, K, H, group=group, S=S)
+    inp, model, planner = make_planner(ctx, env, K, H, group=group, S=S, math=math)
     state_dev = torch.tensor(inp["state"], dtype=torch.float64, device=ctx.dev)
     buf_dev = inp["buffer"].to(ctx.dev)
     # `value`: the control step on inputs already resident in the planner's device buffers - one graph launch per step
@@ -465,11 +465,20 @@ def sharded_vs_unsharded(ctx, env, K, H):
 
 
 # ---- extras (N = 1): the other BASELINE configs -------------------------------------------------------------------------
-def extra_plan(ctx, name, peaks, S=None):
+def extra_plan(ctx, name, peaks, S=None, math=None):
     env, K, H, desc = WORKLOADS[name]
-    r = time_plan(ctx, env, K, H, None, max(5, ctx.args.steps), 3, S=S)
+    r = time_plan(ctx, env, K, H, None, max(5, ctx.args.steps), 3, S=S, math=math)
     tiles = (K + 127) // 128
     split = in_step_split(ctx, r, ctx.args.steps)
+    if math is not None:
+        # the single-pass fp16 tensor-core mode: ONE MMA per product and tanh.approx gates - north_star's "stated looser bound"
+        # path (tests/test_gpu_parity.py::test_full_size_plan_fp16_mode_stated_bound: 5e-2 over the whole horizon, measured 1-3e-2
+        # on trajectories and U at this shape, against 1e-4 / ~1e-5 for the default fp32-class mode)
+        flop = HOISTED_FLOP[env] * K * H
+        return {"workload": f"{desc}, math={math} (looser stated bound: 5e-2 over the horizon, measured 1-3e-2; the default mode holds 1e-4)", "in_step": split,
+                "ms_per_step": r["ms_dev"], "plan_latency_ms_e2e": r["ms_e2e"], "value": K * H / (r["ms_dev"] * 1e-3),
+                "e2e_value": K * H / (r["ms_e2e"] * 1e-3), "unit": UNIT, "math": math,
+                "frac_of_sustained_peak": flop / (r["ms_dev"] * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]}
     if S is not None:
         # the reference CLASS default number of Fourier terms (w_nl.py:73; config.py runs S = 17): 396 (theta, phi) columns for the
         # acrobot - the one-tile rollout with L3 in two column halves and W3 streamed half by half by TMA, whatever the plan size
@@ -651,7 +660,8 @@ def run_gpu(args, env, K, H, desc):
         peaks = load_peaks()
         extra = []
         for fn in (lambda: extra_plan(ctx, "cfg3", peaks), lambda: extra_plan(ctx, "cfg1", peaks), lambda: extra_cfg5(ctx),
-                   lambda: extra_ilt(ctx, peaks), lambda: extra_plan(ctx, "cfg4", peaks, S=33)):
+                   lambda: extra_ilt(ctx, peaks), lambda: extra_plan(ctx, "cfg4", peaks, S=33)) + \
+                  (() if args.math == "tc_fp16" else (lambda: extra_plan(ctx, "cfg4", peaks, math="tc_fp16"),)):
             try:
                 extra.append(fn())
             except Exception as exc:  # an extra must never take the headline line down
