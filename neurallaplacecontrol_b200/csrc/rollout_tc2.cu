@@ -373,8 +373,8 @@ struct L3Loop {
   }
 };
 
-// Ping-pong form: the (theta, phi) columns are dealt in UNITS of 8 columns (4 pairs), and all of a thread's units of a phase
-// are loaded before the first is used (one TMEM round trip per phase instead of one per chunk).
+// Ping-pong and one-tile forms: a thread reads its (theta, phi) columns in UNITS of 8 columns (4 pairs), and all of its units of
+// a phase (up to four) are loaded before the first is used - one TMEM round trip per phase instead of one per chunk.
 __device__ __forceinline__ void ldtm8q(uint32_t taddr, f2_t (&v)[4]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -468,7 +468,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   constexpr int kChunks = N3t / 16;
   // kTiles == 2: two 128-sample tiles per CTA, 8 warps and 256 TMEM columns each, two column groups per tile, L3 in two
   // column halves.  kTiles == 1 (plans of at most one wave of tiles, where the step latency is all that matters): one
-  // tile, all 16 warps on it in four column groups, L3 in one piece (A 128 + D up to 256 columns).
+  // tile, all 16 warps on it in four column groups, L3 in one piece (A 128 + D up to 256 columns), (theta, phi) columns in
+  // the group-uniform order.
   constexpr int kCG = 4 / kTiles;                                   // column groups per tile
   constexpr int kGroupWarps = 4 * kCG, kGroupT = 32 * kGroupWarps;  // warps / threads per tile
   constexpr int kColsPerThread = kH / kCG, kC16 = kColsPerThread / 16;
@@ -778,9 +779,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
 //              for the epilogue warps, 32 for the MMA warp's group (whose issue code is a non-inlined, fully unrolled
 //              function so that it fits that budget).
 //   threads    warp w: TMEM lanes 32 (w & 3).. (its 32 samples of BOTH tiles), column group w >> 2 (32 of the 128 hidden
-//              units; units u = cg (mod 4) of the (theta, phi) columns, 8 columns each).  The state of a sample is replicated in its four
+//              units; of every 32-column unit of the group-uniform (theta, phi) order, columns 8 cg .. 8 cg + 7).  The state of a sample is replicated in its four
 //              threads; partial ILT sums are exchanged through shared memory among the four warps of a row quarter.
-//   L3         first half N3a = min(N3t, 128) columns, second half the rest (<= 128): A 128 + D 128 columns per tile.
+//   L3         first half = the first four units (128 columns), second half the rest (<= 128): A 128 + D 128 columns per tile.
+//   rows       a CTA owns one contiguous row range and walks it 256 rows (two tiles) per pass; a tile without rows in a pass
+//              keeps its hand-offs (the MMA warp's product sequence is fixed) but skips every epilogue.
 template <int NX>
 struct SmemTailPP {
   alignas(8) uint64_t bar_w;
