@@ -237,6 +237,23 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, 
   }
 }
 
+// Every second K-step of the same product (kHalf = 0: steps 0, 2, ..; 1: steps 1, 3, ..): the one-tile form issues a layer's
+// product in two halves, the first as soon as the first 16 of every thread's 32 activation columns are in TMEM, so that half
+// of the product runs under the second half of the epilogue that feeds it (strict chain per sample: nothing else covers it).
+template <bool kSplit3>
+__device__ __forceinline__ void issue_gemm_ts_half(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, int N, int ksteps, uint32_t sbo,
+                                                   int half) {
+  const uint32_t idesc = idesc_f16_f32(kRows, N);
+  for (int ks = half; ks < ksteps; ks += 2) {
+    const uint32_t boff = ks * 2 * kLbo;
+    mma_f16_ts(d_tmem, a_tmem + 8 * ks, smem_desc(b_hi + boff, kLbo, sbo), idesc, ks > 0 ? 1u : 0u);
+    if (kSplit3) {
+      mma_f16_ts(d_tmem, a_tmem + 64 + 8 * ks, smem_desc(b_hi + boff, kLbo, sbo), idesc, 1u);
+      mma_f16_ts(d_tmem, a_tmem + 8 * ks, smem_desc(b_lo + boff, kLbo, sbo), idesc, 1u);
+    }
+  }
+}
+
 // The same product for a warp that lives on 32 registers (the ping-pong form's MMA warp after setmaxnreg.dec).  Not
 // inlined, so that the compiler cannot hoist the descriptors of every product of the step loop into registers (inlined,
 // that spilled 246 words under the small budget); inside, fully unrolled with the descriptors advanced by immediates
@@ -486,6 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
   // each with its own completion barrier, so the epilogue of the first half's columns runs while the second half is still
   // on the tensor pipe - in this form nothing else covers the products (strict chain per sample)
   constexpr bool kSplitD = kTiles == 1 && !kStream && kChunks >= 8;
+  constexpr bool kSplitK = kTiles == 1;                               // M2 / M3 issued in two K-halves (hidden_split)
   constexpr int kUnitsH = kSplitD ? (kUnits + 1) / 2 : kUnits;        // (kGU) units of the first product
   constexpr int kChunksH = kGU ? 2 * kUnitsH : kChunks;               // chunks of the first product
   constexpr int N3h = 16 * kChunksH;
@@ -543,6 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
     const uint32_t w3_hi = smem_u32(w3_img), w3_lo = w3_hi + (uint32_t)N3buf * kH * 2;
     const uint32_t w3b_off = kStream ? 0u : (uint32_t)(N3a / 8) * kSbo;
     uint32_t n = 0, n_w3 = 0, n_b = 0;  // products waited for; W3 halves waited for (issuing warp only); second L3 halves (kSplitD)
+    bool active_w = false;              // (hidden_split) this warp has live samples in the current tile
     int tstep = 0;
     auto mark = [&](int ev) {
       if (a.trace && blockIdx.x == 0 && lane == 0 && tstep < 104) a.trace[(tstep * 16 + warp) * 8 + ev] = clock64();
@@ -573,9 +592,74 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
       }
       __syncwarp();
     };
+    // kSplitK (one tile, four column groups): products M2 and M3 in two K-halves (issue_gemm_ts_half).  half 0 = the K-steps
+    // fed by every thread's first 16 activation columns (even steps: thread columns 32 cg .. 32 cg + 15 are K-step 2 cg),
+    // half 1 = the rest and the commit(s).
+    auto issue_k = [&](int ev, int half) {
+      tmem_st_wait();
+      fence_before_sync();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGroupT) : "memory");
+      if (kStream && wl == 0 && ev >= 2 && half == 0) { mbar_wait(&s.bar_w3, n_w3 & 1); ++n_w3; }  // this half of W3 has landed
+      if (wl == 0 && elect_one()) {
+        fence_after_sync();
+        if (ev == 1) issue_gemm_ts_half<kSplit3>(tg + kColD, tg + kColA, w2_hi, w2_lo, kH, kH / 16, kSbo, half);
+        else if (kSplitD) {
+          issue_gemm_ts_half<kSplit3>(tg + kColD, tg + kColA, w3_hi, w3_lo, N3h, kH / 16, kSbo, half);
+          if (half == 1) mma_commit(done);  // first column half: the epilogue starts on it while the second half computes
+          issue_gemm_ts_half<kSplit3>(tg + kColD + N3h, tg + kColA, w3_hi + (uint32_t)(N3h / 8) * kSbo, w3_lo + (uint32_t)(N3h / 8) * kSbo,
+                                      N3t - N3h, kH / 16, kSbo, half);
+          if (half == 1) mma_commit(&s.done[1]);
+        } else {
+          issue_gemm_ts_half<kSplit3>(tg + kColD, tg + kColA, w3_hi, w3_lo, N3a, kH / 16, kSbo, half);
+        }
+        if (half == 1 && !(ev == 2 && kSplitD)) mma_commit(done);
+      }
+      __syncwarp();
+    };
     auto wait_mma = [&]() {
       mbar_wait_sleep(done, n & 1); ++n;
       fence_after_sync();
+    };
+    // hidden-layer epilogue of the one-tile form with the K-split hand-off: both 16-column chunks of this thread are read
+    // BEFORE the first half of the next product may overwrite the accumulator; kBias: 0 none, 1 b2, 2 per-sample first-layer bias
+    auto hidden_split = [&](int ev_next, int bias_kind, int kk) {
+      f2_t va[8], vb[8];
+      const int n0 = kColsPerThread * cg;
+      if (active_w) {
+        ldtm16p(tD + n0, va);
+        ldtm16p(tD + n0 + 16, vb);
+        tmem_ld_wait();
+      }
+#pragma unroll
+      for (int c16 = 0; c16 < 2; ++c16) {
+        if (active_w) {
+          f2_t (&v)[8] = c16 == 0 ? va : vb;
+          const int nn = n0 + 16 * c16;
+          if (bias_kind == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b = *reinterpret_cast<const float4*>(s.b2 + nn + 4 * i);
+              v[2 * i] = add2(v[2 * i], pk2(b.x, b.y));
+              v[2 * i + 1] = add2(v[2 * i + 1], pk2(b.z, b.w));
+            }
+          } else if (bias_kind == 2) {  // + (-2 log2 e) x this sample's first-layer bias (the accumulator carries the folded scale)
+            const float4* bp = reinterpret_cast<const float4*>(a.row_b1 + (size_t)kk * kH + nn);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b = __ldg(bp + i);
+              const f2_t c = pk2(-2.8853900817779268f, -2.8853900817779268f);
+              v[2 * i] = fma2(pk2(b.x, b.y), c, v[2 * i]);
+              v[2 * i + 1] = fma2(pk2(b.z, b.w), c, v[2 * i + 1]);
+            }
+          }
+          tanh16_scaled<kSplit3, kRcp / 10>(v);
+          uint32_t ph[8], pl[8];
+          pack16<kSplit3>(v, ph, pl);
+          tmem_st8(tA + nn / 2, ph);
+          if (kSplit3) tmem_st8(tA + 64 + nn / 2, pl);
+        }
+        issue_k(ev_next, c16);
+      }
     };
     for (int tile0 = r_begin; tile0 < r_end; tile0 += kRows) {
       const int nrows = (r_end - tile0 < kRows) ? r_end - tile0 : kRows;
@@ -628,6 +712,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         // ---------------- E1: tanh -> A ----------------
         wait_mma();
         mark(1);
+        if constexpr (kSplitK) {
+          active_w = active;
+          hidden_split(1, kPerRow ? 2 : 0, kk);
+          mark(2);
+        } else {
         if (active) {
 #pragma unroll
           for (int c16 = 0; c16 < kC16; ++c16) {
@@ -654,9 +743,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         }
         mark(2);
         issue(1);
+        }
         // ---------------- E2: + b2, tanh -> A ----------------
         wait_mma();
         mark(3);
+        if constexpr (kSplitK) {
+          hidden_split(2, 1, kk);
+          mark(4);
+        } else {
         if (active) {
 #pragma unroll
           for (int c16 = 0; c16 < kC16; ++c16) {
@@ -679,6 +773,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(Args a) {
         }
         mark(4);
         issue(2);
+        }
         // overlapped form: the next step's encoder output, polled for and loaded under the L3 product
         if (kTiles == 1 && a.ready && t + 1 < a.T) {
           wait_windows_ready(a, t + 1, lane);
