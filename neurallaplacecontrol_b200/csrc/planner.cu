@@ -358,7 +358,8 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
       const double beside_tiles = factor * (148 - roll_sms) * (mp.T * (pp ? 13.3 * pp_overlap_iters(n_tiles) : 9.5)) / 12.6;
       long long beside_steps = (long long)(beside_tiles / n_tiles);
       if (beside_steps > mp.T) beside_steps = mp.T;
-      if (n_tiles <= 74) beside_steps = mp.T;  // at least half the SMs for the whole step: everything beside the rollout
+      // (also below half a wave of tiles: 64 tiles, T = 50 - the first 6 steps on all SMs, then 84 SMs beside the rollout:
+      // 0.554 -> 0.538 ms per step against everything beside the rollout)
       if (beside_steps < 1) beside_steps = 1;
       split = (long long)(mp.T - beside_steps) * n_tiles;
     }
