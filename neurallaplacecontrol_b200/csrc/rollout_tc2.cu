@@ -206,7 +206,9 @@ __device__ __forceinline__ void pack16(const f2_t (&v)[8], uint32_t (&ph)[8], ui
     ph[i] = *reinterpret_cast<const uint32_t*>(&hh);
     if (kSplit3) {
       const float2 back = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
+      float r0, r1;  // the residual is exact in fp32 either way; one packed FMA instead of two subtractions
+      upk2(fma2(pk2(back.x, back.y), pk2(-1.0f, -1.0f), v[i]), r0, r1);
+      const __half2 ll = __floats2half2_rn(r0, r1);
       pl[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
   }
