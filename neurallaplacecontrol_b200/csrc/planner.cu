@@ -324,6 +324,34 @@ extern "C" int nlc_planner_buffer(nlc_planner_t p, int which, void** dev_ptr, in
 
 // stages 1-3 + the shard-local half of stage 4; `ev` (optional, 4 events) receives the stage boundaries:
 // ev[0] start | perturb | ev[1] | encoder | ev[2] | rollout + cost | ev[3] | (softmax follows)
+// Schedule of the overlapped step (see planner_rollout_impl): the rollout's form and SM count, and how many of the encoder's
+// step-major tiles run on all SMs before the fork.
+struct OverlapSchedule { bool pp; int roll_sms; long long split; };
+static OverlapSchedule overlap_schedule(const nlc_model_s* m, int K, int T) {
+  const int n_tiles = (K + 127) / 128;
+  OverlapSchedule s;
+  s.pp = rollout_overlap_is_ping_pong(m, K);
+  s.roll_sms = s.pp ? pp_overlap_grid(n_tiles) : n_tiles;
+  static const double factor = [] { const char* e = getenv("NLC_OVERLAP_FACTOR"); return e && e[0] ? atof(e) : 0.9; }();  // measurements
+  const double beside_tiles = factor * (148 - s.roll_sms) * (T * (s.pp ? 13.3 * pp_overlap_iters(n_tiles) : 9.5)) / 12.6;
+  long long beside_steps = (long long)(beside_tiles / n_tiles);
+  if (beside_steps > T) beside_steps = T;
+  // (also below half a wave of tiles: 64 tiles, T = 50 - the first 6 steps on all SMs, then 84 SMs beside the rollout:
+  // 0.554 -> 0.538 ms per step against everything beside the rollout)
+  if (beside_steps < 1) beside_steps = 1;
+  s.split = (long long)(T - beside_steps) * n_tiles;
+  return s;
+}
+// host-side arithmetic only (tests/test_abi_cpu.py): out = {ping-pong form, SMs of the rollout, tiles before the fork, tiles in all}
+extern "C" int nlc_debug_overlap_schedule(int K, int T, int nx, int S, long long* out4) {
+  NLC_REQUIRE(out4 && K >= 1 && T >= 1, NLC_ERR_ARG, "nlc_debug_overlap_schedule: bad argument");
+  nlc_model_s m{};
+  m.nx = nx; m.S = S; m.Hm = 128;
+  const OverlapSchedule s = overlap_schedule(&m, K, T);
+  out4[0] = s.pp ? 1 : 0; out4[1] = s.roll_sms; out4[2] = s.split; out4[3] = (long long)T * ((K + 127) / 128);
+  return NLC_OK;
+}
+
 static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int state_per_sample, const float* action_buffer_dev,
                                 const float* noise_in_dev, void* stream, cudaEvent_t* ev) {
   const nlc_mppi_params& mp = p->d.mppi;
@@ -350,19 +378,9 @@ static int planner_rollout_impl(nlc_planner_t p, const float* state_dev, int sta
     // per step): the encoder has the other SMs for the rollout's duration.  What those cannot encode in that time (12.6 us per
     // tile and SM: measured at config 4 / its shards; a wrong estimate only makes the rollout poll a little longer) is encoded
     // on all SMs BEFORE the fork - the windows of the first steps, the encoder walking its tiles in step-major order.
-    const bool pp = rollout_overlap_is_ping_pong(p->model, mp.K);
-    const int roll_sms = pp ? pp_overlap_grid(n_tiles) : n_tiles;
-    long long split = 0;  // first tile of the part that runs beside the rollout
-    {
-      static const double factor = [] { const char* e = getenv("NLC_OVERLAP_FACTOR"); return e && e[0] ? atof(e) : 0.9; }();  // measurements
-      const double beside_tiles = factor * (148 - roll_sms) * (mp.T * (pp ? 13.3 * pp_overlap_iters(n_tiles) : 9.5)) / 12.6;
-      long long beside_steps = (long long)(beside_tiles / n_tiles);
-      if (beside_steps > mp.T) beside_steps = mp.T;
-      // (also below half a wave of tiles: 64 tiles, T = 50 - the first 6 steps on all SMs, then 84 SMs beside the rollout:
-      // 0.554 -> 0.538 ms per step against everything beside the rollout)
-      if (beside_steps < 1) beside_steps = 1;
-      split = (long long)(mp.T - beside_steps) * n_tiles;
-    }
+    const OverlapSchedule sch = overlap_schedule(p->model, mp.K, mp.T);
+    const int roll_sms = sch.roll_sms;
+    const long long split = sch.split;  // first tile of the part that runs beside the rollout
     if (split > 0) {
       rc = encode_history_overlapped(p->model, p->hist, mp.K, mp.T, mp.B, p->p, p->d.math_mode, p->ready, 148, 0, split, s);
       if (rc != NLC_OK) return rc;

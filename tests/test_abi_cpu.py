@@ -137,3 +137,37 @@ def test_sharded_combine_over_gloo_world_size_2():
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err.decode()[-2000:]
         assert b"ok" in out
+
+
+def test_overlap_schedule_host_logic():
+    """The planner's schedule for the encoder beside the rollout (``csrc/planner.cu`` ``overlap_schedule``; host arithmetic
+    only, no device): the rollout's form and SM count and the encoder tiles that run on all SMs before the fork, at the shard
+    sizes of config 4 (strong scaling over 8 / 4 / 2 GPUs), at configs 1 and 3, and at the form crossover."""
+    from neurallaplacecontrol_b200 import _lib
+
+    lib = _lib.load()
+    fn = lib.nlc_debug_overlap_schedule
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    fn.restype = C.c_int
+
+    def sched(K, T, nx=6, S=17):
+        out = (C.c_longlong * 4)()
+        assert fn(K, T, nx, S, out) == 0
+        return tuple(out)
+
+    # 8 GPUs: 64 tiles, one tile per CTA on 64 SMs, the first 6 of 50 steps encoded before the fork
+    assert sched(8192, 50) == (0, 64, 6 * 64, 50 * 64)
+    # 4 GPUs: 128 tiles, ping-pong form on 64 SMs, 19 steps before the fork
+    pp, sms, split, total = sched(16384, 50)
+    assert (pp, sms, total) == (1, 64, 50 * 128) and split == 19 * 128
+    # 2 GPUs: 256 tiles, ping-pong form on 128 SMs, only the last steps beside the rollout on the 20 spare SMs
+    pp, sms, split, total = sched(32768, 50)
+    assert (pp, sms) == (1, 128) and 0 < total - split <= 4 * 256
+    # form crossover at 89 tiles
+    assert sched(88 * 128, 50)[:2] == (0, 88) and sched(89 * 128, 50)[:2] == (1, 45)
+    # config 1 (8 tiles): everything beside the rollout; config 3 (64 tiles, T = 30): a few steps first
+    assert sched(1000, 20, nx=3) == (0, 8, 0, 20 * 8)
+    pp, sms, split, total = sched(8192, 30, nx=5)
+    assert (pp, sms) == (0, 64) and split % 64 == 0 and 0 < split < total // 4
+    # S = 33 with nx >= 5 has no ping-pong instantiation: one tile per CTA whatever the size
+    assert sched(16384, 50, nx=6, S=33)[:2] == (0, 128)
